@@ -1,0 +1,266 @@
+"""
+TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+ctypes binding of the CPU oracle (oracle/gsr_oracle.c), a C restatement of the reference's
+Taichi kernels (3D/GSR.py, 2D/GSR.py), plus numpy restatements of the reference's small
+host-side formulas.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import this module; the product package never does.
+
+Parity status: pinned — see tests/golden/make_golden.py (golden vectors produced by running the
+reference's own kernel bodies) and tests/test_oracle_golden.py.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, '_build', 'libgsr_oracle.so')
+_lib = None
+
+
+def build(force=False):
+	"""Compile the oracle with the system gcc (`make -C oracle`)."""
+	srcs = [os.path.join(_HERE, f) for f in ('gsr_oracle.c', 'gsr3d_oracle_impl.h', 'gsr2d_oracle_impl.h', 'Makefile')]
+	if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+		subprocess.run(['make', '-C', _HERE], check=True, stdout=subprocess.DEVNULL)
+	return _SO
+
+
+def lib():
+	global _lib
+	if _lib is None:
+		build()
+		_lib = C.CDLL(_SO)
+	return _lib
+
+
+class _Grid3(C.Structure):
+	_fields_ = [('lo', C.c_float * 3), ('hi', C.c_float * 3), ('grid_scale', C.c_float), ('dims', C.c_int * 3),
+				('cnt', C.c_void_p), ('offset', C.c_void_p), ('sorted_id', C.c_void_p)]
+
+
+class _Grid2(C.Structure):
+	_fields_ = [('lo', C.c_float * 2), ('hi', C.c_float * 2), ('grid_scale', C.c_float), ('dims', C.c_int * 2),
+				('cnt', C.c_void_p), ('offset', C.c_void_p), ('sorted_id', C.c_void_p)]
+
+
+def _p(a):
+	return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+	return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side formulas of the reference
+# ---------------------------------------------------------------------------------------------
+
+def default_min_grid_scale(D, bounds, N):
+	"""3D/GSR.py:160 (2 * (V/N)^(1/3)); 2D/GSR.py:177 (3 * (A/N)^(1/2)). bounds = (x_min, x_max, y_min, ...)."""
+	ext = [bounds[2 * k + 1] - bounds[2 * k] for k in range(D)]
+	if D == 3:
+		return (ext[0] * ext[1] * ext[2] / N) ** (1. / 3.) * 2.
+	return (ext[0] * ext[1] / N) ** .5 * 3.
+
+
+def extended_bounds(D, bounds, min_grid_scale):
+	"""3D/GSR.py:162-164; 2D/GSR.py:179."""
+	out = []
+	for k in range(D):
+		out += [bounds[2 * k] - min_grid_scale, bounds[2 * k + 1] + min_grid_scale]
+	return tuple(out)
+
+
+def initial_scaling(tau, min_grid_scale):
+	"""3D/GSR.py:166; 2D/GSR.py:181."""
+	return .5 * np.log(-2. * np.log(tau)) - np.log(min_grid_scale)
+
+
+def grid_dims(D, ext_bounds, min_grid_scale):
+	"""create_grid_data: 3D/GSR.py:173 (all axes `//`), 2D/GSR.py:188 (x uses `//`, y uses `/`)."""
+	if D == 3:
+		return [int((ext_bounds[2 * k + 1] - ext_bounds[2 * k]) // min_grid_scale) + 1 for k in range(3)]
+	return [int((ext_bounds[1] - ext_bounds[0]) // min_grid_scale) + 1, int((ext_bounds[3] - ext_bounds[2]) / min_grid_scale) + 1]
+
+
+def grid_scale_of(tau, scalings, min_grid_scale, ext_bounds):
+	"""reinitialize_grid: 3D/GSR.py:247-251; 2D/GSR.py:224-228 (host double arithmetic on the f32 min)."""
+	if tau:
+		return max(np.sqrt(-2. * np.log(tau)) * np.exp(-float(np.min(scalings))), min_grid_scale)
+	D = len(ext_bounds) // 2
+	return max(ext_bounds[2 * k + 1] - ext_bounds[2 * k] for k in range(D))
+
+
+# ---------------------------------------------------------------------------------------------
+# field objects
+# ---------------------------------------------------------------------------------------------
+
+class OracleGSR:
+	"""CPU oracle of GaussianSplatting3DFast (D=3) / GaussianSplattingFast (D=2) for fixed parameters."""
+
+	def __init__(self, D, ext_bounds, positions, scalings, rotations, values, tau, min_grid_scale, dims=None, grid_scale=None, precision='f32', nthreads=1):
+		assert D in (2, 3)
+		self.D = D
+		self.sfx = '_' + precision
+		self.real = np.float32 if precision == 'f32' else np.float64
+		self.creal = C.c_float if precision == 'f32' else C.c_double
+		self.nthreads = int(nthreads)
+		self.ext_bounds = tuple(float(b) for b in ext_bounds)
+		self.positions, self.scalings, self.rotations, self.values = _f32(positions), _f32(scalings), _f32(rotations), _f32(values)
+		self.N = self.positions.shape[0]
+		self.dim = self.values.shape[1]
+		self.tau = float(tau)
+		self.min_grid_scale = float(min_grid_scale)
+		self.dims = list(dims) if dims is not None else grid_dims(D, self.ext_bounds, self.min_grid_scale)
+		self.grid_scale = float(grid_scale) if grid_scale is not None else grid_scale_of(self.tau, self.scalings, self.min_grid_scale, self.ext_bounds)
+		self.build_grid()
+
+	def build_grid(self):
+		D = self.D
+		ncell = int(np.prod(self.dims))
+		self.cnt = np.zeros(ncell, np.int32)
+		self.offset = np.zeros(ncell, np.int32)
+		self.sorted_id = np.full(max(self.N, 1), -1, np.int32)
+		lo = np.array([self.ext_bounds[2 * k] for k in range(D)], np.float32)
+		hi = np.array([self.ext_bounds[2 * k + 1] for k in range(D)], np.float32)
+		dims = np.array(self.dims, np.int32)
+		fn = lib().o3_build_grid if D == 3 else lib().o2_build_grid
+		fn.restype = C.c_int
+		self.n_in = fn(_p(self.positions), C.c_long(self.N), _p(lo), _p(hi), C.c_float(np.float32(self.grid_scale)), _p(dims),
+					   _p(self.cnt), _p(self.offset), _p(self.sorted_id))
+		G = _Grid3() if D == 3 else _Grid2()
+		for k in range(D):
+			G.lo[k], G.hi[k], G.dims[k] = lo[k], hi[k], int(dims[k])
+		G.grid_scale = np.float32(self.grid_scale)
+		G.cnt, G.offset, G.sorted_id = self.cnt.ctypes.data, self.offset.ctypes.data, self.sorted_id.ctypes.data
+		self._G = G
+		return self.cnt, self.offset, self.sorted_id
+
+	def _fn(self, name):
+		f = getattr(lib(), f'o{self.D}_{name}{self.sfx}')
+		f.restype = None
+		return f
+
+	def forward(self, x, need_grad=True, need_val=True):
+		"""loop 1 of get_losses_ti — returns (val (Q,dim), grad (Q,dim,D) | None)."""
+		x = _f32(x)
+		Q, D, dim = x.shape[0], self.D, self.dim
+		val = np.zeros((Q, dim), self.real)
+		grad = np.zeros((Q, dim, D), self.real) if need_grad else None
+		self._fn('forward')(C.byref(self._G), _p(self.positions), _p(self.scalings), _p(self.rotations), _p(self.values),
+							C.c_double(self.tau), C.c_int(dim), _p(x), C.c_long(Q), _p(val), _p(grad), C.c_int(self.nthreads))
+		return val, grad
+
+	def zero_grads(self):
+		return [np.zeros(a.shape, self.real) for a in (self.positions, self.scalings, self.rotations, self.values)]
+
+	def backward3d(self, x, val, grad, ref_val=None, weight_val=0., normals=None, weight_boundary=0., ref_grad=None, weight_grad=0.,
+				   ref_vor=None, weight_vor=0., ref_hel=None, weight_hel=0., weight_div=0., stop_gradient=None,
+				   direct=None, vor=None, div=None):
+		"""loop 2 of 3D get_losses_ti.  direct/vor/div are lists of 4 arrays (pos, scal, rot, val grads) accumulated into;
+		vor/div default to `direct` (the aliasing of 3D/GSR.py:564-579)."""
+		assert self.D == 3
+		x = _f32(x)
+		Q, dim = x.shape[0], self.dim
+		z = lambda *s: np.zeros(s, np.float32)
+		ref_val = _f32(ref_val) if weight_val != 0. else z(Q, dim)
+		normals = _f32(normals) if weight_boundary != 0. else z(Q, dim)
+		ref_grad = _f32(ref_grad) if weight_grad != 0. else z(Q, dim, 3)
+		ref_vor = _f32(ref_vor) if weight_vor != 0. else z(Q, 3)
+		ref_hel = _f32(ref_hel) if weight_hel != 0. else z(Q)
+		direct = direct if direct is not None else self.zero_grads()
+		vor = vor if vor is not None else direct
+		div = div if div is not None else direct
+		w = np.array([weight_val, weight_boundary, weight_grad, weight_vor, weight_hel, weight_div], np.float64)
+		sg = None if stop_gradient is None else np.ascontiguousarray(stop_gradient, dtype=np.int32)
+		val = np.ascontiguousarray(val, dtype=self.real)
+		grad = np.ascontiguousarray(grad, dtype=self.real)
+		self._fn('backward')(C.byref(self._G), _p(self.positions), _p(self.scalings), _p(self.rotations), _p(self.values),
+							 C.c_double(self.tau), C.c_int(dim), _p(x), C.c_long(Q), _p(val), _p(grad),
+							 _p(ref_val), _p(normals), _p(ref_grad), _p(ref_vor), _p(ref_hel), _p(w), _p(sg),
+							 *[_p(a) for a in direct], *[_p(a) for a in vor], *[_p(a) for a in div], C.c_int(self.nthreads))
+		return direct, vor, div
+
+	def backward2d_val(self, x, val, ref=None, weight=0., normals=None, normal_ref=None, weight_boundary=0., stop_gradient=None, direct=None):
+		"""loop 2 of the 2D value kernel (2D/GSR.py:282-339) with the wrapper's defaults (:341-350)."""
+		assert self.D == 2
+		x = _f32(x)
+		Q, dim = x.shape[0], self.dim
+		if ref is None:
+			ref, weight = np.zeros((Q, dim), np.float32), 0.
+		if normals is None or normal_ref is None:
+			normals, normal_ref, weight_boundary = np.zeros((Q, dim), np.float32), np.zeros(Q, np.float32), 0.
+		direct = direct if direct is not None else self.zero_grads()
+		w = np.array([weight, weight_boundary], np.float64)
+		sg = None if stop_gradient is None else np.ascontiguousarray(stop_gradient, dtype=np.int32)
+		val = np.ascontiguousarray(val, dtype=self.real)
+		self._fn('backward_val')(C.byref(self._G), _p(self.positions), _p(self.scalings), _p(self.rotations), _p(self.values),
+								 C.c_double(self.tau), C.c_int(dim), _p(x), C.c_long(Q), _p(val),
+								 _p(_f32(ref)), _p(_f32(normals)), _p(_f32(normal_ref)), _p(w), _p(sg),
+								 *[_p(a) for a in direct], C.c_int(self.nthreads))
+		return direct
+
+	def backward2d_grad(self, x, grad, ref_grad=None, weight_grad=0., ref_vor=None, weight_vor=0., weight_div=0., stop_gradient=None,
+						direct=None, vor=None, div=None):
+		"""loop 2 of get_grad_losses_ti (2D/GSR.py:396-476) with the wrapper's defaults (:485-509)."""
+		assert self.D == 2
+		x = _f32(x)
+		Q, dim = x.shape[0], self.dim
+		if ref_grad is None:
+			ref_grad, weight_grad = np.zeros((Q, dim, 2), np.float32), 0.
+		if ref_vor is None:
+			ref_vor, weight_vor = np.zeros(Q, np.float32), 0.
+		direct = direct if direct is not None else self.zero_grads()
+		vor = vor if vor is not None else direct
+		div = div if div is not None else direct
+		w = np.array([weight_grad, weight_vor, weight_div], np.float64)
+		sg = None if stop_gradient is None else np.ascontiguousarray(stop_gradient, dtype=np.int32)
+		grad = np.ascontiguousarray(grad, dtype=self.real)
+		self._fn('backward_grad')(C.byref(self._G), _p(self.positions), _p(self.scalings), _p(self.rotations), _p(self.values),
+								  C.c_double(self.tau), C.c_int(dim), _p(x), C.c_long(Q), _p(grad),
+								  _p(_f32(ref_grad)), _p(_f32(ref_vor)), _p(w), _p(sg),
+								  *[_p(a) for a in direct], *[_p(a) for a in vor], *[_p(a) for a in div], C.c_int(self.nthreads))
+		return direct, vor, div
+
+	def rk4(self, start, dt, pos_only=True):
+		"""advection_rk4 (3D/GSR.py:634-677; 2D/GSR.py:549-592)."""
+		start = _f32(start)
+		Q, D = start.shape[0], self.D
+		goal = np.zeros((Q, D), self.real)
+		deform = None if pos_only else np.zeros((Q, D, D), self.real)
+		gval = None if pos_only else np.zeros((Q, D), self.real)
+		ggrad = None if pos_only else np.zeros((Q, D, D), self.real)
+		self._fn('rk4')(C.byref(self._G), _p(self.positions), _p(self.scalings), _p(self.rotations), _p(self.values),
+						C.c_double(self.tau), _p(start), C.c_long(Q), C.c_double(dt), _p(goal), _p(deform), _p(gval), _p(ggrad), C.c_int(self.nthreads))
+		return goal if pos_only else (goal, deform, gval, ggrad)
+
+	def mark_neighbors(self, x):
+		x = _f32(x)
+		mark = np.zeros(self.N, np.int32)
+		fn = lib().o3_mark_neighbors if self.D == 3 else lib().o2_mark_neighbors
+		fn.restype = None
+		fn(C.byref(self._G), _p(self.positions), _p(x), C.c_long(x.shape[0]), _p(mark))
+		return mark
+
+	def count_candidates(self, x):
+		"""C of SURVEY 8(d): candidate visits for one evaluation of the points x (3D)."""
+		assert self.D == 3
+		x = _f32(x)
+		out = C.c_longlong(0)
+		lib().o3_count_pairs.restype = None
+		lib().o3_count_pairs(C.byref(self._G), _p(x), C.c_long(x.shape[0]), C.byref(out))
+		return out.value
+
+	def classify_pairs(self, x, rel_band=1e-4):
+		"""(n_accepted, n_in_band) per sample; band = |q - q_max| <= rel_band*q_max (SURVEY 8c tolerance policy)."""
+		x = _f32(x)
+		Q = x.shape[0]
+		n_acc, n_band = np.zeros(Q, np.int32), np.zeros(Q, np.int32)
+		fn = lib().o3_classify_pairs if self.D == 3 else lib().o2_classify_pairs
+		fn.restype = None
+		fn(C.byref(self._G), _p(self.positions), _p(self.scalings), _p(self.rotations), C.c_double(self.tau), C.c_double(rel_band),
+		   _p(x), C.c_long(Q), _p(n_acc), _p(n_band))
+		return n_acc, n_band

@@ -1,0 +1,120 @@
+"""
+Pins the CPU oracle (oracle/) against golden vectors produced by executing the reference's own
+kernel bodies and dense torch classes (tests/golden/make_golden.py).  CPU only.
+"""
+import numpy as np
+import pytest
+
+from helpers import NAMES, load_golden, oracle_from_golden, rel_err
+
+TOL = {'f64': 1e-11, 'f32': 3e-5}
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+def test_grid3d(prec):
+	g = load_golden(f'ref3d_kernels_{prec}.npz')
+	o = oracle_from_golden(g, 3, prec)
+	assert list(g['grid_size']) == o.dims
+	assert np.float32(g['grid_scale']) == np.float32(o.grid_scale)
+	np.testing.assert_array_equal(o.cnt, g['grid_cnt'])
+	np.testing.assert_array_equal(o.offset, g['grid_offset'])
+	np.testing.assert_array_equal(o.sorted_id, g['sorted_id'])
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('case', ['project', 'fit', 'boundary', 'all'])
+def test_losses3d(prec, case):
+	g = load_golden(f'ref3d_kernels_{prec}.npz')
+	o = oracle_from_golden(g, 3, prec)
+	val, grad = o.forward(g['in_x'])
+	assert rel_err(val, g[f'{case}_val']) < TOL[prec]
+	assert rel_err(grad, g[f'{case}_grad']) < TOL[prec]
+	wv, wb, wg, wo, wh, wd = g[f'{case}_weights']
+	separate = f'{case}_vor_positions' in g
+	direct, vor, div = o.zero_grads(), (o.zero_grads() if separate else None), (o.zero_grads() if separate else None)
+	o.backward3d(g['in_x'], val, grad, ref_val=g['in_ref_val'], weight_val=wv, normals=g['in_normals'], weight_boundary=wb,
+				 ref_grad=g['in_ref_grad'], weight_grad=wg, ref_vor=g['in_ref_vor'], weight_vor=wo, ref_hel=g['in_ref_hel'], weight_hel=wh,
+				 weight_div=wd, stop_gradient=g['in_stop_gradient'] if case == 'all' else None, direct=direct, vor=vor, div=div)
+	for tag, grp in (('direct', direct), ('vor', vor), ('div', div)):
+		if grp is None:
+			continue
+		for nm, a in zip(NAMES, grp):
+			ref = g[f'{case}_{tag}_{nm}']
+			if np.abs(ref).max() == 0:
+				assert np.abs(a).max() == 0
+			else:
+				assert rel_err(a, ref) < TOL[prec], (tag, nm)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('D', [2, 3])
+def test_rk4_and_neighbors(prec, D):
+	g = load_golden(f'ref{D}d_kernels_{prec}.npz')
+	o = oracle_from_golden(g, D, prec)
+	pos, deform, val, grad = o.rk4(g['in_x'], float(g['rk4_dt']), pos_only=False)
+	for a, k in ((pos, 'rk4_pos'), (deform, 'rk4_deformation'), (val, 'rk4_val'), (grad, 'rk4_grad')):
+		assert rel_err(a, g[k]) < TOL[prec], k
+	assert rel_err(o.rk4(g['in_x'], float(g['rk4_dt'])), g['rk4_pos']) < TOL[prec]
+	np.testing.assert_array_equal(o.mark_neighbors(g['in_x'][:3]), g['neighbors_mark'])
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+def test_grid2d(prec):
+	g = load_golden(f'ref2d_kernels_{prec}.npz')
+	o = oracle_from_golden(g, 2, prec)
+	assert list(g['grid_size']) == o.dims
+	np.testing.assert_array_equal(o.cnt, g['grid_cnt'])
+	np.testing.assert_array_equal(o.offset, g['grid_offset'])
+	np.testing.assert_array_equal(o.sorted_id, g['sorted_id'])
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('case', ['val', 'valb'])
+def test_losses2d_value_kernel(prec, case):
+	g = load_golden(f'ref2d_kernels_{prec}.npz')
+	o = oracle_from_golden(g, 2, prec)
+	val, _ = o.forward(g['in_x'], need_grad=False)
+	assert rel_err(val, g[f'{case}_val']) < TOL[prec]
+	w, wb = g[f'{case}_weights']
+	direct = o.backward2d_val(g['in_x'], val, ref=g['in_ref'], weight=w, normals=g['in_normals'], normal_ref=g['in_normal_ref'], weight_boundary=wb,
+							  stop_gradient=g['in_stop_gradient'] if case == 'valb' else None)
+	for nm, a in zip(NAMES, direct):
+		assert rel_err(a, g[f'{case}_direct_{nm}']) < TOL[prec], nm
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('case', ['project', 'gall'])
+def test_losses2d_gradient_kernel(prec, case):
+	g = load_golden(f'ref2d_kernels_{prec}.npz')
+	o = oracle_from_golden(g, 2, prec)
+	_, grad = o.forward(g['in_x'], need_val=False)
+	assert rel_err(grad, g[f'{case}_grad']) < TOL[prec]
+	wg, wo, wd = g[f'{case}_weights']
+	separate = f'{case}_vor_positions' in g
+	direct, vor, div = o.zero_grads(), (o.zero_grads() if separate else None), (o.zero_grads() if separate else None)
+	o.backward2d_grad(g['in_x'], grad, ref_grad=g['in_ref_grad'] if wg else None, weight_grad=wg, ref_vor=g['in_ref_vor'] if wo else None, weight_vor=wo,
+					  weight_div=wd, stop_gradient=g['in_stop_gradient'] if case == 'gall' else None, direct=direct, vor=vor, div=div)
+	for tag, grp in (('direct', direct), ('vor', vor), ('div', div)):
+		if grp is None:
+			continue
+		for nm, a in zip(NAMES, grp):
+			ref = g[f'{case}_{tag}_{nm}']
+			if np.abs(ref).max() == 0:
+				assert np.abs(a).max() == 0
+			else:
+				assert rel_err(a, ref) < TOL[prec], (tag, nm)
+
+
+@pytest.mark.parametrize('D', [2, 3])
+def test_dense_reference_class(D):
+	"""tau = 0: the Fast path equals the reference's dense torch class (3D/GSR.py:118-130, 2D/GSR.py:115-147)."""
+	from oracle.oracle import OracleGSR, extended_bounds
+	g = load_golden('ref_dense_f64.npz')
+	p = f'd{D}_in_'
+	mgs = float(g[p + 'min_grid_scale'])
+	ext = extended_bounds(D, (0., 1.) * D, mgs)
+	o = OracleGSR(D, ext, g[p + 'positions'], g[p + 'scalings'], g[p + 'rotations'], g[p + 'values'], 0., mgs, precision='f64')
+	assert o.cnt[0] == o.N	# one cell holds everything
+	val, grad = o.forward(g[p + 'x'])
+	assert rel_err(val, g[f'd{D}_val']) < 1e-11
+	assert rel_err(grad, g[f'd{D}_grad']) < 1e-11
