@@ -1,0 +1,384 @@
+"""
+Drop-in replacement of the reference's 3D/advance.py: AdvectedCovectorField, clone_velocity_field,
+advect_covector_field and project keep their names, arguments and behaviour.
+
+project() has two implementations of the same iteration:
+  * fused=True (default): the whole iteration stays on the device — sample binning, RK4 pull-back of the previous
+    field, forward, atomics-free backward, boundary pass, then ONE fused step (PCGrad projection, closed-form
+    regularisers, Adam x4, ReduceLROnPlateau x4, next grid_scale) and the hash rebuild; the host reads scalars only
+    every `check_iter` iterations for the early-stop rule.
+  * fused=False: the reference's structure (get_losses + torch autograd regularisers + torch.optim) on top of the
+    same CUDA kernels — >= 8 host syncs per iteration like the reference; kept for API fidelity and as a cross-check.
+
+Deliberate deviations from the reference, both in clone_velocity_field: `test_data` is
+generated before its first use, and the neighbour mask is converted to bool before `~` (the 2D reference does both).
+"""
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import gsr3d
+from .engine import FusedStepper
+from .gsr3d import GaussianSplatting3DFast, get_grid_points  # noqa: F401  (re-exported like the reference's star import)
+
+
+def _dev():
+	return gsr3d.device
+
+
+def curl(jacob):
+	"""omega_k from grad u[j, d, l] = d u_d / d x_l"""
+	return torch.stack((jacob[:, 2, 1] - jacob[:, 1, 2], jacob[:, 0, 2] - jacob[:, 2, 0], jacob[:, 1, 0] - jacob[:, 0, 1]), dim=-1)
+
+
+class AdvectedCovectorField:
+	"""origin_covector_field advected by velocity_field for time_step seconds (3D/advance.py:11-49)"""
+
+	def __init__(self, origin_covector_field, velocity_field, time_step, x_min, x_max, y_min, y_max, z_min, z_max, advection_scheme='rk4'):
+		self.origin_covector_field = origin_covector_field
+		self.velocity_field = velocity_field
+		self.time_step = time_step
+		self.x_min, self.x_max, self.y_min, self.y_max, self.z_min, self.z_max = x_min, x_max, y_min, y_max, z_min, z_max
+		self.advection_scheme = advection_scheme
+
+	def vorticity(self, x, need_hel=False):
+		"""vorticity (and helicity) of the advected covector field at x; x is left untouched"""
+		if self.advection_scheme != 'rk4':
+			raise NotImplementedError
+		# RK4 back-trace by -dt, curl of the pulled-back Jacobian, Dpsi^-1 and u.curl fused in one kernel
+		return self.velocity_field.advected_vorticity(x, self.time_step, need_hel=need_hel)
+
+
+def _regularisers(scalings, stop_gradient=None):
+	"""anisotropy hinge at ratio 1.5 and volume uniformity (3D/advance.py:107-115, :237-241)"""
+	aniso_ratio = 1.5
+	s = scalings if stop_gradient is None else scalings[~stop_gradient]
+	ratio = torch.exp(s.max(dim=-1).values - s.min(dim=-1).values)
+	if not ratio.shape[0]:
+		ratio = torch.ones((1,), device=_dev())
+	loss_aniso = (torch.where(ratio >= aniso_ratio, ratio, aniso_ratio) - aniso_ratio).mean()
+	if stop_gradient is None:
+		volumes = torch.exp(-scalings.sum(dim=-1))
+	else:
+		volumes = torch.where(stop_gradient, torch.exp(-scalings.detach().sum(dim=-1)), torch.exp(-scalings.sum(dim=-1)))
+	loss_vol = ((volumes / volumes.mean() - 1) ** 2).mean()
+	return loss_aniso, loss_vol
+
+
+def clone_velocity_field(res, velocity_field, x_min, x_max, y_min, y_max, z_min, z_max, data_generator, test_data_generator,
+						 reinitialize=False, batch_size=8192, max_epoch=3000, patience=500, verbose=1):
+	"""copy velocity_field into res, split over-stretched Gaussians and refit the new ones (3D/advance.py:51-165)"""
+	device = _dev()
+	with torch.no_grad():
+		res.positions, res.scalings = velocity_field.positions.clone(), velocity_field.scalings.clone()
+		res.rotations, res.values = velocity_field.rotations.clone(), velocity_field.values.clone()
+		res.N = res.positions.shape[0]
+		stop_gradient = torch.ones((res.N,), dtype=torch.bool, device=device)
+		lo = torch.tensor([res.x_min, res.y_min, res.z_min], dtype=torch.float32, device=device)
+		hi = torch.tensor([res.x_max, res.y_max, res.z_max], dtype=torch.float32, device=device)
+		while True:
+			min_scalings, split_axes = res.scalings.min(dim=-1)
+			ratio = torch.exp(res.scalings.max(dim=-1).values - min_scalings)
+			need_split = ratio >= 2.
+			if verbose:
+				print(f'Add {need_split.sum()} particles. {ratio.max()}')
+			if not need_split.any():
+				break
+			prec = res.get_variances()[need_split]
+			new_pos = torch.distributions.MultivariateNormal(res.positions[need_split], precision_matrix=(prec + prec.transpose(-1, -2)) * .5).sample((2,)).flatten(0, 1)
+			new_pos.clamp_(lo, hi)
+			new_rot = res.rotations[need_split].repeat(2, 1)
+			res.scalings[need_split, split_axes[need_split]] += np.log(2.)
+			res.scalings[need_split] -= np.log(2.) / 3.
+			new_scal = res.scalings[need_split].repeat(2, 1)
+			new_val = res.values[need_split].repeat(2, 1)
+			keep = ~need_split
+			res.positions = torch.cat([res.positions[keep], new_pos], dim=0)
+			res.rotations = torch.cat([res.rotations[keep], new_rot], dim=0)
+			res.scalings = torch.cat([res.scalings[keep], new_scal], dim=0)
+			res.values = torch.cat([res.values[keep], new_val], dim=0)
+			res.N = res.positions.shape[0]
+			stop_gradient = torch.cat([stop_gradient[keep], torch.zeros((new_pos.shape[0],), dtype=torch.bool, device=device)], dim=0)
+	res.unfreeze()
+	res.zero_grad()
+	if stop_gradient.all():
+		return res
+	stop_gradient = torch.logical_and(stop_gradient, ~res.get_all_neighbors(res.positions[~stop_gradient].detach().contiguous()).bool())
+
+	def get_losses(data, backward=True):
+		ref_val, ref_grad = velocity_field.get_losses(data)
+		if backward:
+			val, grad = res.get_losses(data, ref_val=ref_val, weight_val=1., ref_grad=ref_grad, weight_grad=1., stop_gradient=stop_gradient)
+		else:
+			val, grad = res.get_losses(data)
+		loss_val, loss_grad = F.l1_loss(val, ref_val), F.l1_loss(grad, ref_grad)
+		loss_aniso, loss_vol = _regularisers(res.scalings, stop_gradient)
+		if backward:
+			(loss_aniso + loss_vol).backward()
+		return loss_val + loss_grad + loss_aniso + loss_vol, loss_val, loss_grad, loss_aniso, loss_vol
+
+	res.positions_lr = res.rotations_lr = res.scalings_lr = res.values_lr = 1e-3
+	res.initialize_optimizers()
+	for s in res.schedulers:
+		s.factor = .9
+	test_data = test_data_generator(res)
+	_, loss_val, loss_grad, loss_aniso, loss_vol = get_losses(test_data, backward=False)
+	if verbose:
+		print(f'[clone] loss: {loss_val.item()}, loss_grad: {loss_grad.item()}, loss_aniso: {loss_aniso.item()}, loss_vol: {loss_vol.item()}')
+	st_time = time.time()
+	check_iter = 100
+	best = {'val': np.inf, 'grad': np.inf}
+	stale = {'val': 0, 'grad': 0}
+	for epoch in range(max_epoch):
+		data = data_generator(batch_size, res, ~stop_gradient)
+		loss_tot, loss_val, loss_grad, loss_aniso, loss_vol = get_losses(data)
+		res.step(loss_tot)
+		if epoch % check_iter == check_iter - 1:
+			test_data = test_data_generator(res)
+			_, loss_val, loss_grad, loss_aniso, loss_vol = get_losses(test_data, backward=False)
+			for key, cur in (('val', loss_val.item()), ('grad', loss_grad.item())):
+				if cur < best[key] * (1. - 1e-3):
+					best[key], stale[key] = cur, 0
+				else:
+					stale[key] += check_iter
+			if verbose:
+				print(f'[clone] loss: {loss_val.item()}, loss_grad: {loss_grad.item()}, loss_aniso: {loss_aniso.item()}, loss_vol: {loss_vol.item()}, time: {time.time() - st_time}')
+				st_time = time.time()
+			if stale['val'] >= patience and stale['grad'] >= patience:
+				print('[clone] Total epoch:', epoch + 1)
+				break
+	else:
+		print('[clone] Total epoch:', max_epoch, '(Reached maximum iteration number)')
+	return res
+
+
+def advect_covector_field(covector_field, velocity_field, dt, x_min=None, x_max=None, y_min=None, y_max=None, z_min=None, z_max=None, advection_scheme='rk4'):
+	"""move the Gaussians of covector_field along velocity_field (RK4, positions only), clamp, rebuild the hash (3D/advance.py:167-180)"""
+	if advection_scheme != 'rk4':
+		raise NotImplementedError
+	new_positions = velocity_field.advection_rk4(covector_field.positions.detach(), dt)
+	if x_min is not None:
+		device = _dev()
+		new_positions.clamp_(torch.tensor([x_min, y_min, z_min], dtype=torch.float32, device=device), torch.tensor([x_max, y_max, z_max], dtype=torch.float32, device=device))
+	new_positions.requires_grad_()
+	covector_field.positions = new_positions
+	covector_field.zero_grad()
+
+
+PROJECT_WEIGHTS = dict(vor=1., hel=1., div=1., aniso=10., vol=10., val_reg=0.)	# 3D/advance.py:184
+PROJECT_LRS = dict(positions=3e-4, scalings=1e-5, rotations=3e-4, values=1e-5)	# 3D/advance.py:258-261
+
+
+class FusedProjector:
+	"""One device-resident `project` phase for gaussian_velocity against the advected previous field."""
+
+	def __init__(self, gaussian_velocity, reference_field, boundary_lambda=0., patience=50, weights=None, lrs=None):
+		gv = self.gv = gaussian_velocity
+		self.ref = reference_field
+		self.w = dict(PROJECT_WEIGHTS, **(weights or {}))
+		self.lrs = dict(PROJECT_LRS, **(lrs or {}))
+		self.boundary_lambda = float(boundary_lambda)
+		e = gv._engine
+		self.stepper = FusedStepper(e, [self.lrs[k] for k in ('positions', 'scalings', 'rotations', 'values')], patience,
+									self.w['aniso'], self.w['vol'], w_valreg=self.w['val_reg'], pcgrad=True,
+									tau=gv.clamp_threshold, min_grid_scale=gv.min_grid_scale, ext_bounds=gv._ext())
+		self.stepper.init(gv.scalings)
+		self._rebuild()
+		cur = reference_field.velocity_field
+		cur._engine.ensure_packed(cur._params())
+		self._buf = {}
+
+	def _rebuild(self):
+		gv = self.gv
+		e = gv._engine
+		e.build(gv.positions.detach())
+		e._packed_key = None
+		e.ensure_packed(gv._params())
+		e._packed_key = None	# parameters are updated in place by raw pointers: never trust the version counters here
+
+	def _tmp(self, name, shape):
+		t = self._buf.get(name)
+		if t is None or tuple(t.shape) != tuple(shape):
+			t = torch.empty(shape, dtype=torch.float32, device=_dev())
+			self._buf[name] = t
+		return t
+
+	def iterate(self, data, boundary=None):
+		"""one optimiser iteration; no host synchronisation"""
+		gv, e = self.gv, self.gv._engine
+		cur = self.ref.velocity_field
+		Q = data.shape[0]
+		data = data.detach()
+		perm, scs = e.bin_samples(data, True)
+		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
+		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=perm)
+		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
+		e.forward(data, val, grad, accumulate=False, perm=perm)
+		acc, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
+									  {'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, want_losses=True)
+		lp, nblk = e.last_loss_partials
+		srcs = [(lp, nblk, [self.w['vor'] / Q, 0., self.w['div'] / Q, 0., 0., 0., 0., 0.])]
+		extra = []
+		if boundary is not None and self.boundary_lambda:
+			bdata, bnormal = boundary
+			bdata, bnormal = bdata.detach(), bnormal.detach()
+			Qb = bdata.shape[0]
+			perm_b, scs_b = e.bin_samples(bdata, True, tag='b')
+			valb = self._tmp('valb', (Qb, 3))
+			e.forward(bdata, valb, None, accumulate=False, perm=perm_b)
+			acc_b, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
+											  {'normals': bnormal}, None, tag='acc_b', want_losses=True)
+			lpb, nblkb = e.last_loss_partials
+			srcs.append((lpb, nblkb, [0., 0., 0., self.boundary_lambda / Qb, 0., 0., 0., 0.]))
+			extra.append(acc_b)
+		self.stepper.step(gv._params(), acc, mask, extra=extra, loss_srcs=srcs)
+		self._rebuild()
+
+	def evaluate(self, data):
+		"""losses of the current field on `data` without a gradient (the test pass, 3D/advance.py:226-235): device sums"""
+		gv, e = self.gv, self.gv._engine
+		data = data.detach()
+		Q = data.shape[0]
+		perm, _ = e.bin_samples(data, False)
+		ref_vor, ref_hel = self._tmp('t_ref_vor', (Q, 3)), self._tmp('t_ref_hel', (Q,))
+		self.ref.velocity_field._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=perm)
+		val, grad = self._tmp('t_val', (Q, 3)), self._tmp('t_grad', (Q, 3, 3))
+		e.forward(data, val, grad, accumulate=False, perm=perm)
+		return e.sample_losses(val, grad, {'ref_vor': ref_vor, 'ref_hel': ref_hel}, Q) / Q
+
+	def finish(self):
+		"""return control to the generic API: host grid_scale, fresh hash, version-tracked packing"""
+		gv = self.gv
+		gv.grid_scale = self.stepper.detach()
+		gv._engine._packed_key = None
+		for p in gv._params():
+			p.add_(0.)	# bump the autograd version counters: the tensors were modified through raw pointers
+
+
+def project(gaussian_velocity, reference_field, x_min, x_max, y_min, y_max, z_min, z_max, data_generator, test_data_generator,
+			boundary_generator=None, boundary_lambda=0., batch_size=8192, max_epoch=3000, patience=500, verbose=1, frame_id=None,
+			fused=True, check_iter=100, history=None):
+	"""
+	Solve one time step's projection by first-order optimisation (3D/advance.py:182-316): fit the vorticity and helicity
+	of the advected covector field while driving the divergence to zero.  Early stop: every `check_iter` iterations the
+	test losses must improve by 0.1 %, or `patience` iterations without improvement on all three end the phase.
+	Returns the number of iterations run.  (The reference's loss-curve PNG, :317-331, is not produced; pass a dict as
+	`history` to collect the same series.)
+	"""
+	gv = gaussian_velocity
+	gv.positions_lr, gv.scalings_lr, gv.rotations_lr, gv.values_lr = [PROJECT_LRS[k] for k in ('positions', 'scalings', 'rotations', 'values')]
+	gv.initialize_optimizers(patience=50)
+	for s in gv.schedulers:
+		s.factor = .9
+	if not fused:
+		return _project_unfused(gv, reference_field, data_generator, test_data_generator, boundary_generator, boundary_lambda,
+								batch_size, max_epoch, patience, verbose, check_iter, history)
+	fp = FusedProjector(gv, reference_field, boundary_lambda if boundary_generator else 0., patience=50)
+	names = ('loss_vor', 'loss_hel', 'loss_div')
+	if verbose:
+		t = fp.evaluate(test_data_generator(gv)).tolist()
+		print(f'[projection] loss_vor: {t[0]}, loss_hel: {t[1]}, loss_div: {t[2]}')
+	best = {k: np.inf for k in names}
+	stale = {k: 0 for k in names}
+	st_time = time.time()
+	epochs = max_epoch
+	for epoch in range(max_epoch):
+		data = data_generator(batch_size, gv)
+		boundary = boundary_generator(batch_size) if (boundary_lambda and boundary_generator) else None
+		fp.iterate(data, boundary)
+		if epoch % check_iter == check_iter - 1:
+			t = fp.evaluate(test_data_generator(gv)).tolist()	# the only host sync of the loop
+			cur = dict(zip(names, t[:3]))
+			if history is not None:
+				history.setdefault('test', []).append(cur)
+				history.setdefault('state', []).append(fp.stepper.scalars()[:16])
+			if verbose:
+				print(f'[projection] loss_vor: {t[0]}, loss_hel: {t[1]}, loss_div: {t[2]}, time: {time.time() - st_time}')
+				st_time = time.time()
+			for k in names:
+				if cur[k] < best[k] * (1. - 1e-3):
+					best[k], stale[k] = cur[k], 0
+				else:
+					stale[k] += check_iter
+			if all(stale[k] >= patience for k in names):
+				epochs = epoch + 1
+				if verbose:
+					print('[projection] Total epoch:', epochs)
+				break
+	else:
+		if verbose:
+			print('[projection] Total epoch:', max_epoch, '(Reached maximum iteration number)')
+	fp.finish()
+	return epochs
+
+
+def _project_unfused(gv, reference_field, data_generator, test_data_generator, boundary_generator, boundary_lambda,
+					 batch_size, max_epoch, patience, verbose, check_iter, history):
+	"""the reference's iteration structure on the CUDA kernels: explicit accumulators, host-side PCGrad, autograd regularisers, torch.optim"""
+	device = _dev()
+	W = PROJECT_WEIGHTS
+	names = ('positions', 'scalings', 'rotations', 'values')
+
+	def pcgrad_(g1, g2):
+		if (g1 * g2).sum() < 0.:
+			n1, n2 = g1 / g1.norm(), g2 / g2.norm()
+			g1 -= (g1 * n2).sum() * n2
+			g2 -= (g2 * n1).sum() * n1
+
+	def get_losses(data, backward=True):
+		ref_vor, ref_hel = reference_field.vorticity(data, need_hel=True)
+		if backward:
+			sets = {f'{tag}_{nm}_grad': torch.zeros_like(getattr(gv, nm)) for tag in ('vor', 'div') for nm in names}
+			val, grad = gv.get_losses(data, ref_vor=ref_vor, weight_vor=W['vor'], ref_hel=ref_hel, weight_hel=W['hel'], weight_div=W['div'], **sets)
+			for nm in names:
+				g1, g2 = sets[f'vor_{nm}_grad'], sets[f'div_{nm}_grad']
+				pcgrad_(g1, g2)
+				getattr(gv, nm).grad += g1 + g2
+		else:
+			grad, val = gv.gradient(data, need_val=True)
+		vor = curl(grad)
+		loss_vor = (vor - ref_vor).abs().mean(dim=-1)
+		loss_hel = ((val * vor).sum(dim=-1) - ref_hel).abs()
+		loss_div = (grad[:, 0, 0] + grad[:, 1, 1] + grad[:, 2, 2]) ** 2
+		loss_aniso, loss_vol = _regularisers(gv.scalings)
+		loss_val_reg = gv.values.abs().mean()
+		if backward:
+			(W['aniso'] * loss_aniso + W['vol'] * loss_vol + W['val_reg'] * loss_val_reg).backward()
+		boundary_constraint = torch.tensor(0., device=device)
+		if boundary_lambda and boundary_generator:
+			bdata, bnormal = boundary_generator(batch_size)
+			if backward:
+				bout, _ = gv.get_losses(bdata, normals=bnormal, weight_boundary=boundary_lambda)
+			else:
+				bout = gv(bdata)
+			boundary_constraint = (bout * bnormal).sum(dim=1).abs().mean()
+		loss_tot = (W['vor'] * loss_vor.mean() + W['div'] * loss_div.mean() + W['aniso'] * loss_aniso + W['vol'] * loss_vol
+					+ W['val_reg'] * loss_val_reg + boundary_lambda * boundary_constraint)
+		return loss_tot, loss_vor, loss_hel, loss_div
+
+	keys = ('loss_vor', 'loss_hel', 'loss_div')
+	best = {k: np.inf for k in keys}
+	stale = {k: 0 for k in keys}
+	epochs = max_epoch
+	for epoch in range(max_epoch):
+		data = data_generator(batch_size, gv)
+		loss_tot, loss_vor, loss_hel, loss_div = get_losses(data)
+		gv.step(loss_tot)
+		if history is not None:
+			history.setdefault('loss_tot', []).append(loss_tot.item())
+		if epoch % check_iter == check_iter - 1:
+			_, loss_vor, loss_hel, loss_div = get_losses(test_data_generator(gv), backward=False)
+			cur = {'loss_vor': loss_vor.mean().item(), 'loss_hel': loss_hel.mean().item(), 'loss_div': loss_div.mean().item()}
+			if verbose:
+				print(f'[projection] {cur}')
+			for k in keys:
+				if cur[k] < best[k] * (1. - 1e-3):
+					best[k], stale[k] = cur[k], 0
+				else:
+					stale[k] += check_iter
+			if all(stale[k] >= patience for k in keys):
+				epochs = epoch + 1
+				break
+	return epochs

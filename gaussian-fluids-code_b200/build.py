@@ -1,0 +1,46 @@
+"""Builds csrc/*.cu into csrc/libgsr_b200.so for sm_100a with nvcc (in-tree, so the .so travels to the GPU box)."""
+import glob
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+SO = os.path.join(CSRC, 'libgsr_b200.so')
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
+
+
+def sources():
+	return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
+
+
+def needs_build():
+	if not os.path.exists(SO):
+		return True
+	deps = sources() + glob.glob(os.path.join(CSRC, '*.cuh')) + glob.glob(os.path.join(HERE, '..', 'include', '*.h'))
+	return any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps)
+
+
+def build(force=False, verbose=False):
+	if not force and not needs_build():
+		return SO
+	nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+	objs, procs = [], []
+	os.makedirs(os.path.join(CSRC, 'build'), exist_ok=True)
+	for src in sources():
+		obj = os.path.join(CSRC, 'build', os.path.basename(src)[:-3] + '.o')
+		objs.append(obj)
+		cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+		procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+	for cmd, p in procs:
+		out, _ = p.communicate()
+		if verbose and out:
+			print(out)
+		if p.returncode != 0:
+			raise RuntimeError('nvcc failed: ' + ' '.join(cmd) + '\n' + out)
+	cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', SO] + objs
+	subprocess.run(cmd, check=True)
+	return SO
+
+
+if __name__ == '__main__':
+	print(build(force=True, verbose=False))

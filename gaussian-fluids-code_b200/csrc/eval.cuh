@@ -1,0 +1,119 @@
+// eval.cuh — device functions that evaluate the truncated-Gaussian field at one point.
+//
+// u(x) = sum_i v_i (g_i - tau)+,  grad u[d][l] = sum_i v_i[d] * (-g_i (Sigma_i^-1 (x - mu_i))[l]),
+// g_i = exp(-1/2 (x-mu_i)^T Sigma_i^-1 (x-mu_i)), accepted iff g_i >= tau   (3D/GSR.py:599-632, 2D/GSR.py:527-547)
+//
+// Candidates come from the 27 (9) cells around the point's cell.  Because the hash is cell-sorted and the
+// cell key is row-major with z (y in 2D) fastest, the stencil is 9 (3) CONTIGUOUS runs of packed records.
+// Per candidate: 3 FADD + 9 FFMA/FMUL (w = A d) + 3 (q = d.w) + 1 FMUL + compare  = 24 flop;
+// per accepted pair: 1 MUFU.EX2 (+1 FMUL) + 28 flop.
+#pragma once
+#include "common.cuh"
+
+namespace gsr {
+
+// Acceptance is decided on h = -q/2 against h_thr = min{h : expf(h) >= tau} (computed on the host with
+// libm's expf), which is equivalent to the reference's `exp(h) >= tau` for a monotone expf and keeps the
+// MUFU off the rejected 85 % of the candidates.
+struct EvalParams {
+	Grid g;
+	float h_thr;
+};
+
+template <bool NEED_GRAD>
+__device__ __forceinline__ void eval_point3(const EvalParams &P, const int32_t *__restrict__ cell_start, const float4 *__restrict__ packed,
+					    float x, float y, float z, float u[3], float G[9])
+{
+	const Grid &g = P.g;
+	u[0] = u[1] = u[2] = 0.f;
+	if (NEED_GRAD) {
+#pragma unroll
+		for (int k = 0; k < 9; k++) G[k] = 0.f;
+	}
+	const float gs = grid_gs(g);
+	const int cx = cell_coord(x, g.lo[0], gs), cy = cell_coord(y, g.lo[1], gs), cz = cell_coord(z, g.lo[2], gs);
+	const int zlo = max(cz - 1, 0), zhi = min(cz + 1, g.dims[2] - 1);
+	if (zlo > zhi) return;
+	const float tau = g.tau, h_thr = P.h_thr;
+	for (int gi = max(cx - 1, 0); gi <= min(cx + 1, g.dims[0] - 1); gi++) {
+		for (int gj = max(cy - 1, 0); gj <= min(cy + 1, g.dims[1] - 1); gj++) {
+			const int base = (gi * g.dims[1] + gj) * g.dims[2];
+			const int s = __ldg(cell_start + base + zlo), e = __ldg(cell_start + base + zhi + 1);
+			for (int t = s; t < e; t++) {
+				const float4 p0 = __ldg(packed + 3 * t), p1 = __ldg(packed + 3 * t + 1), p2 = __ldg(packed + 3 * t + 2);
+				const float dx = x - p0.x, dy = y - p0.y, dz = z - p0.z;
+				const float wx = p1.x * dx + p1.y * dy + p1.z * dz;
+				const float wy = p1.y * dx + p2.x * dy + p2.y * dz;
+				const float wz = p1.z * dx + p2.y * dy + p2.z * dz;
+				const float h = -.5f * (dx * wx + dy * wy + dz * wz);
+				if (h >= h_thr) {
+					const float gs_ = __expf(h);
+					const float gm = gs_ - tau;
+					u[0] = fmaf(p0.w, gm, u[0]);
+					u[1] = fmaf(p1.w, gm, u[1]);
+					u[2] = fmaf(p2.w, gm, u[2]);
+					if (NEED_GRAD) {
+						const float ax = -gs_ * wx, ay = -gs_ * wy, az = -gs_ * wz;
+						G[0] = fmaf(p0.w, ax, G[0]); G[1] = fmaf(p0.w, ay, G[1]); G[2] = fmaf(p0.w, az, G[2]);
+						G[3] = fmaf(p1.w, ax, G[3]); G[4] = fmaf(p1.w, ay, G[4]); G[5] = fmaf(p1.w, az, G[5]);
+						G[6] = fmaf(p2.w, ax, G[6]); G[7] = fmaf(p2.w, ay, G[7]); G[8] = fmaf(p2.w, az, G[8]);
+					}
+				}
+			}
+		}
+	}
+}
+
+template <bool NEED_GRAD>
+__device__ __forceinline__ void eval_point2(const EvalParams &P, const int32_t *__restrict__ cell_start, const float4 *__restrict__ packed,
+					    float x, float y, float u[2], float G[4])
+{
+	const Grid &g = P.g;
+	u[0] = u[1] = 0.f;
+	if (NEED_GRAD) G[0] = G[1] = G[2] = G[3] = 0.f;
+	const float gs = grid_gs(g);
+	const int cx = cell_coord(x, g.lo[0], gs), cy = cell_coord(y, g.lo[1], gs);
+	const int ylo = max(cy - 1, 0), yhi = min(cy + 1, g.dims[1] - 1);
+	if (ylo > yhi) return;
+	const float tau = g.tau, h_thr = P.h_thr;
+	for (int gi = max(cx - 1, 0); gi <= min(cx + 1, g.dims[0] - 1); gi++) {
+		const int base = gi * g.dims[1];
+		const int s = __ldg(cell_start + base + ylo), e = __ldg(cell_start + base + yhi + 1);
+		for (int t = s; t < e; t++) {
+			const float4 p0 = __ldg(packed + 2 * t), p1 = __ldg(packed + 2 * t + 1);
+			const float dx = x - p0.x, dy = y - p0.y;
+			const float wx = p1.x * dx + p1.y * dy, wy = p1.y * dx + p1.z * dy;
+			const float h = -.5f * (dx * wx + dy * wy);
+			if (h >= h_thr) {
+				const float gs_ = __expf(h);
+				const float gm = gs_ - tau;
+				u[0] = fmaf(p0.z, gm, u[0]);
+				u[1] = fmaf(p0.w, gm, u[1]);
+				if (NEED_GRAD) {
+					const float ax = -gs_ * wx, ay = -gs_ * wy;
+					G[0] = fmaf(p0.z, ax, G[0]); G[1] = fmaf(p0.z, ay, G[1]);
+					G[2] = fmaf(p0.w, ax, G[2]); G[3] = fmaf(p0.w, ay, G[3]);
+				}
+			}
+		}
+	}
+}
+
+// C = A * B (row-major 3x3)
+__device__ __forceinline__ void mm3(const float *A, const float *B, float *C)
+{
+#pragma unroll
+	for (int i = 0; i < 3; i++)
+#pragma unroll
+		for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+
+__device__ __forceinline__ void mm2(const float *A, const float *B, float *C)
+{
+	C[0] = A[0] * B[0] + A[1] * B[2]; C[1] = A[0] * B[1] + A[1] * B[3];
+	C[2] = A[2] * B[0] + A[3] * B[2]; C[3] = A[2] * B[1] + A[3] * B[3];
+}
+
+float host_h_threshold(float tau);	// defined in eval.cu
+
+}  // namespace gsr

@@ -1,0 +1,518 @@
+// grid.cu — the cell-binned spatial hash.
+//
+// Replaces reinitialize_grid_ti (reference 3D/GSR.py:205-245, 2D/GSR.py:194-222): instead of a
+// histogram + serial prefix + atomic-slot scatter, Gaussian cell keys are radix-sorted (stable, LSD,
+// 8-bit digits, hand-written) which yields the reference's grid_cnt / grid_offset bit-exactly and
+// sorted_id in canonical (ascending id inside a cell) order, deterministically.
+//
+// HBM-bound integer work: 1 key pass + P radix passes (P = ceil(log2(ncell+1)/8)) over 8 B/item,
+// then a gather that writes the 48 B (3D) / 32 B (2D) packed Gaussian record in cell order.
+#include "common.cuh"
+#include <math.h>
+
+namespace gsr {
+
+// ------------------------------------------------------------------------------------------------
+// keys
+// ------------------------------------------------------------------------------------------------
+
+// Gaussian keys: row-major cell index, or ncell for Gaussians outside the extended domain
+// (the reference silently drops those from the hash: 3D/GSR.py:212).
+template <int D>
+__global__ void gauss_keys_kernel(const float *__restrict__ pos, int n, Grid g, uint32_t *__restrict__ keys)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	bool in = true;
+	int c[3] = {0, 0, 0};
+	const float gs = grid_gs(g);
+#pragma unroll
+	for (int k = 0; k < D; k++) {
+		float p = pos[(size_t)D * i + k];
+		in = in && (g.lo[k] <= p) && (p <= g.hi[k]);
+		c[k] = cell_coord(p, g.lo[k], gs);
+	}
+	// quirk B.8 of the survey: an index == dims is possible at the upper face in the reference (unchecked
+	// write there).  We treat any out-of-grid index as "not in the hash" instead of writing out of bounds.
+#pragma unroll
+	for (int k = 0; k < D; k++) in = in && c[k] >= 0 && c[k] < g.dims[k];
+	uint32_t key = (uint32_t)g.ncell;
+	if (in) key = (uint32_t)((c[0] * g.dims[1] + c[1]) * g.dims[2] + c[2]);
+	keys[i] = key;
+}
+
+// Sample keys on the padded grid (dims+2): a sample whose cell index is -1 or dims still sees the border
+// cells through the reference's clamped stencil (3D/GSR.py:272-274), anything further out sees nothing.
+template <int D>
+__global__ void sample_keys_kernel(const float *__restrict__ x, int n, Grid g, uint32_t *__restrict__ keys)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	bool ok = true;
+	int c[3] = {-1, -1, -1};
+	const float gs = grid_gs(g);
+#pragma unroll
+	for (int k = 0; k < D; k++) {
+		c[k] = cell_coord(x[(size_t)D * i + k], g.lo[k], gs);
+		ok = ok && c[k] >= -1 && c[k] <= g.dims[k];
+	}
+	uint32_t key = (uint32_t)g.pcell;
+	if (ok) key = (uint32_t)(((c[0] + 1) * g.pdims[1] + (c[1] + 1)) * g.pdims[2] + (c[2] + 1));
+	keys[i] = key;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stable LSD radix sort of (key, index) pairs, 8 bits per pass
+// ------------------------------------------------------------------------------------------------
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;	// 2048 keys per block
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t *__restrict__ keys, int n, int shift, uint32_t *__restrict__ hist, int nblocks)
+{
+	__shared__ uint32_t h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	int base = blockIdx.x * RS_TILE;
+#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		int idx = base + i * RS_THREADS + threadIdx.x;
+		if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+	}
+	__syncthreads();
+	hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];	// digit-major
+}
+
+// exclusive scan of m entries by one block
+__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ a, int m)
+{
+	__shared__ uint32_t warp_sums[32];
+	__shared__ uint32_t carry_s;
+	const int T = 1024;
+	int chunk = (m + T - 1) / T;
+	int b = threadIdx.x * chunk, e = min(b + chunk, m);
+	uint32_t s = 0;
+	for (int i = b; i < e; i++) s += a[i];
+	// block exclusive scan of s
+	uint32_t v = s;
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+		if (lane >= o) v += t;
+	}
+	if (lane == 31) warp_sums[w] = v;
+	if (threadIdx.x == 0) carry_s = 0;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t ws = warp_sums[lane], t2 = ws;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t t = __shfl_up_sync(0xffffffffu, t2, o);
+			if (lane >= o) t2 += t;
+		}
+		warp_sums[lane] = t2 - ws;	// exclusive
+	}
+	__syncthreads();
+	uint32_t run = warp_sums[w] + (v - s);
+	for (int i = b; i < e; i++) {
+		uint32_t t = a[i];
+		a[i] = run;
+		run += t;
+	}
+}
+
+// Stable in-warp ranking of one 32-key slice: lanes with equal digits get consecutive offsets in lane
+// order; `cnt` is this warp's private digit counter row (shared memory).
+__device__ __forceinline__ uint32_t warp_rank(uint32_t digit, bool valid, uint32_t *cnt, int lane)
+{
+	uint32_t d = valid ? digit : 256u;
+	uint32_t mask = __match_any_sync(0xffffffffu, d);
+	int leader = __ffs(mask) - 1;
+	uint32_t old = 0;
+	if (valid && lane == leader) {
+		old = cnt[d];
+		cnt[d] = old + __popc(mask);
+	}
+	old = __shfl_sync(0xffffffffu, old, leader);
+	__syncwarp();
+	return old + __popc(mask & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+								uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+								int n, int shift, const uint32_t *__restrict__ hist, int nblocks)
+{
+	__shared__ uint32_t cnt[RS_WARPS][256];
+	__shared__ uint32_t gbase[256];
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+	gbase[threadIdx.x] = hist[threadIdx.x * nblocks + blockIdx.x];
+	__syncthreads();
+	int base = blockIdx.x * RS_TILE + w * (32 * RS_ITEMS);
+	uint32_t key[RS_ITEMS], off[RS_ITEMS];
+#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		int idx = base + i * 32 + lane;
+		bool valid = idx < n;
+		key[i] = valid ? keys_in[idx] : 0u;
+		off[i] = warp_rank((key[i] >> shift) & 255u, valid, cnt[w], lane);
+	}
+	__syncthreads();
+	{	// exclusive prefix over warps for digit = threadIdx.x
+		uint32_t run = 0;
+#pragma unroll
+		for (int ww = 0; ww < RS_WARPS; ww++) {
+			uint32_t t = cnt[ww][threadIdx.x];
+			cnt[ww][threadIdx.x] = run;
+			run += t;
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < RS_ITEMS; i++) {
+		int idx = base + i * 32 + lane;
+		if (idx < n) {
+			uint32_t d = (key[i] >> shift) & 255u;
+			uint32_t p = gbase[d] + cnt[w][d] + off[i];
+			keys_out[p] = key[i];
+			vals_out[p] = vals_in ? vals_in[idx] : (uint32_t)idx;
+		}
+	}
+}
+
+// Whole sort in ONE block for small inputs (n <= 16384): the latency-bound regime of the reference's own
+// problem sizes (N = 1000 .. 64000, rebuilt every optimiser iteration).
+constexpr int SB_THREADS = 1024;
+constexpr int SB_WARPS = 32;
+constexpr int SB_MAX_ITERS = 16;
+constexpr int SB_MAX_N = SB_WARPS * 32 * SB_MAX_ITERS;
+
+__global__ void __launch_bounds__(SB_THREADS) rs_single_block_kernel(const uint32_t *__restrict__ keys0, int n, int passes,
+								     uint32_t *kA, uint32_t *vA, uint32_t *kB, uint32_t *vB)
+{
+	extern __shared__ uint32_t smem[];
+	uint32_t(*cnt)[256] = reinterpret_cast<uint32_t(*)[256]>(smem);	// [SB_WARPS][256]
+	uint32_t *dbase = smem + SB_WARPS * 256;				// [256]
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	int per_warp = ((n + SB_WARPS - 1) / SB_WARPS + 31) & ~31;
+	int iters = per_warp / 32;
+	const uint32_t *kin = keys0, *vin = nullptr;
+	for (int p = 0; p < passes; p++) {
+		uint32_t *kout = (p & 1) ? kB : kA, *vout = (p & 1) ? vB : vA;
+		int shift = 8 * p;
+		for (int i = threadIdx.x; i < SB_WARPS * 256; i += SB_THREADS) (&cnt[0][0])[i] = 0;
+		__syncthreads();
+		uint32_t key[SB_MAX_ITERS], off[SB_MAX_ITERS];
+#pragma unroll
+		for (int i = 0; i < SB_MAX_ITERS; i++) {
+			if (i < iters) {
+				int idx = w * per_warp + i * 32 + lane;
+				bool valid = idx < n;
+				key[i] = valid ? kin[idx] : 0u;
+				off[i] = warp_rank((key[i] >> shift) & 255u, valid, cnt[w], lane);
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x < 256) {
+			uint32_t run = 0;
+			for (int ww = 0; ww < SB_WARPS; ww++) {
+				uint32_t t = cnt[ww][threadIdx.x];
+				cnt[ww][threadIdx.x] = run;
+				run += t;
+			}
+			dbase[threadIdx.x] = run;	// digit total
+		}
+		__syncthreads();
+		if (w == 0) {	// exclusive scan of the 256 digit totals by one warp (8 per lane)
+			uint32_t loc[8], s = 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) { loc[k] = dbase[lane * 8 + k]; s += loc[k]; }
+			uint32_t v = s;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+				if (lane >= o) v += t;
+			}
+			uint32_t run = v - s;
+#pragma unroll
+			for (int k = 0; k < 8; k++) { dbase[lane * 8 + k] = run; run += loc[k]; }
+		}
+		__syncthreads();
+#pragma unroll
+		for (int i = 0; i < SB_MAX_ITERS; i++) {
+			if (i < iters) {
+				int idx = w * per_warp + i * 32 + lane;
+				if (idx < n) {
+					uint32_t d = (key[i] >> shift) & 255u;
+					uint32_t q = dbase[d] + cnt[w][d] + off[i];
+					kout[q] = key[i];
+					vout[q] = vin ? vin[idx] : (uint32_t)idx;
+				}
+			}
+		}
+		__syncthreads();	// global writes of this block are visible to it after the barrier
+		kin = kout;
+		vin = vout;
+	}
+}
+
+static inline int key_passes(uint32_t max_key)
+{
+	int bits = 1;
+	while (bits < 32 && (max_key >> bits)) bits++;
+	return (bits + 7) / 8;
+}
+
+struct SortWs {
+	uint32_t *keys0, *kA, *kB, *vTmp, *hist;
+	int nblocks;
+};
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static size_t sort_ws_bytes(int64_t n)
+{
+	int64_t nb = (n + RS_TILE - 1) / RS_TILE;
+	if (nb < 1) nb = 1;
+	return 4 * align256(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1)) + align256(sizeof(uint32_t) * 256 * (size_t)nb);
+}
+
+static bool carve_sort_ws(void *ws, size_t ws_bytes, int64_t n, SortWs &s)
+{
+	if (ws_bytes < sort_ws_bytes(n)) return false;
+	char *p = (char *)ws;
+	size_t a = align256(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+	s.keys0 = (uint32_t *)p; p += a;
+	s.kA = (uint32_t *)p; p += a;
+	s.kB = (uint32_t *)p; p += a;
+	s.vTmp = (uint32_t *)p; p += a;
+	s.hist = (uint32_t *)p;
+	s.nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+	if (s.nblocks < 1) s.nblocks = 1;
+	return true;
+}
+
+// Sort (s.keys0[i], i) by key; sorted indices land in out_vals, sorted keys in *keys_sorted.
+static int radix_sort_index(SortWs &s, int n, uint32_t max_key, uint32_t *out_vals, const uint32_t **keys_sorted, cudaStream_t st)
+{
+	int passes = key_passes(max_key);
+	// ping-pong so that the LAST pass writes its values into out_vals
+	uint32_t *vA = (passes & 1) ? out_vals : s.vTmp;
+	uint32_t *vB = (passes & 1) ? s.vTmp : out_vals;
+	if (n <= SB_MAX_N) {
+		size_t sm = sizeof(uint32_t) * (SB_WARPS * 256 + 256);
+		rs_single_block_kernel<<<1, SB_THREADS, sm, st>>>(s.keys0, n, passes, s.kA, vA, s.kB, vB);
+		GSR_CHECK_LAUNCH();
+	} else {
+		const uint32_t *kin = s.keys0, *vin = nullptr;
+		for (int p = 0; p < passes; p++) {
+			uint32_t *kout = (p & 1) ? s.kB : s.kA, *vout = (p & 1) ? vB : vA;
+			rs_hist_kernel<<<s.nblocks, RS_THREADS, 0, st>>>(kin, n, 8 * p, s.hist, s.nblocks);
+			rs_scan_kernel<<<1, 1024, 0, st>>>(s.hist, 256 * s.nblocks);
+			rs_scatter_kernel<<<s.nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, 8 * p, s.hist, s.nblocks);
+			GSR_CHECK_LAUNCH();
+			kin = kout;
+			vin = vout;
+		}
+	}
+	*keys_sorted = ((passes - 1) & 1) ? s.kB : s.kA;
+	return 0;
+}
+
+// cell_start[c] = first sorted position whose key >= c, for c in [0, ncell].  Items whose key is ncell (not in
+// the hash) stay at the tail of the sorted order, past cell_start[ncell].
+__global__ void cell_start_kernel(const uint32_t *__restrict__ keys_sorted, int n, int ncell, int32_t *__restrict__ cell_start)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n) return;
+	int prev = (i == 0) ? -1 : min((int)keys_sorted[i - 1], ncell);
+	int cur = (i == n) ? ncell : min((int)keys_sorted[i], ncell);
+	for (int c = prev + 1; c <= cur; c++) cell_start[c] = i;
+}
+
+__global__ void ref_format_kernel(const int32_t *__restrict__ cell_start, int ncell, int32_t *__restrict__ cnt, int32_t *__restrict__ offset)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= ncell) return;
+	int s = cell_start[c];
+	if (cnt) cnt[c] = cell_start[c + 1] - s;
+	if (offset) offset[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-Gaussian precompute, gathered into cell order
+// ------------------------------------------------------------------------------------------------
+
+// exp(2 s) rounded once from double: matches a correctly-rounded expf (glibc) bit-for-bit in practice
+__device__ __forceinline__ float exp2s(float s) { return (float)exp(2.0 * (double)s); }
+
+// 3D record (3 x float4): {mu.x, mu.y, mu.z, v.x} {A00, A01, A02, v.y} {A11, A12, A22, v.z},  A = Sigma^-1.
+// R(q), S^2 and R S^2 R^T are formed in the reference's operation order (3D/GSR.py:278-289), unfused.
+__global__ void pack3d_kernel(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
+			      int n, const int32_t *__restrict__ sorted_id, float4 *__restrict__ packed)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	int i = sorted_id[t];
+	float4 r = reinterpret_cast<const float4 *>(rot)[i];
+	float len = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.x, r.x), __fmul_rn(r.y, r.y)), __fmul_rn(r.z, r.z)), __fmul_rn(r.w, r.w)));
+	float q0 = __fdiv_rn(r.x, len), q1 = __fdiv_rn(r.y, len), q2 = __fdiv_rn(r.z, len), q3 = __fdiv_rn(r.w, len);
+#define MUL __fmul_rn
+#define ADD __fadd_rn
+#define SUB __fsub_rn
+	float R[3][3];
+	R[0][0] = SUB(1.f, MUL(2.f, ADD(MUL(q2, q2), MUL(q3, q3))));
+	R[0][1] = MUL(2.f, SUB(MUL(q1, q2), MUL(q0, q3)));
+	R[0][2] = MUL(2.f, ADD(MUL(q1, q3), MUL(q0, q2)));
+	R[1][0] = MUL(2.f, ADD(MUL(q1, q2), MUL(q0, q3)));
+	R[1][1] = SUB(1.f, MUL(2.f, ADD(MUL(q1, q1), MUL(q3, q3))));
+	R[1][2] = MUL(2.f, SUB(MUL(q2, q3), MUL(q0, q1)));
+	R[2][0] = MUL(2.f, SUB(MUL(q1, q3), MUL(q0, q2)));
+	R[2][1] = MUL(2.f, ADD(MUL(q2, q3), MUL(q0, q1)));
+	R[2][2] = SUB(1.f, MUL(2.f, ADD(MUL(q1, q1), MUL(q2, q2))));
+	float S[3] = {exp2s(scal[3 * (size_t)i]), exp2s(scal[3 * (size_t)i + 1]), exp2s(scal[3 * (size_t)i + 2])};
+	float A[3][3];
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = a; b < 3; b++)
+			A[a][b] = ADD(ADD(MUL(MUL(R[a][0], S[0]), R[b][0]), MUL(MUL(R[a][1], S[1]), R[b][1])), MUL(MUL(R[a][2], S[2]), R[b][2]));
+#undef MUL
+#undef ADD
+#undef SUB
+	const float *p = pos + 3 * (size_t)i, *v = vals + 3 * (size_t)i;
+	packed[3 * (size_t)t + 0] = make_float4(p[0], p[1], p[2], v[0]);
+	packed[3 * (size_t)t + 1] = make_float4(A[0][0], A[0][1], A[0][2], v[1]);
+	packed[3 * (size_t)t + 2] = make_float4(A[1][1], A[1][2], A[2][2], v[2]);
+}
+
+// 2D record (2 x float4): {mu.x, mu.y, v.x, v.y} {A00, A01, A11, 0},  A = R(theta) diag(e^{2s}) R^T (2D/GSR.py:275-277)
+__global__ void pack2d_kernel(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
+			      int n, const int32_t *__restrict__ sorted_id, float4 *__restrict__ packed)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	int i = sorted_id[t];
+	double th = (double)rot[i];
+	float c = (float)cos(th), s = (float)sin(th);
+	float S0 = exp2s(scal[2 * (size_t)i]), S1 = exp2s(scal[2 * (size_t)i + 1]);
+	float R[2][2] = {{c, -s}, {s, c}};
+	float A00 = __fadd_rn(__fmul_rn(__fmul_rn(R[0][0], S0), R[0][0]), __fmul_rn(__fmul_rn(R[0][1], S1), R[0][1]));
+	float A01 = __fadd_rn(__fmul_rn(__fmul_rn(R[0][0], S0), R[1][0]), __fmul_rn(__fmul_rn(R[0][1], S1), R[1][1]));
+	float A11 = __fadd_rn(__fmul_rn(__fmul_rn(R[1][0], S0), R[1][0]), __fmul_rn(__fmul_rn(R[1][1], S1), R[1][1]));
+	packed[2 * (size_t)t + 0] = make_float4(pos[2 * (size_t)i], pos[2 * (size_t)i + 1], vals[2 * (size_t)i], vals[2 * (size_t)i + 1]);
+	packed[2 * (size_t)t + 1] = make_float4(A00, A01, A11, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// min over scalings (reinitialize_grid's `self.scalings.min()`)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_float(float *addr, float v)
+{
+	if (v >= 0.f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+	else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+__global__ void min_init_kernel(float *out) { *out = __int_as_float(0x7f800000); }
+
+__global__ void min_kernel(const float *__restrict__ a, int64_t n, float *out)
+{
+	float m = __int_as_float(0x7f800000);
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fminf(m, a[i]);
+#pragma unroll
+	for (int o = 16; o; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0) atomic_min_float(out, m);
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" size_t gsr_build_grid_ws_bytes(const gsr_grid_desc *, int64_t N) { return sort_ws_bytes(N); }
+extern "C" size_t gsr_bin_samples_ws_bytes(const gsr_grid_desc *, int64_t Q) { return sort_ws_bytes(Q); }
+
+extern "C" int64_t gsr_padded_cells(const gsr_grid_desc *d)
+{
+	Grid g;
+	if (!make_grid(d, g)) return GSR_EINVAL;
+	return g.pcell;
+}
+
+extern "C" int gsr_build_grid(const gsr_grid_desc *d, const float *positions, int64_t N,
+			      int32_t *cell_start, int32_t *sorted_id, int32_t *grid_cnt, int32_t *grid_offset,
+			      void *ws, size_t ws_bytes, void *stream)
+{
+	Grid g;
+	if (!make_grid(d, g) || N < 0 || N >= ((int64_t)1 << 30) || !cell_start || !sorted_id) return GSR_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	SortWs s;
+	if (!carve_sort_ws(ws, ws_bytes, N, s)) return GSR_EWS;
+	int n = (int)N;
+	const uint32_t *ks = s.keys0;
+	if (n > 0) {
+		if (g.D == 3) gauss_keys_kernel<3><<<(n + 255) / 256, 256, 0, st>>>(positions, n, g, s.keys0);
+		else gauss_keys_kernel<2><<<(n + 255) / 256, 256, 0, st>>>(positions, n, g, s.keys0);
+		GSR_CHECK_LAUNCH();
+		int rc = radix_sort_index(s, n, (uint32_t)g.ncell, (uint32_t *)sorted_id, &ks, st);
+		if (rc) return rc;
+	}
+	cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.ncell, cell_start);
+	if (grid_cnt || grid_offset) ref_format_kernel<<<(g.ncell + 255) / 256, 256, 0, st>>>(cell_start, g.ncell, grid_cnt, grid_offset);
+	GSR_CHECK_LAUNCH();
+	return GSR_OK;
+}
+
+extern "C" int gsr_bin_samples(const gsr_grid_desc *d, const float *x, int64_t Q, int32_t *perm, int32_t *sample_cell_start,
+			       void *ws, size_t ws_bytes, void *stream)
+{
+	Grid g;
+	if (!make_grid(d, g) || Q < 0 || Q >= ((int64_t)1 << 30) || !perm) return GSR_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	SortWs s;
+	if (!carve_sort_ws(ws, ws_bytes, Q, s)) return GSR_EWS;
+	int n = (int)Q;
+	const uint32_t *ks = s.keys0;
+	if (n > 0) {
+		if (g.D == 3) sample_keys_kernel<3><<<(n + 255) / 256, 256, 0, st>>>(x, n, g, s.keys0);
+		else sample_keys_kernel<2><<<(n + 255) / 256, 256, 0, st>>>(x, n, g, s.keys0);
+		GSR_CHECK_LAUNCH();
+		int rc = radix_sort_index(s, n, (uint32_t)g.pcell, (uint32_t *)perm, &ks, st);
+		if (rc) return rc;
+	}
+	if (sample_cell_start) {
+		cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.pcell, sample_cell_start);
+		GSR_CHECK_LAUNCH();
+	}
+	return GSR_OK;
+}
+
+extern "C" int gsr_pack_gaussians(const gsr_grid_desc *d, const float *positions, const float *scalings, const float *rotations,
+				  const float *values, int64_t N, const int32_t *, const int32_t *sorted_id, float *packed, void *stream)
+{
+	Grid g;
+	if (!make_grid(d, g) || N < 0 || !packed || !sorted_id) return GSR_EINVAL;
+	if (N == 0) return GSR_OK;
+	cudaStream_t st = (cudaStream_t)stream;
+	int n = (int)N;
+	if (g.D == 3) pack3d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed);
+	else pack2d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed);
+	GSR_CHECK_LAUNCH();
+	return GSR_OK;
+}
+
+extern "C" int gsr_min_scaling(const float *scalings, int64_t count, float *out_min, void *stream)
+{
+	if (!out_min || count < 0) return GSR_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	min_init_kernel<<<1, 1, 0, st>>>(out_min);
+	if (count > 0) {
+		int blocks = (int)((count + 1023) / 1024);
+		if (blocks > kSMs * 8) blocks = kSMs * 8;
+		min_kernel<<<blocks, 256, 0, st>>>(scalings, count, out_min);
+	}
+	GSR_CHECK_LAUNCH();
+	return GSR_OK;
+}

@@ -1,0 +1,387 @@
+// step.cu — the per-iteration optimiser step of project(), fused and device-resident.
+//
+// Reference (3D/advance.py:183-287 + 3D/GSR.py:148-152, :704-716; 2D/advance.py:187-259): PCGrad-style mutual
+// projection of the vorticity and divergence gradients per parameter group (4 x 3 global dot products, each a
+// host sync), torch-autograd regularisers, 4 x torch.optim.Adam, 4 x ReduceLROnPlateau (float(loss) sync),
+// scalings.min().item() (sync) — about 200 small launches and >= 8 host syncs per iteration.
+// Here: 4 launches, no sync.  HBM-bound: per Gaussian reads params 52 B + Adam m,v 104 B + accumulators
+// 48 B/set (twice: kernels A and B), writes params 52 B + m,v 104 B.
+#include "chain.cuh"
+#include <math.h>
+
+namespace gsr {
+
+template <int D> struct Dim {
+	static constexpr int P = (D == 3) ? 13 : 7;	// parameter floats per Gaussian
+	static constexpr int AF = (D == 3) ? 12 : 7;	// accumulator floats per set
+	static constexpr int NR = (D == 3) ? 4 : 1;	// rotation parameters
+};
+
+// parameter-space gradient (positions D, scalings D, rotations NR, values D) of one compact accumulator record
+template <int D>
+__device__ __forceinline__ void param_grad(const float *a, const float *sc, const float *rot, float *gp, float *gs, float *gr, float *gv)
+{
+	if (D == 3) {
+		chain3d(a + 6, sc, rot, gs, gr);
+#pragma unroll
+		for (int k = 0; k < 3; k++) { gv[k] = a[k]; gp[k] = a[3 + k]; }
+	} else {
+		chain2d(a + 4, sc, rot[0], gs, gr);
+#pragma unroll
+		for (int k = 0; k < 2; k++) { gv[k] = a[k]; gp[k] = a[2 + k]; }
+	}
+}
+
+// partial-sum slots of kernel A
+enum { S_DOT = 0 /* [g]: <g_vor, g_div> */, S_N1 = 4 /* |g_vor|^2 */, S_N2 = 8 /* |g_div|^2 */, S_V = 12, S_V2 = 13, S_ANISO = 14, S_ABSV = 15, S_DPOS = 16, S_COUNT = 20 };
+
+constexpr int ST_THREADS = 128;
+
+template <int D>
+__global__ void __launch_bounds__(ST_THREADS) stepA_kernel(int N, const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot,
+							   const float *__restrict__ vals, const float *__restrict__ acc, int sets_mask,
+							   const float *__restrict__ pos_org, float aniso_ratio, float *__restrict__ partials)
+{
+	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR;
+	__shared__ float sm[ST_THREADS / 32][S_COUNT];
+	float S[S_COUNT];
+#pragma unroll
+	for (int k = 0; k < S_COUNT; k++) S[k] = 0.f;
+	int i = blockIdx.x * ST_THREADS + threadIdx.x;
+	if (i < N) {
+		float sc[D], r[NR];
+#pragma unroll
+		for (int k = 0; k < D; k++) sc[k] = scal[(size_t)D * i + k];
+#pragma unroll
+		for (int k = 0; k < NR; k++) r[k] = rot[(size_t)NR * i + k];
+		if ((sets_mask & 6) == 6) {
+			float p1[D], s1[D], r1[NR], v1[D], p2[D], s2[D], r2[NR], v2[D];
+			param_grad<D>(acc + ((size_t)1 * N + i) * AF, sc, r, p1, s1, r1, v1);
+			param_grad<D>(acc + ((size_t)2 * N + i) * AF, sc, r, p2, s2, r2, v2);
+#pragma unroll
+			for (int k = 0; k < D; k++) {
+				S[S_DOT + 0] += p1[k] * p2[k]; S[S_N1 + 0] += p1[k] * p1[k]; S[S_N2 + 0] += p2[k] * p2[k];
+				S[S_DOT + 1] += s1[k] * s2[k]; S[S_N1 + 1] += s1[k] * s1[k]; S[S_N2 + 1] += s2[k] * s2[k];
+				S[S_DOT + 3] += v1[k] * v2[k]; S[S_N1 + 3] += v1[k] * v1[k]; S[S_N2 + 3] += v2[k] * v2[k];
+			}
+#pragma unroll
+			for (int k = 0; k < NR; k++) { S[S_DOT + 2] += r1[k] * r2[k]; S[S_N1 + 2] += r1[k] * r1[k]; S[S_N2 + 2] += r2[k] * r2[k]; }
+		}
+		// regulariser moments (3D/advance.py:237-242): V = exp(-sum s), rho = exp(max s - min s)
+		float ssum = 0.f, smin = sc[0], smax = sc[0];
+#pragma unroll
+		for (int k = 0; k < D; k++) { ssum += sc[k]; smin = fminf(smin, sc[k]); smax = fmaxf(smax, sc[k]); }
+		const float V = expf(-ssum);
+		S[S_V] = V;
+		S[S_V2] = V * V;
+		const float rho = expf(smax - smin);
+		S[S_ANISO] = (rho >= aniso_ratio ? rho : aniso_ratio) - aniso_ratio;
+#pragma unroll
+		for (int k = 0; k < D; k++) S[S_ABSV] += fabsf(vals[(size_t)D * i + k]);
+		if (pos_org) {
+#pragma unroll
+			for (int k = 0; k < D; k++) {
+				const float dlt = pos[(size_t)D * i + k] - pos_org[(size_t)D * i + k];
+				S[S_DPOS] += dlt * dlt;
+			}
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < S_COUNT; k++) {
+#pragma unroll
+		for (int o = 16; o; o >>= 1) S[k] += __shfl_xor_sync(0xffffffffu, S[k], o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+		for (int k = 0; k < S_COUNT; k++) sm[threadIdx.x >> 5][k] = S[k];
+	}
+	__syncthreads();
+	if (threadIdx.x < S_COUNT) {
+		float s = 0.f;
+#pragma unroll
+		for (int w = 0; w < ST_THREADS / 32; w++) s += sm[w][threadIdx.x];
+		partials[(size_t)blockIdx.x * S_COUNT + threadIdx.x] = s;
+	}
+}
+
+// coefficient block written by kernel R for kernel B (inside the state scalars)
+enum { C_A1 = 24 /* [4] */, C_A2 = 28 /* [4] */, C_STEP = 32 /* [4] lr / bias_correction1 */, C_BC2 = 36 /* 1/sqrt(bias_correction2) */,
+       C_MEANV = 37, C_MEANR2 = 38, C_LRUSED = 40 /* [4] */ };
+
+struct LossSrcs {
+	const float *partials[3];
+	int nblocks[3];
+	float w[3][8];
+	int n;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) stepR_kernel(gsr_step_cfg cfg, int N, int nblkA, const float *__restrict__ partials, LossSrcs ls, float *__restrict__ st)
+{
+	__shared__ double red[S_COUNT + 8][8];
+	// deterministic reduction: 8 strided lanes per slot, then a fixed-order sum
+	const int slot = threadIdx.x >> 3, lane = threadIdx.x & 7;
+	if (slot < S_COUNT) {
+		double s = 0.;
+		for (int b = lane; b < nblkA; b += 8) s += (double)partials[(size_t)b * S_COUNT + slot];
+		red[slot][lane] = s;
+	} else if (slot < S_COUNT + 8) {
+		const int k = slot - S_COUNT;
+		double s = 0.;
+		for (int src = 0; src < ls.n; src++) {
+			double t = 0.;
+			for (int b = lane; b < ls.nblocks[src]; b += 8) t += (double)ls.partials[src][(size_t)b * 8 + k];
+			s += (double)ls.w[src][k] * t;
+		}
+		red[slot][lane] = s;
+	}
+	__syncthreads();
+	if (threadIdx.x != 0) return;
+	double T[S_COUNT + 8];
+	for (int k = 0; k < S_COUNT + 8; k++) {
+		double s = 0.;
+		for (int l = 0; l < 8; l++) s += red[k][l];
+		T[k] = s;
+	}
+	// PCGrad coefficients (3D/advance.py:202-225): g1 -= <g1,n2> n2, g2 -= <g2,n1> n1 when <g1,g2> < 0
+	for (int g = 0; g < 4; g++) {
+		float a1 = 1.f, a2 = 1.f;
+		if (cfg.pcgrad && T[S_DOT + g] < 0.) {
+			a1 = (float)(1. - T[S_DOT + g] / T[S_N1 + g]);
+			a2 = (float)(1. - T[S_DOT + g] / T[S_N2 + g]);
+		}
+		st[C_A1 + g] = a1;
+		st[C_A2 + g] = a2;
+	}
+	const double n = (double)N;
+	const double meanV = T[S_V] / n, meanR2 = T[S_V2] / n / (meanV * meanV);
+	st[C_MEANV] = (float)meanV;
+	st[C_MEANR2] = (float)meanR2;
+	const double L_aniso = T[S_ANISO] / n, L_vol = meanR2 - 1., L_valreg = T[S_ABSV] / (n * D), L_dpos = T[S_DPOS] / (n * D);
+	double loss_src = 0.;
+	for (int k = 0; k < 8; k++) loss_src += T[S_COUNT + k];
+	const double loss_tot = loss_src + cfg.w_aniso * L_aniso + cfg.w_vol * L_vol + cfg.w_valreg * L_valreg + cfg.w_dpos * L_dpos;
+	st[GSR_ST_LOSS_TOT] = (float)loss_tot;
+	st[GSR_ST_L_ANISO] = (float)L_aniso;
+	st[GSR_ST_L_VOL] = (float)L_vol;
+	st[GSR_ST_L_VALREG] = (float)L_valreg;
+	st[GSR_ST_L_DPOS] = (float)L_dpos;
+	// Adam bias corrections for step t (torch: step_size = lr / (1 - beta1^t), denom = sqrt(v)/sqrt(1 - beta2^t) + eps)
+	const double t = (double)st[GSR_ST_T] + 1.;
+	st[GSR_ST_T] = (float)t;
+	const double bc1 = 1. - pow((double)cfg.beta1, t), bc2 = 1. - pow((double)cfg.beta2, t);
+	for (int g = 0; g < 4; g++) {
+		st[C_LRUSED + g] = st[GSR_ST_LR + g];
+		st[C_STEP + g] = (float)((double)st[GSR_ST_LR + g] / bc1);
+	}
+	st[C_BC2] = (float)(1. / sqrt(bc2));
+	// ReduceLROnPlateau.step(loss_tot): mode min, rel threshold, cooldown 0
+	const float cur = (float)loss_tot;
+	float best = st[GSR_ST_BEST], bad = st[GSR_ST_BAD];
+	if (cur < best * (1.f - cfg.sched_threshold)) { best = cur; bad = 0.f; } else bad += 1.f;
+	if (bad > (float)cfg.sched_patience) {
+		for (int g = 0; g < 4; g++) {
+			const float old_lr = st[GSR_ST_LR + g], new_lr = fmaxf(old_lr * cfg.sched_factor, cfg.sched_min_lr);
+			if (old_lr - new_lr > cfg.sched_eps) st[GSR_ST_LR + g] = new_lr;
+		}
+		bad = 0.f;
+	}
+	st[GSR_ST_BEST] = best;
+	st[GSR_ST_BAD] = bad;
+}
+
+__device__ __forceinline__ void atomic_min_f(float *addr, float v)
+{
+	if (v >= 0.f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+	else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+template <int D>
+__global__ void __launch_bounds__(ST_THREADS) stepB_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__restrict__ scal, float *__restrict__ rot, float *__restrict__ vals,
+							   const float *__restrict__ acc, int sets_mask, const float *__restrict__ ex0, const float *__restrict__ ex1,
+							   const float *__restrict__ pos_org, float *__restrict__ st)
+{
+	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR, P = Dim<D>::P;
+	int i = blockIdx.x * ST_THREADS + threadIdx.x;
+	float smin = __int_as_float(0x7f800000);
+	if (i < N) {
+		float sc[D], r[NR], p[D], v[D];
+#pragma unroll
+		for (int k = 0; k < D; k++) { sc[k] = scal[(size_t)D * i + k]; p[k] = pos[(size_t)D * i + k]; v[k] = vals[(size_t)D * i + k]; }
+#pragma unroll
+		for (int k = 0; k < NR; k++) r[k] = rot[(size_t)NR * i + k];
+		float g[P];	// total gradient: [pos D][scal D][rot NR][val D]
+#pragma unroll
+		for (int k = 0; k < P; k++) g[k] = 0.f;
+		float gp[D], gs[D], gr[NR], gv[D];
+		auto add = [&](const float *a, float cp, float cs, float cr, float cv) {
+			param_grad<D>(a, sc, r, gp, gs, gr, gv);
+#pragma unroll
+			for (int k = 0; k < D; k++) { g[k] += cp * gp[k]; g[D + k] += cs * gs[k]; g[2 * D + NR + k] += cv * gv[k]; }
+#pragma unroll
+			for (int k = 0; k < NR; k++) g[2 * D + k] += cr * gr[k];
+		};
+		if (sets_mask & 2) add(acc + ((size_t)1 * N + i) * AF, st[C_A1 + 0], st[C_A1 + 1], st[C_A1 + 2], st[C_A1 + 3]);
+		if (sets_mask & 4) add(acc + ((size_t)2 * N + i) * AF, st[C_A2 + 0], st[C_A2 + 1], st[C_A2 + 2], st[C_A2 + 3]);
+		if (sets_mask & 1) add(acc + (size_t)i * AF, 1.f, 1.f, 1.f, 1.f);
+		if (ex0) add(ex0 + (size_t)i * AF, 1.f, 1.f, 1.f, 1.f);
+		if (ex1) add(ex1 + (size_t)i * AF, 1.f, 1.f, 1.f, 1.f);
+		// closed-form regulariser gradients (autograd in the reference, 3D/advance.py:237-244)
+		{
+			float ssum = 0.f;
+			int kmin = 0, kmax = 0;
+#pragma unroll
+			for (int k = 0; k < D; k++) {
+				ssum += sc[k];
+				if (sc[k] < sc[kmin]) kmin = k;	// first index on ties, like torch.min / torch.max
+				if (sc[k] > sc[kmax]) kmax = k;
+			}
+			const float rho = expf(sc[kmax] - sc[kmin]);
+			if (rho >= cfg.aniso_ratio && kmin != kmax) {
+				const float c = cfg.w_aniso * rho / (float)N;
+#pragma unroll
+				for (int k = 0; k < D; k++) g[D + k] += (k == kmax ? c : 0.f) - (k == kmin ? c : 0.f);
+			}
+			const float rV = expf(-ssum) / st[C_MEANV];
+			const float cv = -cfg.w_vol * 2.f / (float)N * rV * (rV - st[C_MEANR2]);
+#pragma unroll
+			for (int k = 0; k < D; k++) g[D + k] += cv;
+			if (cfg.w_valreg != 0.f) {
+				const float c = cfg.w_valreg / (float)(N * D);
+#pragma unroll
+				for (int k = 0; k < D; k++) g[2 * D + NR + k] += c * (float)((v[k] > 0.f) - (v[k] < 0.f));
+			}
+			if (pos_org && cfg.w_dpos != 0.f) {
+				const float c = cfg.w_dpos * 2.f / (float)(N * D);
+#pragma unroll
+				for (int k = 0; k < D; k++) g[k] += c * (p[k] - pos_org[(size_t)D * i + k]);
+			}
+		}
+		// Adam (torch.optim.Adam defaults; lr of the group as it was BEFORE this step's scheduler update)
+		float *m = st + GSR_STATE_SCALARS + (size_t)i * P, *vv = st + GSR_STATE_SCALARS + (size_t)N * P + (size_t)i * P;
+		float prm[P];
+#pragma unroll
+		for (int k = 0; k < D; k++) { prm[k] = p[k]; prm[D + k] = sc[k]; prm[2 * D + NR + k] = v[k]; }
+#pragma unroll
+		for (int k = 0; k < NR; k++) prm[2 * D + k] = r[k];
+		const float bc2 = st[C_BC2];
+#pragma unroll
+		for (int k = 0; k < P; k++) {
+			const int grp = k < D ? 0 : (k < 2 * D ? 1 : (k < 2 * D + NR ? 2 : 3));
+			const float mk = m[k] + (g[k] - m[k]) * (1.f - cfg.beta1);		// exp_avg.lerp_(grad, 1 - beta1)
+			const float vk = vv[k] * cfg.beta2 + (1.f - cfg.beta2) * g[k] * g[k];	// exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+			m[k] = mk;
+			vv[k] = vk;
+			const float denom = sqrtf(vk) * bc2 + cfg.eps;
+			prm[k] -= st[C_STEP + grp] * (mk / denom);
+		}
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			pos[(size_t)D * i + k] = prm[k];
+			scal[(size_t)D * i + k] = prm[D + k];
+			vals[(size_t)D * i + k] = prm[2 * D + NR + k];
+			smin = fminf(smin, prm[D + k]);
+		}
+#pragma unroll
+		for (int k = 0; k < NR; k++) rot[(size_t)NR * i + k] = prm[2 * D + k];
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+	if ((threadIdx.x & 31) == 0) atomic_min_f(st + GSR_ST_MIN_S, smin);
+}
+
+// next grid_scale (3D/GSR.py:248-251), formed in double like the reference's host code, then rounded to f32;
+// re-arms the min accumulator for the next iteration.
+__global__ void stepS_kernel(gsr_step_cfg cfg, float *st, float *min_out)
+{
+	const float min_s = st[GSR_ST_MIN_S];
+	double gs = cfg.grid_scale_tau0;
+	if (cfg.grid_coef > 0.) gs = fmax(cfg.grid_coef * exp(-(double)min_s), cfg.min_grid_scale);
+	st[GSR_ST_GRID_SCALE] = (float)gs;
+	if (min_out) *min_out = min_s;
+	st[GSR_ST_MIN_S] = __int_as_float(0x7f800000);
+}
+
+__global__ void init_state_kernel(float *st, size_t n_moments, gsr_step_cfg cfg)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_moments) st[GSR_STATE_SCALARS + i] = 0.f;
+	if (i < GSR_STATE_SCALARS) {
+		float v = 0.f;
+		if (i == GSR_ST_BEST || i == GSR_ST_MIN_S) v = __int_as_float(0x7f800000);
+		if (i >= GSR_ST_LR && i < GSR_ST_LR + 4) v = cfg.lr[i - GSR_ST_LR];
+		st[i] = v;
+	}
+}
+
+__global__ void min_into_kernel(const float *__restrict__ a, size_t n, float *out)
+{
+	float m = __int_as_float(0x7f800000);
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fminf(m, a[i]);
+#pragma unroll
+	for (int o = 16; o; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0) atomic_min_f(out, m);
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" size_t gsr_step_state_floats(int D, int64_t N) { return GSR_STATE_SCALARS + 2 * (size_t)(D == 3 ? 13 : 7) * (size_t)N; }
+
+extern "C" size_t gsr_step_ws_bytes(int, int64_t N)
+{
+	size_t nblk = (size_t)((N + ST_THREADS - 1) / ST_THREADS);
+	return sizeof(float) * S_COUNT * (nblk ? nblk : 1);
+}
+
+extern "C" int gsr_step_init(const gsr_step_cfg *cfg, int64_t N, const float *scalings, float *state, void *stream)
+{
+	if (!cfg || (cfg->D != 2 && cfg->D != 3) || N < 0 || !state) return GSR_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	size_t nm = 2 * (size_t)(cfg->D == 3 ? 13 : 7) * (size_t)N;
+	size_t total = nm > GSR_STATE_SCALARS ? nm : GSR_STATE_SCALARS;
+	init_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(state, nm, *cfg);
+	if (scalings && N > 0) {
+		size_t n = (size_t)N * cfg->D;
+		int blocks = (int)((n + 1023) / 1024);
+		if (blocks > kSMs * 8) blocks = kSMs * 8;
+		min_into_kernel<<<blocks, 256, 0, st>>>(scalings, n, state + GSR_ST_MIN_S);
+		stepS_kernel<<<1, 1, 0, st>>>(*cfg, state, nullptr);
+	}
+	GSR_CHECK_LAUNCH();
+	return GSR_OK;
+}
+
+extern "C" int gsr_step(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalings, float *rotations, float *values,
+			const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
+			const float *positions_org, float *state, void *ws, size_t ws_bytes, void *stream)
+{
+	if (!cfg || (cfg->D != 2 && cfg->D != 3) || N <= 0 || N >= ((int64_t)1 << 30) || !state || !positions || !scalings || !rotations || !values) return GSR_EINVAL;
+	if ((sets_mask & 7) && !acc) return GSR_EINVAL;
+	if (n_loss_src < 0 || n_loss_src > 3) return GSR_EINVAL;
+	if (ws_bytes < gsr_step_ws_bytes(cfg->D, N)) return GSR_EWS;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int n = (int)N, nblk = (n + ST_THREADS - 1) / ST_THREADS;
+	float *partials = (float *)ws;
+	LossSrcs ls;
+	ls.n = n_loss_src;
+	for (int s = 0; s < 3; s++) {
+		ls.partials[s] = (s < n_loss_src) ? loss_src[s].partials : nullptr;
+		ls.nblocks[s] = (s < n_loss_src) ? loss_src[s].nblocks : 0;
+		for (int k = 0; k < 8; k++) ls.w[s][k] = (s < n_loss_src) ? loss_src[s].w[k] : 0.f;
+	}
+	const float *ex0 = extra_direct ? extra_direct[0] : nullptr, *ex1 = extra_direct ? extra_direct[1] : nullptr;
+	if (cfg->D == 3) {
+		stepA_kernel<3><<<nblk, ST_THREADS, 0, st>>>(n, positions, scalings, rotations, values, acc, sets_mask, positions_org, cfg->aniso_ratio, partials);
+		stepR_kernel<3><<<1, 256, 0, st>>>(*cfg, n, nblk, partials, ls, state);
+		stepB_kernel<3><<<nblk, ST_THREADS, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, state);
+	} else {
+		stepA_kernel<2><<<nblk, ST_THREADS, 0, st>>>(n, positions, scalings, rotations, values, acc, sets_mask, positions_org, cfg->aniso_ratio, partials);
+		stepR_kernel<2><<<1, 256, 0, st>>>(*cfg, n, nblk, partials, ls, state);
+		stepB_kernel<2><<<nblk, ST_THREADS, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, state);
+	}
+	stepS_kernel<<<1, 1, 0, st>>>(*cfg, state, nullptr);
+	GSR_CHECK_LAUNCH();
+	return GSR_OK;
+}

@@ -1,0 +1,284 @@
+"""
+Device-side plumbing shared by the 2D and 3D drop-in classes: owns the hash buffers and scratch (torch tensors),
+turns tensors into raw pointers and calls the C ABI (include/gsr_b200.h).  No arithmetic happens here.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, host
+from ._lib import GSR_NSETS, LossCfg, check, ptr, stream
+
+
+class _Scratch:
+	"""grow-only byte buffers, one per purpose, so steady-state calls do not allocate"""
+
+	def __init__(self, device):
+		self.device = device
+		self.bufs = {}
+
+	def get(self, name, nbytes):
+		b = self.bufs.get(name)
+		if b is None or b.numel() < nbytes:
+			b = torch.empty(max(int(nbytes * 1.25), 256), dtype=torch.uint8, device=self.device)
+			self.bufs[name] = b
+		return b
+
+	def typed(self, name, shape, dtype):
+		n = 1
+		for s in shape:
+			n *= int(s)
+		itemsize = torch.empty((), dtype=dtype).element_size()
+		return self.get(name, max(n, 1) * itemsize)[:n * itemsize].view(dtype).view(*shape)
+
+
+class HashEngine:
+	"""
+	State: cell_start (ncell+1) int32, sorted_id (N) int32, packed (N, 12|8) f32 — see include/gsr_b200.h.
+	`params` is a callable returning the CURRENT (positions, scalings, rotations, values) tensors of the owner,
+	because the reference's callers replace those tensor objects outright (3D/advance.py:54-58, :178-179).
+	"""
+
+	def __init__(self, D, device):
+		if not torch.cuda.is_available():
+			raise _lib.GsrError('the B200 engine needs a CUDA device; there is no CPU fallback')
+		self.D = D
+		self.device = torch.device(device)
+		self.lib = _lib.lib()
+		self.scratch = _Scratch(self.device)
+		self.desc = None
+		self.N = 0
+		self.cell_start = self.sorted_id = self.packed = None
+		self._packed_key = None
+
+	# ---- hash -------------------------------------------------------------------------------------
+	def set_grid(self, ext_bounds, dims, grid_scale, tau):
+		self.ext_bounds, self.dims = list(ext_bounds), list(dims)
+		self.desc = host.make_desc(self.D, ext_bounds, dims, grid_scale, tau)
+		self.ncell = host.n_cells(self.D, dims)
+
+	def build(self, positions, want_ref_format=False):
+		"""gsr_build_grid: radix sort of the Gaussian cell keys"""
+		N = positions.shape[0]
+		dev = self.device
+		if self.cell_start is None or self.cell_start.numel() != self.ncell + 1:
+			self.cell_start = torch.empty(self.ncell + 1, dtype=torch.int32, device=dev)
+		if self.sorted_id is None or self.sorted_id.numel() != N:
+			self.sorted_id = torch.empty(N, dtype=torch.int32, device=dev)
+			self.packed = torch.empty((N, 12 if self.D == 3 else 8), dtype=torch.float32, device=dev)
+		self.N = N
+		nbytes = self.lib.gsr_build_grid_ws_bytes(C.byref(self.desc), C.c_int64(N))
+		ws = self.scratch.get('sort', nbytes)
+		cnt = off = None
+		if want_ref_format:
+			cnt = torch.empty(self.ncell, dtype=torch.int32, device=dev)
+			off = torch.empty(self.ncell, dtype=torch.int32, device=dev)
+		check(self.lib.gsr_build_grid(C.byref(self.desc), ptr(positions, name='positions'), C.c_int64(N),
+									  ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
+									  ptr(cnt, torch.int32, True), ptr(off, torch.int32, True),
+									  ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()), 'gsr_build_grid')
+		self._packed_key = None
+		return cnt, off
+
+	@staticmethod
+	def _key(tensors):
+		return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+
+	def ensure_packed(self, params):
+		"""(re)pack {mu, Sigma^-1, v} in cell order when any parameter tensor changed since the last pack"""
+		key = self._key(params)
+		if key == self._packed_key:
+			return
+		p, s, r, v = params
+		if p.shape[0] != self.N:
+			raise _lib.GsrError('the number of Gaussians changed since the last reinitialize_grid()')
+		check(self.lib.gsr_pack_gaussians(C.byref(self.desc), ptr(p, name='positions'), ptr(s, name='scalings'),
+										  ptr(r, name='rotations', align16=True), ptr(v, name='values'), C.c_int64(self.N),
+										  ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
+										  ptr(self.packed, align16=True), stream()), 'gsr_pack_gaussians')
+		self._packed_key = key
+
+	def min_scaling(self, scalings):
+		out = torch.empty(1, dtype=torch.float32, device=self.device)
+		check(self.lib.gsr_min_scaling(ptr(scalings, name='scalings'), C.c_int64(scalings.numel()), ptr(out), stream()), 'gsr_min_scaling')
+		return out
+
+	# ---- samples ----------------------------------------------------------------------------------
+	def bin_samples(self, x, need_cells, tag='x'):
+		Q = x.shape[0]
+		perm = self.scratch.typed('perm_' + tag, (Q,), torch.int32)
+		scs = None
+		if need_cells:
+			pcell = self.lib.gsr_padded_cells(C.byref(self.desc))
+			scs = self.scratch.typed('scs_' + tag, (pcell + 1,), torch.int32)
+		nbytes = self.lib.gsr_bin_samples_ws_bytes(C.byref(self.desc), C.c_int64(Q))
+		ws = self.scratch.get('sort', nbytes)
+		check(self.lib.gsr_bin_samples(C.byref(self.desc), ptr(x, name='x'), C.c_int64(Q), ptr(perm, torch.int32), ptr(scs, torch.int32, True),
+									   ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()), 'gsr_bin_samples')
+		return perm, scs
+
+	def _x(self, x):
+		if x.dim() != 2 or x.shape[1] != self.D:
+			raise _lib.GsrError(f'sample points must have shape (Q, {self.D})')
+		return x.detach()
+
+	# ---- kernels ----------------------------------------------------------------------------------
+	def forward(self, x, val, grad, accumulate, perm=None):
+		x = self._x(x)
+		if perm is None:
+			perm, _ = self.bin_samples(x, False)
+		check(self.lib.gsr_forward(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True),
+								   ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(perm, torch.int32),
+								   ptr(val, allow_none=True, name='val'), ptr(grad, allow_none=True, name='grad'), C.c_int(1 if accumulate else 0), stream()), 'gsr_forward')
+
+	def rk4(self, start, dt, goal_pos, deformation=None, goal_val=None, goal_grad=None):
+		start = self._x(start)
+		perm, _ = self.bin_samples(start, False)
+		check(self.lib.gsr_rk4(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True),
+							   ptr(start, name='start_pos'), C.c_int64(start.shape[0]), ptr(perm, torch.int32), C.c_float(dt),
+							   ptr(goal_pos), ptr(deformation, allow_none=True), ptr(goal_val, allow_none=True), ptr(goal_grad, allow_none=True), stream()), 'gsr_rk4')
+
+	def advected_vorticity(self, x, dt, ref_vor, ref_hel=None, domain=None, perm=None):
+		x = self._x(x)
+		if perm is None:
+			perm, _ = self.bin_samples(x, False)
+		dom = (C.c_float * 4)(*domain) if domain is not None else None
+		check(self.lib.gsr_advected_vorticity(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True),
+											  ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(perm, torch.int32), C.c_float(dt), dom,
+											  ptr(ref_vor), ptr(ref_hel, allow_none=True), stream()), 'gsr_advected_vorticity')
+
+	def mark_neighbors(self, x, mark):
+		x = self._x(x)
+		check(self.lib.gsr_mark_neighbors(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
+										  ptr(self.packed, align16=True), ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(mark, torch.int32), stream()), 'gsr_mark_neighbors')
+
+	def backward_gather(self, x, perm, scs, val, grad, weights, refs, stop_gradient, Q_norm=None, tag='acc', want_losses=False):
+		"""returns (acc, sets_mask); acc is (3, N, 12|7) in original Gaussian order"""
+		x = self._x(x)
+		Q = x.shape[0]
+		cfg = LossCfg()
+		cfg.w_val, cfg.w_boundary, cfg.w_grad, cfg.w_vor, cfg.w_hel, cfg.w_div = [float(w) for w in weights]
+		cfg.Q_norm = int(Q_norm if Q_norm is not None else Q)
+		keep = []
+		for name in ('ref_val', 'normals', 'normal_ref', 'ref_grad', 'ref_vor', 'ref_hel'):
+			t = refs.get(name)
+			if t is not None:
+				t = t.detach()
+				keep.append(t)
+				setattr(cfg, name, ptr(t, name=name).value)
+		if stop_gradient is not None:
+			if stop_gradient.dtype != torch.int32:
+				stop_gradient = stop_gradient.to(torch.int32)
+			keep.append(stop_gradient)
+			cfg.stop_gradient = ptr(stop_gradient, torch.int32, name='stop_gradient').value
+		self.last_loss_partials = None
+		if want_losses:
+			nblk = self.lib.gsr_loss_blocks(C.c_int64(Q))
+			lp = self.scratch.typed('lp_' + tag, (nblk, 8), torch.float32)
+			cfg.loss_partials = ptr(lp).value
+			self.last_loss_partials = (lp, nblk)
+		AF = 12 if self.D == 3 else 7
+		acc = self.scratch.typed(tag, (GSR_NSETS, self.N, AF), torch.float32)
+		nbytes = self.lib.gsr_backward_ws_bytes(C.byref(self.desc), C.c_int64(self.N), C.c_int64(Q))
+		ws = self.scratch.get('adjoint', nbytes)
+		mask = C.c_int(0)
+		check(self.lib.gsr_backward_gather(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
+										   ptr(self.packed, align16=True), C.c_int64(self.N), ptr(x, name='x'), C.c_int64(Q),
+										   ptr(perm, torch.int32), ptr(scs, torch.int32), ptr(val, name='val'), ptr(grad, allow_none=True, name='grad'),
+										   C.byref(cfg), ptr(acc, align16=True), C.byref(mask), ptr(ws, torch.uint8, align16=True), C.c_size_t(ws.numel()), stream()),
+			  'gsr_backward_gather')
+		return acc, mask.value
+
+	def backward_epilogue(self, scalings, rotations, acc, mask, outs):
+		"""outs: 3 lists (direct, vor, div) of 4 gradient tensors (positions, scalings, rotations, values), accumulated into"""
+		if mask == 0:
+			return
+		arr = ((C.c_void_p * 4) * GSR_NSETS)()
+		for s in range(GSR_NSETS):
+			for k in range(4):
+				t = outs[s][k] if outs[s] is not None else None
+				arr[s][k] = ptr(t, name='gradient buffer').value if t is not None else None
+		check(self.lib.gsr_backward_epilogue(C.byref(self.desc), ptr(scalings.detach(), name='scalings'), ptr(rotations.detach(), name='rotations'),
+											 C.c_int64(self.N), ptr(acc, align16=True), C.c_int(mask), arr, stream()), 'gsr_backward_epilogue')
+
+	def sample_losses(self, val, grad, refs, Q):
+		"""gsr_sample_losses: the 8 loss slots of include/gsr_b200.h summed over the samples (device tensor, no sync)"""
+		cfg = LossCfg()
+		keep = []
+		for name in ('ref_val', 'normals', 'normal_ref', 'ref_grad', 'ref_vor', 'ref_hel'):
+			t = refs.get(name)
+			if t is not None:
+				keep.append(t)
+				setattr(cfg, name, ptr(t.detach(), name=name).value)
+		sums = torch.empty(8, dtype=torch.float32, device=self.device)
+		nblk = self.lib.gsr_loss_blocks(C.c_int64(Q))
+		ws = self.scratch.get('loss_ws', nblk * 8 * 4)
+		check(self.lib.gsr_sample_losses(C.byref(self.desc), C.c_int64(Q), ptr(val, allow_none=True), ptr(grad, allow_none=True), C.byref(cfg),
+										 ptr(sums), ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()), 'gsr_sample_losses')
+		return sums
+
+
+class FusedStepper:
+	"""
+	Device-resident optimiser of one `project` / fit phase: Adam moments, lrs, ReduceLROnPlateau state, the loss metric
+	and the next grid_scale all live in one float32 state tensor (layout: include/gsr_b200.h); gsr_step advances it
+	with 4 launches and no host synchronisation.
+	"""
+
+	def __init__(self, engine, lrs, patience, w_aniso, w_vol, w_valreg=0., w_dpos=0., pcgrad=True, factor=.9,
+				 tau=None, min_grid_scale=None, ext_bounds=None):
+		import numpy as np
+		self.e = engine
+		D = engine.D
+		cfg = _lib.StepCfg()
+		cfg.D = D
+		for k in range(4):
+			cfg.lr[k] = float(lrs[k])
+		cfg.beta1, cfg.beta2, cfg.eps = .9, .999, 1e-8
+		cfg.sched_factor, cfg.sched_threshold, cfg.sched_eps, cfg.sched_min_lr = float(factor), 1e-4, 1e-8, 0.
+		cfg.sched_patience = int(patience)
+		cfg.w_aniso, cfg.w_vol, cfg.w_valreg, cfg.w_dpos = float(w_aniso), float(w_vol), float(w_valreg), float(w_dpos)
+		cfg.aniso_ratio = 1.5
+		cfg.pcgrad = 1 if pcgrad else 0
+		cfg.grid_coef = float(np.sqrt(-2. * np.log(tau))) if tau else 0.
+		cfg.min_grid_scale = float(min_grid_scale)
+		cfg.grid_scale_tau0 = float(max(ext_bounds[2 * k + 1] - ext_bounds[2 * k] for k in range(D)))
+		self.cfg = cfg
+		self.N = None
+		self.state = None
+
+	def init(self, scalings):
+		N = scalings.shape[0]
+		self.N = N
+		nfl = self.e.lib.gsr_step_state_floats(C.c_int(self.e.D), C.c_int64(N))
+		self.state = torch.empty(nfl, dtype=torch.float32, device=self.e.device)
+		check(self.e.lib.gsr_step_init(C.byref(self.cfg), C.c_int64(N), ptr(scalings.detach()), ptr(self.state), stream()), 'gsr_step_init')
+		self.ws = torch.empty(self.e.lib.gsr_step_ws_bytes(C.c_int(self.e.D), C.c_int64(N)), dtype=torch.uint8, device=self.e.device)
+		# from now on the engine's kernels read grid_scale from the device-resident state
+		self.e.desc.grid_scale_dev = self.state.data_ptr() + 4 * _lib.ST_GRID_SCALE
+
+	def step(self, params, acc, mask, extra=(), loss_srcs=(), positions_org=None):
+		p, s, r, v = params
+		ex = (C.c_void_p * 2)()
+		for k in range(2):
+			ex[k] = ptr(extra[k], align16=True).value if k < len(extra) and extra[k] is not None else None
+		srcs = (_lib.LossSrc * 3)()
+		for k, (partials, nblk, w) in enumerate(loss_srcs):
+			srcs[k].partials = ptr(partials).value
+			srcs[k].nblocks = int(nblk)
+			for q in range(8):
+				srcs[k].w[q] = float(w[q])
+		check(self.e.lib.gsr_step(C.byref(self.cfg), C.c_int64(self.N), ptr(p), ptr(s), ptr(r), ptr(v),
+								  ptr(acc, allow_none=True, align16=True), C.c_int(mask), ex, srcs, C.c_int(len(loss_srcs)),
+								  ptr(positions_org, allow_none=True), ptr(self.state), ptr(self.ws, torch.uint8), C.c_size_t(self.ws.numel()), stream()), 'gsr_step')
+
+	def scalars(self):
+		"""host copy of the scalar block (synchronises)"""
+		return self.state[:_lib.STATE_SCALARS].tolist()
+
+	def detach(self):
+		"""hand grid_scale back to the host descriptor (synchronises once)"""
+		gs = float(self.state[_lib.ST_GRID_SCALE].item())
+		self.e.desc.grid_scale_dev = None
+		self.e.desc.grid_scale = gs
+		return gs

@@ -1,0 +1,225 @@
+/*
+ * gsr_b200.h — C ABI of the B200-native Gaussian-Spatial-Representation engine.
+ *
+ * This is the drop-in boundary for the hot path of DvvCz/Gaussian-Fluids-Code: one entry point per
+ * Taichi kernel of the reference (3D/GSR.py, 2D/GSR.py) plus the fused per-iteration optimisation
+ * step of advance.py.  Plain pointers and sizes only — no torch types.  All pointers are DEVICE
+ * pointers unless the parameter is a `const gsr_grid_desc*` or `const gsr_*_cfg*` (host structs).
+ * Every function enqueues work on `stream` (a cudaStream_t passed as void*), never synchronises
+ * the host, never allocates (scratch comes from the caller's `ws` buffer, sized by
+ * gsr_*_ws_bytes), and is CUDA-graph capturable.  Return value: 0 = ok, otherwise a negative
+ * GSR_E* code or a positive cudaError_t.
+ *
+ * Layouts (all float32, C-contiguous, as the reference's torch tensors):
+ *   3D: positions (N,3) scalings (N,3) rotations (N,4 quaternion [w,x,y,z]) values (N,3)
+ *   2D: positions (N,2) scalings (N,2) rotations (N,)  angle                values (N,2)
+ *   val (Q,D)   grad (Q,D,D) with grad[j,d,l] = d u_d / d x_l.
+ *
+ * The engine's own hash representation (built by gsr_build_grid + gsr_pack_gaussians):
+ *   cell_start (ncell+1) int32 : exclusive prefix of the per-cell counts in row-major cell order
+ *                                (== the reference's grid_offset, plus the total at [ncell]);
+ *   sorted_id  (N) int32       : Gaussian ids ordered by cell, ascending id inside a cell
+ *                                (== the reference's sorted_id, canonical intra-cell order);
+ *   packed     (N * GSR_PACK_FLOATS(D)) float32 : per-Gaussian {mu, Sigma^-1, v} in cell order.
+ */
+#ifndef GSR_B200_H
+#define GSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_OK 0
+#define GSR_EINVAL (-1)	/* bad argument (D, dims, NULL pointer, ...) */
+#define GSR_EWS (-2)	/* workspace too small */
+
+#define GSR_PACK_FLOATS(D) ((D) == 3 ? 12 : 8)
+
+/* Spatial-hash descriptor.  Mirrors the constants the reference bakes into its kernels
+ * (3D/GSR.py:160-177, 2D/GSR.py:177-192): the extended domain rounded to f32, grid_size, tau,
+ * and the run-time grid_scale (3D/GSR.py:247-252). */
+typedef struct {
+	int32_t D;		/* 2 or 3 */
+	int32_t dims[3];	/* grid_size; dims[2] ignored for D == 2 */
+	float lo[3], hi[3];	/* x_min.. / x_max.. of the EXTENDED domain */
+	float grid_scale;
+	float tau;		/* clamp_threshold */
+	const float *grid_scale_dev;	/* optional DEVICE scalar: when non-NULL the kernels read grid_scale from it
+					 * (kept up to date by gsr_step, so the optimisation loop never syncs the host) */
+} gsr_grid_desc;
+
+/* ---- a1: spatial hash  (reinitialize_grid_ti: 3D/GSR.py:205-245, 2D/GSR.py:194-222) ------------ */
+size_t gsr_build_grid_ws_bytes(const gsr_grid_desc *g, int64_t N);
+/* Outputs: cell_start (ncell+1), sorted_id (N; entries past cell_start[ncell] list the Gaussians outside the hash),
+ * optionally the reference-format grid_cnt (ncell) and grid_offset (ncell) (may be NULL). */
+int gsr_build_grid(const gsr_grid_desc *g, const float *positions, int64_t N,
+		   int32_t *cell_start, int32_t *sorted_id, int32_t *grid_cnt, int32_t *grid_offset,
+		   void *ws, size_t ws_bytes, void *stream);
+
+/* Per-Gaussian precompute {mu, Sigma^-1 = R diag(e^{2s}) R^T, v}, gathered into cell order
+ * (hoists the per-pair recomputation of 3D/GSR.py:277-289, 2D/GSR.py:274-277 out of the pair loop). */
+int gsr_pack_gaussians(const gsr_grid_desc *g, const float *positions, const float *scalings, const float *rotations,
+		       const float *values, int64_t N, const int32_t *cell_start, const int32_t *sorted_id,
+		       float *packed, void *stream);
+
+/* min over all entries of scalings -> *out_min (device float); the reduction behind
+ * `self.scalings.min().item()` of reinitialize_grid (3D/GSR.py:249). */
+int gsr_min_scaling(const float *scalings, int64_t count, float *out_min, void *stream);
+
+/* ---- sample binning (engine-internal ordering of the query points) ------------------------------ */
+size_t gsr_bin_samples_ws_bytes(const gsr_grid_desc *g, int64_t Q);
+/* perm (Q): sample indices ordered by (padded) cell key, stable;  sample_cell_start: (pcell+1)
+ * with pcell = prod(dims+2), may be NULL when only the ordering is needed. */
+int gsr_bin_samples(const gsr_grid_desc *g, const float *x, int64_t Q, int32_t *perm, int32_t *sample_cell_start,
+		    void *ws, size_t ws_bytes, void *stream);
+int64_t gsr_padded_cells(const gsr_grid_desc *g);
+
+/* ---- a2: forward  (loop 1 of get_losses_ti 3D/GSR.py:270-298; 2D/GSR.py:266-281, :378-395) ------ */
+/* perm may be NULL (process samples in the given order).  val and/or grad may be NULL.
+ * accumulate != 0: outputs are += (3D reference semantics); 0: overwritten (2D semantics). */
+int gsr_forward(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed,
+		const float *x, int64_t Q, const int32_t *perm, float *val, float *grad, int accumulate, void *stream);
+
+/* ---- a4: RK4 advection + pull-back  (advection_rk4_ti 3D/GSR.py:634-665; 2D/GSR.py:549-580) ----- */
+/* deformation / goal_val / goal_grad may be NULL (the reference's size-0 outputs). */
+int gsr_rk4(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed,
+	    const float *start, int64_t Q, const int32_t *perm, float dt,
+	    float *goal_pos, float *deformation, float *goal_val, float *goal_grad, void *stream);
+
+/* ---- a5: advected-covector reference  (AdvectedCovectorField.vorticity 3D/advance.py:24-47,
+ *          2D/advance.py:46-54): RK4 back-trace fused with curl, 3x3 inverse and helicity -------- */
+/* 3D: ref_vor (Q,3), ref_hel (Q) | NULL.  2D: ref_vor (Q), zeroed where the back-traced point leaves
+ * domain[4] = {x_min,x_max,y_min,y_max} (host pointer, may be NULL); ref_hel ignored. */
+int gsr_advected_vorticity(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed,
+			   const float *x, int64_t Q, const int32_t *perm, float dt, const float *domain,
+			   float *ref_vor, float *ref_hel, void *stream);
+
+/* ---- a6: neighbour marking  (get_all_neighbors_ti 3D/GSR.py:679-690; 2D/GSR.py:620-630) --------- */
+int gsr_mark_neighbors(const gsr_grid_desc *g, const int32_t *cell_start, const int32_t *sorted_id, const float *packed,
+		       const float *x, int64_t Q, int32_t *mark, void *stream);
+
+/* ---- a3: backward  (loop 2 of get_losses_ti 3D/GSR.py:299-540; 2D/GSR.py:282-339, :396-476) ----- */
+typedef struct {
+	/* 3D: weight_val, weight_boundary, weight_grad, weight_vor, weight_hel, weight_div.
+	 * 2D: `weight`, weight_boundary, weight_grad, weight_vor, (unused), weight_div — the value kernel
+	 *     and the gradient kernel of 2D/GSR.py share this struct (set the other kernel's weights to 0). */
+	float w_val, w_boundary, w_grad, w_vor, w_hel, w_div;
+	int64_t Q_norm;		/* the Q of the loss normalisers (global sample count when sharded) */
+	/* reference inputs, each (Q, ...) or NULL when its weight is 0 */
+	const float *ref_val;	/* (Q,D) */
+	const float *normals;	/* (Q,D) */
+	const float *normal_ref;	/* 2D only: (Q) target of u.n (2D/GSR.py:302) */
+	const float *ref_grad;	/* (Q,D,D) */
+	const float *ref_vor;	/* 3D (Q,3); 2D (Q) */
+	const float *ref_hel;	/* 3D (Q) */
+	const int32_t *stop_gradient;	/* (N) int32 or NULL */
+	float *loss_partials;	/* optional out, device (gsr_loss_blocks(Q), 8): per-block partial sums of the sample losses,
+				 * reduced deterministically by gsr_step / gsr_sample_losses.  Slots (sums over the samples):
+				 * 0 mean_k|omega-omega_ref| (3D) or |omega-omega_ref| (2D)   1 |u.omega - hel_ref|   2 (div u)^2
+				 * 3 |u.n| (3D) or |u.n - normal_ref| (2D)   4 mean_d|u-ref_val|   5 mean|grad u - ref_grad|   6,7 unused */
+} gsr_loss_cfg;
+
+int64_t gsr_loss_blocks(int64_t Q);
+/* The sample losses alone (no gradient): sums[8] (device) = slots above summed over the Q samples.
+ * ws: gsr_loss_blocks(Q)*8 floats. */
+int gsr_sample_losses(const gsr_grid_desc *g, int64_t Q, const float *val, const float *grad, const gsr_loss_cfg *cfg,
+		      float *sums, void *ws, size_t ws_bytes, void *stream);
+
+/* number of compact accumulator sets the gather produces: direct, vor(+hel), div */
+#define GSR_NSETS 3
+/* floats per Gaussian per set: d/dv (D), d/dmu (D), d/dSigma^-1 (D(D+1)/2) */
+#define GSR_ACC_FLOATS(D) ((D) == 3 ? 12 : 7)
+
+size_t gsr_backward_ws_bytes(const gsr_grid_desc *g, int64_t N, int64_t Q);
+/*
+ * Stage 1+2: per-sample adjoints, then the atomics-free Gaussian-centric gather.
+ * acc: (GSR_NSETS, N, GSR_ACC_FLOATS(D)) in ORIGINAL Gaussian id order, overwritten (zero for
+ * out-of-domain or stop_gradient Gaussians).  `sets_mask` (host, out): bit s set when set s is active.
+ * This buffer is what a multi-GPU run all-reduces (sum) across sample shards.
+ */
+int gsr_backward_gather(const gsr_grid_desc *g, const int32_t *cell_start, const int32_t *sorted_id, const float *packed, int64_t N,
+			const float *x, int64_t Q, const int32_t *perm, const int32_t *sample_cell_start,
+			const float *val, const float *grad, const gsr_loss_cfg *cfg,
+			float *acc, int *sets_mask, void *ws, size_t ws_bytes, void *stream);
+/*
+ * Stage 3: per-Gaussian chain rule Sigma^-1 -> (scalings, rotations) and accumulation (+=) into the
+ * reference's gradient buffers.  out[s] = {positions, scalings, rotations, values} grads of set s
+ * (s = 0 direct, 1 vor, 2 div); buffers of different sets MAY alias (3D/GSR.py:564-579).
+ */
+int gsr_backward_epilogue(const gsr_grid_desc *g, const float *scalings, const float *rotations, int64_t N,
+			  const float *acc, int sets_mask, float *const out[GSR_NSETS][4], void *stream);
+
+/* ---- a7: fused per-iteration optimiser step of project()  (3D/advance.py:183-287, GSR.py:148-152,
+ *          :704-716; 2D/advance.py:187-259) -------------------------------------------------------- */
+typedef struct {
+	int32_t D;
+	float lr[4];		/* initial lrs: positions, scalings, rotations, values */
+	float beta1, beta2, eps;	/* torch.optim.Adam defaults .9 .999 1e-8 */
+	/* torch ReduceLROnPlateau(mode='min', threshold_mode='rel', cooldown=0): factor .9, threshold 1e-4, eps 1e-8 */
+	float sched_factor, sched_threshold, sched_eps, sched_min_lr;
+	int32_t sched_patience;
+	float w_aniso, w_vol, w_valreg, w_dpos;	/* regulariser weights (3D: 10,10,0,-; 2D: 10,10,-,.5) */
+	float aniso_ratio;	/* 1.5 */
+	int32_t pcgrad;		/* 1: mutual projection of the vor and div sets (3D/advance.py:202-225) */
+	double grid_coef;	/* sqrt(-2 ln tau) in host double (3D/GSR.py:249); 0 when tau == 0 */
+	double min_grid_scale;
+	double grid_scale_tau0;	/* the constant grid_scale used when tau == 0 (3D/GSR.py:251) */
+} gsr_step_cfg;
+
+/* one source of sample-loss partial sums and its weights in the scheduler metric:
+ * loss_tot += sum_k w[k] * (sum over blocks of partials[.,k]) */
+typedef struct {
+	const float *partials;
+	int32_t nblocks;
+	float w[8];
+} gsr_loss_src;
+
+/* Device-resident optimiser state (float32): [GSR_STATE_SCALARS scalars][Adam m: P*N][Adam v: P*N], P = 13 (3D) / 7 (2D),
+ * parameter order positions, scalings, rotations, values.  Scalars: */
+#define GSR_STATE_SCALARS 64
+#define GSR_ST_T 0		/* Adam step count */
+#define GSR_ST_BEST 1		/* scheduler: best metric */
+#define GSR_ST_BAD 2		/* scheduler: num_bad_epochs */
+#define GSR_ST_LR 3		/* [3..6] current lr per group */
+#define GSR_ST_GRID_SCALE 7	/* grid_scale for the NEXT hash build (point gsr_grid_desc.grid_scale_dev here) */
+#define GSR_ST_MIN_S 8		/* min over scalings after the update */
+#define GSR_ST_LOSS_TOT 9	/* the scheduler metric of this iteration */
+#define GSR_ST_L_ANISO 10
+#define GSR_ST_L_VOL 11
+#define GSR_ST_L_VALREG 12
+#define GSR_ST_L_DPOS 13
+#define GSR_ST_LOSS_SRC 14	/* [14..21] sum over sources of the raw loss slots divided by nothing (plain sums) */
+size_t gsr_step_state_floats(int D, int64_t N);
+size_t gsr_step_ws_bytes(int D, int64_t N);
+/* zero the moments, t = 0, best = +inf, lrs = cfg->lr, grid_scale from the current scalings */
+int gsr_step_init(const gsr_step_cfg *cfg, int64_t N, const float *scalings, float *state, void *stream);
+/*
+ * One optimiser iteration on device with no host sync (4 launches):
+ *   A  per Gaussian: chain rule of the vor and div sets, block partial sums of the 12 PCGrad dot products,
+ *      the volume moments and the regulariser losses;
+ *   R  one block: deterministic reduction, PCGrad coefficients, loss_tot, Adam bias corrections,
+ *      ReduceLROnPlateau update (the lr used by this step is the one before the update, as in torch);
+ *   B  per Gaussian: total gradient = projected vor + div sets + extra direct sets (boundary passes)
+ *      + closed-form regulariser gradients; Adam; parameters updated in place; min over the new scalings;
+ *   S  next grid_scale = max(grid_coef * exp(-min s), min_grid_scale) in double, rounded to f32.
+ * acc/sets_mask: from gsr_backward_gather (already all-reduced when sharded).  extra_direct[k]: accumulator buffers
+ * whose set 0 (direct) is added (boundary passes), or NULL.  positions_org: 2D position-drift anchor or NULL.
+ */
+int gsr_step(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalings, float *rotations, float *values,
+	     const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
+	     const float *positions_org, float *state, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- measurement helpers (bench.py roofline denominators) --------------------------------------- */
+/* runs an FFMA-only / ex2.approx-only loop on every SM; returns elapsed ms via *ms (host sync inside) */
+int gsr_peak_fma(int iters, double *tflops, void *stream);
+int gsr_peak_mufu(int iters, double *tops, void *stream);
+
+const char *gsr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

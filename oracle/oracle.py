@@ -237,6 +237,19 @@ class OracleGSR:
 						C.c_double(self.tau), _p(start), C.c_long(Q), C.c_double(dt), _p(goal), _p(deform), _p(gval), _p(ggrad), C.c_int(self.nthreads))
 		return goal if pos_only else (goal, deform, gval, ggrad)
 
+	def rk4_eval_points(self, start, dt):
+		"""the five points at which advection_rk4 evaluates the field (start, three stages, end point)"""
+		x = np.asarray(start, np.float64)
+		dt = float(np.float32(dt))
+		pts, vs = [x], []
+		for c in (.5, .5, 1.):
+			v, _ = self.forward(pts[-1].astype(np.float32), need_grad=False)
+			vs.append(v.astype(np.float64))
+			pts.append(x + dt * c * vs[-1])
+		v3, _ = self.forward(pts[-1].astype(np.float32), need_grad=False)
+		pts.append(x + dt / 6. * (vs[0] + 2. * vs[1] + 2. * vs[2] + v3))
+		return pts
+
 	def mark_neighbors(self, x):
 		x = _f32(x)
 		mark = np.zeros(self.N, np.int32)

@@ -1,0 +1,148 @@
+"""
+GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the drop-in class and hence the
+C ABI, against (i) the golden vectors produced from the reference's own kernel bodies and (ii) the CPU oracle on
+seeded inputs.  Tolerances (BASELINE.json north_star): integer outputs bit-exact; fields and gradients 1e-5
+relative, measured per tensor as max|a-b| / max|b| against the float64 oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import NAMES, load_golden, oracle_from_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def make_fast3d(pos, scal, rot, vals, tau, mgs):
+	from gaussian_fluids_code_b200 import gsr3d
+	o = gsr3d.GaussianSplatting3DFast(0., 1., 0., 1., 0., 1., np.asarray(pos, np.float32), min_grid_scale=mgs, clamp_threshold=tau, dim=3)
+	dev = gsr3d.device
+	with torch.no_grad():
+		o.scalings.copy_(torch.tensor(np.asarray(scal, np.float32), device=dev))
+		o.rotations.copy_(torch.tensor(np.asarray(rot, np.float32), device=dev))
+		o.values.copy_(torch.tensor(np.asarray(vals, np.float32), device=dev))
+	o.zero_grad()
+	return o
+
+
+def from_golden(g):
+	return make_fast3d(g['in_positions'], g['in_scalings'], g['in_rotations'], g['in_values'], float(g['in_tau']), float(g['in_min_grid_scale']))
+
+
+def T(a, dtype=torch.float32):
+	return torch.tensor(np.asarray(a), dtype=dtype, device='cuda')
+
+
+def test_grid_matches_reference_golden():
+	g = load_golden('ref3d_kernels_f32.npz')
+	o = from_golden(g)
+	assert list(g['grid_size']) == o.grid_size
+	assert np.float32(o.grid_scale) == np.float32(g['grid_scale'])
+	cnt, off, sid = o.grid_arrays()
+	np.testing.assert_array_equal(cnt.cpu().numpy().ravel(), g['grid_cnt'])
+	np.testing.assert_array_equal(off.cpu().numpy().ravel(), g['grid_offset'])
+	np.testing.assert_array_equal(sid.cpu().numpy(), g['sorted_id'])
+
+
+@pytest.mark.parametrize('case', ['project', 'fit', 'boundary', 'all'])
+def test_losses_match_reference_golden(case):
+	"""forward + backward of get_losses against the reference kernels run in float64 (tests/golden)"""
+	g = load_golden('ref3d_kernels_f64.npz')
+	o = from_golden(g)
+	wv, wb, wg, wo, wh, wd = [float(w) for w in g[f'{case}_weights']]
+	separate = f'{case}_vor_positions' in g
+	x = T(g['in_x'])
+	kw = {}
+	if separate:
+		for tag in ('vor', 'div'):
+			for nm in NAMES:
+				kw[f'{tag}_{nm}_grad'] = torch.zeros_like(getattr(o, nm))
+	val, grad = o.get_losses(x, ref_val=T(g['in_ref_val']), weight_val=wv, normals=T(g['in_normals']), weight_boundary=wb,
+							 ref_grad=T(g['in_ref_grad']), weight_grad=wg, ref_vor=T(g['in_ref_vor']), weight_vor=wo,
+							 ref_hel=T(g['in_ref_hel']), weight_hel=wh, weight_div=wd,
+							 stop_gradient=T(g['in_stop_gradient'], torch.int32) if case == 'all' else None, **kw)
+	assert rel_err(val.cpu().numpy(), g[f'{case}_val']) < TOL
+	assert rel_err(grad.cpu().numpy(), g[f'{case}_grad']) < TOL
+	for nm in NAMES:
+		assert rel_err(getattr(o, nm).grad.cpu().numpy(), g[f'{case}_direct_{nm}']) < TOL, ('direct', nm)
+		if separate:
+			for tag in ('vor', 'div'):
+				assert rel_err(kw[f'{tag}_{nm}_grad'].cpu().numpy(), g[f'{case}_{tag}_{nm}']) < TOL, (tag, nm)
+
+
+def test_rk4_and_neighbors_match_reference_golden():
+	g = load_golden('ref3d_kernels_f64.npz')
+	o = from_golden(g)
+	x = T(g['in_x'])
+	pos, deform, val, grad = o.advection_rk4(x, float(g['rk4_dt']), pos_only=False)
+	for a, k in ((pos, 'rk4_pos'), (deform, 'rk4_deformation'), (val, 'rk4_val'), (grad, 'rk4_grad')):
+		assert rel_err(a.cpu().numpy(), g[k]) < TOL, k
+	assert rel_err(o.advection_rk4(x, float(g['rk4_dt'])).cpu().numpy(), g['rk4_pos']) < TOL
+	np.testing.assert_array_equal(o.get_all_neighbors(x[:3].contiguous()).cpu().numpy(), g['neighbors_mark'])
+
+
+def synthetic(n, seed=42, tau=5e-3):
+	"""BASELINE.md §3 synthetic field: jittered n^3 lattice, s0 + N(0, .1^2) (clipped), random quaternions and values"""
+	gen = torch.Generator().manual_seed(seed)
+	N = n ** 3
+	ax = torch.linspace(0., 1., n)
+	P = torch.stack(torch.meshgrid(ax, ax, ax, indexing='ij'), -1).reshape(-1, 3)
+	h = 1. / (n - 1)
+	P = (P + (torch.rand(P.shape, generator=gen) - .5) * .5 * h).clamp(0., 1.)
+	mgs = 2. * N ** (-1. / 3.)
+	s0 = .5 * np.log(-2. * np.log(tau)) - np.log(mgs)
+	S = s0 + (torch.randn((N, 3), generator=gen) * .1).clamp(-.2, .2)
+	R = torch.randn((N, 4), generator=gen)
+	V = torch.randn((N, 3), generator=gen) * .1
+	return P.numpy(), S.numpy(), R.numpy(), V.numpy(), mgs, gen
+
+
+@pytest.mark.parametrize('n,Q', [(10, 1000), (20, 8000), (32, 4096)])
+def test_against_oracle_seeded(n, Q):
+	"""seeded synthetic fields at sizes the oracle finishes in seconds: hash bit-exact, fields/gradients 1e-5 vs f64"""
+	from oracle.oracle import OracleGSR, extended_bounds
+	tau = 5e-3
+	P, S, R, V, mgs, gen = synthetic(n)
+	o = make_fast3d(P, S, R, V, tau, mgs)
+	ext = extended_bounds(3, (0., 1.) * 3, mgs)
+	orc = OracleGSR(3, ext, P, S, R, V, tau, mgs, precision='f64', nthreads=8)
+	cnt, off, sid = o.grid_arrays()
+	assert np.float32(o.grid_scale) == np.float32(orc.grid_scale)
+	np.testing.assert_array_equal(cnt.cpu().numpy().ravel(), orc.cnt)
+	np.testing.assert_array_equal(off.cpu().numpy().ravel(), orc.offset)
+	np.testing.assert_array_equal(sid.cpu().numpy(), orc.sorted_id[:orc.n_in])
+	X = torch.rand((Q, 3), generator=gen)
+	x = X.cuda()
+	# samples with a pair inside the borderline band |q - q_max| <= 1e-4 q_max are compared separately
+	n_acc, n_band = orc.classify_pairs(X.numpy())
+	clean = n_band == 0
+	assert clean.mean() > .95
+	val, grad = o.get_losses(x)
+	oval, ograd = orc.forward(X.numpy())
+	assert rel_err(val.cpu().numpy()[clean], oval[clean]) < TOL
+	assert rel_err(grad.cpu().numpy()[clean], ograd[clean]) < TOL
+	# in-band samples: val is continuous across the cut, grad jumps by O(tau |Sigma^-1 d| |v|)
+	assert rel_err(val.cpu().numpy(), oval) < 1e-4
+	# RK4 with all outputs
+	res = o.advection_rk4(x, -.02, pos_only=False)
+	ores = orc.rk4(X.numpy(), -.02, pos_only=False)
+	rk_clean = clean.copy()
+	for pts in orc.rk4_eval_points(X.numpy(), -.02)[1:]:	# every stage / end point must be free of borderline pairs too
+		rk_clean &= orc.classify_pairs(pts)[1] == 0
+	assert rk_clean.mean() > .9
+	for a, b, nm in zip(res, ores, ('pos', 'deformation', 'val', 'grad')):
+		assert rel_err(a.cpu().numpy()[rk_clean], b[rk_clean]) < TOL, nm
+		assert rel_err(a.cpu().numpy(), b) < 2e-2, nm
+	# backward (project weights) fed with the oracle's own forward totals so that no sign() can flip
+	ref_vor = torch.randn((Q, 3), generator=gen) * .1
+	ref_hel = torch.randn((Q,), generator=gen) * .1
+	acc = {f'{tag}_{nm}_grad': torch.zeros_like(getattr(o, nm)) for tag in ('vor', 'div') for nm in NAMES}
+	o.get_losses(x, ref_vor=ref_vor.cuda(), weight_vor=1., ref_hel=ref_hel.cuda(), weight_hel=1., weight_div=1., **acc)
+	direct, vor, div = orc.zero_grads(), orc.zero_grads(), orc.zero_grads()
+	orc.backward3d(X.numpy(), oval, ograd, ref_vor=ref_vor.numpy(), weight_vor=1., ref_hel=ref_hel.numpy(), weight_hel=1., weight_div=1.,
+				   direct=direct, vor=vor, div=div)
+	for tag, grp in (('vor', vor), ('div', div)):
+		for nm, b in zip(NAMES, grp):
+			a = acc[f'{tag}_{nm}_grad'].cpu().numpy()
+			assert rel_err(a, b) < 5e-4, (tag, nm, rel_err(a, b))
