@@ -236,14 +236,21 @@ class FusedProjector:
 		self.stepper.step(gv._params(), acc, mask, extra=extra, loss_srcs=srcs)
 		self._rebuild()
 
-	def evaluate(self, data):
-		"""losses of the current field on `data` without a gradient (the test pass, 3D/advance.py:226-235): device sums"""
+	def evaluate(self, data, probe=None):
+		"""losses of the current field on `data` without a gradient (the test pass, 3D/advance.py:226-235): device sums.
+		probe: optional list that receives a (start, end) CUDA-event pair around the RK4 pull-back kernel (bench.py)."""
 		gv, e = self.gv, self.gv._engine
 		data = data.detach()
 		Q = data.shape[0]
 		perm, _ = e.bin_samples(data, False)
 		ref_vor, ref_hel = self._tmp('t_ref_vor', (Q, 3)), self._tmp('t_ref_hel', (Q,))
+		if probe is not None:
+			ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+			ev[0].record()
 		self.ref.velocity_field._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=perm)
+		if probe is not None:
+			ev[1].record()
+			probe.append(ev)
 		val, grad = self._tmp('t_val', (Q, 3)), self._tmp('t_grad', (Q, 3, 3))
 		e.forward(data, val, grad, accumulate=False, perm=perm)
 		return e.sample_losses(val, grad, {'ref_vor': ref_vor, 'ref_hel': ref_hel}, Q) / Q

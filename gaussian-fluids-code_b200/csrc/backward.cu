@@ -221,21 +221,34 @@ __device__ __forceinline__ void pair_accum3(Acc12 &acc, const float a[3], const 
 
 constexpr int GA_THREADS = 128;
 
-template <bool HAS_DIR, bool HAS_VOR, bool HAS_DIV>
+template <int LPG>
+__device__ __forceinline__ void acc12_reduce(Acc12 &a)
+{
+#pragma unroll
+	for (int k = 0; k < 3; k++) { a.dv[k] = lane_sum<LPG>(a.dv[k]); a.dm[k] = lane_sum<LPG>(a.dm[k]); }
+#pragma unroll
+	for (int k = 0; k < 6; k++) a.G[k] = lane_sum<LPG>(a.G[k]);
+}
+
+// LPG lanes cooperate on one Gaussian (1: throughput shape for large N; 8 / 32: latency shape for small N or Q >> N)
+template <bool HAS_DIR, bool HAS_VOR, bool HAS_DIV, int LPG>
 __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_id,
 							      const float4 *__restrict__ packed, int N, const int32_t *__restrict__ scs /* sample_cell_start */,
 							      const float4 *__restrict__ rec, const int32_t *__restrict__ stop_gradient, float tscale,
 							      float *__restrict__ acc_out)
 {
 	constexpr int STRIDE = 1 + (HAS_VOR ? 2 : 0) + (HAS_DIR ? 3 : 0);
-	int t = blockIdx.x * GA_THREADS + threadIdx.x;
-	if (t >= N) return;
+	const int gt = blockIdx.x * GA_THREADS + threadIdx.x;
+	const int tq = gt / LPG, lane = gt % LPG;
+	if (LPG == 1 && tq >= N) return;
+	const bool valid = tq < N;
+	const int t = valid ? tq : N - 1;
 	const Grid &g = P.g;
 	const int id = sorted_id[t];
 	const int n_in = cell_start[g.ncell];
 	Acc12 aD, aV, aX;
 	aD.zero(); aV.zero(); aX.zero();
-	const bool active = t < n_in && !(stop_gradient && stop_gradient[id]);
+	const bool active = valid && t < n_in && !(stop_gradient && stop_gradient[id]);
 	if (active) {
 		const float4 p0 = packed[3 * (size_t)t], p1 = packed[3 * (size_t)t + 1], p2 = packed[3 * (size_t)t + 2];
 		const float v[3] = {p0.w, p1.w, p2.w};
@@ -244,18 +257,18 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 		const float Av[3] = {Am[0] * v[0] + Am[1] * v[1] + Am[2] * v[2], Am[1] * v[0] + Am[3] * v[1] + Am[4] * v[2], Am[2] * v[0] + Am[4] * v[1] + Am[5] * v[2]};
 		const float gs = grid_gs(g);
 		const int cx = cell_coord(p0.x, g.lo[0], gs), cy = cell_coord(p0.y, g.lo[1], gs), cz = cell_coord(p0.z, g.lo[2], gs);
-		const float tau = g.tau, h_thr = P.h_thr;
+		const float tau = g.tau, q_thr = P.q_thr;
 		for (int pi = cx; pi <= cx + 2; pi++) {
 			for (int pj = cy; pj <= cy + 2; pj++) {
 				const int base = (pi * g.pdims[1] + pj) * g.pdims[2] + cz;
 				const int s = __ldg(scs + base), e = __ldg(scs + base + 3);
-				for (int k = s; k < e; k++) {
+				for (int k = s + lane; k < e; k += LPG) {
 					const float4 r0 = __ldg(rec + (size_t)STRIDE * k);
 					const float d[3] = {r0.x - p0.x, r0.y - p0.y, r0.z - p0.z};
 					const float w[3] = {Am[0] * d[0] + Am[1] * d[1] + Am[2] * d[2], Am[1] * d[0] + Am[3] * d[1] + Am[4] * d[2], Am[2] * d[0] + Am[4] * d[1] + Am[5] * d[2]};
-					const float h = -.5f * (d[0] * w[0] + d[1] * w[1] + d[2] * w[2]);
-					if (h >= h_thr) {
-						const float gg = __expf(h), gm = gg - tau;
+					const float q = d[0] * w[0] + d[1] * w[1] + d[2] * w[2];
+					if (q <= q_thr) {
+						const float gg = ex2_approx(q * kNegHalfLog2e), gm = gg - tau;
 						const float dd[6] = {d[0] * d[0], d[0] * d[1], d[0] * d[2], d[1] * d[1], d[1] * d[2], d[2] * d[2]};
 						int o = 1;
 						if (HAS_VOR) {
@@ -294,6 +307,12 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 			}
 		}
 	}
+	if (LPG > 1) {
+		if (HAS_DIR) acc12_reduce<LPG>(aD);
+		if (HAS_VOR) acc12_reduce<LPG>(aV);
+		if (HAS_DIV) acc12_reduce<LPG>(aX);
+		if (!valid || lane != 0) return;
+	}
 	// original-id order, set-major
 	const Acc12 *sets[3] = {&aD, &aV, &aX};
 	const bool has[3] = {HAS_DIR, HAS_VOR, HAS_DIV};
@@ -329,37 +348,48 @@ __device__ __forceinline__ void pair_accum2(Acc7 &acc, const float a[2], const f
 	acc.G[2] += hc * d[1] * d[1] + hg * (2.f * t[1] * d[1]);
 }
 
-template <bool HAS_DIR, bool HAS_VOR, bool HAS_DIV>
+template <int LPG>
+__device__ __forceinline__ void acc7_reduce(Acc7 &a)
+{
+	a.dv[0] = lane_sum<LPG>(a.dv[0]); a.dv[1] = lane_sum<LPG>(a.dv[1]);
+	a.dm[0] = lane_sum<LPG>(a.dm[0]); a.dm[1] = lane_sum<LPG>(a.dm[1]);
+	a.G[0] = lane_sum<LPG>(a.G[0]); a.G[1] = lane_sum<LPG>(a.G[1]); a.G[2] = lane_sum<LPG>(a.G[2]);
+}
+
+template <bool HAS_DIR, bool HAS_VOR, bool HAS_DIV, int LPG>
 __global__ void __launch_bounds__(GA_THREADS) gather2d_kernel(EvalParams P, const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_id,
 							      const float4 *__restrict__ packed, int N, const int32_t *__restrict__ scs,
 							      const float4 *__restrict__ rec, const int32_t *__restrict__ stop_gradient, float *__restrict__ acc_out)
 {
 	constexpr int STRIDE = 1 + (HAS_VOR ? 1 : 0) + (HAS_DIR ? 2 : 0);
-	int t = blockIdx.x * GA_THREADS + threadIdx.x;
-	if (t >= N) return;
+	const int gt = blockIdx.x * GA_THREADS + threadIdx.x;
+	const int tq = gt / LPG, lane = gt % LPG;
+	if (LPG == 1 && tq >= N) return;
+	const bool valid = tq < N;
+	const int t = valid ? tq : N - 1;
 	const Grid &g = P.g;
 	const int id = sorted_id[t];
 	const int n_in = cell_start[g.ncell];
 	Acc7 aD, aV, aX;
 	aD.zero(); aV.zero(); aX.zero();
-	const bool active = t < n_in && !(stop_gradient && stop_gradient[id]);
+	const bool active = valid && t < n_in && !(stop_gradient && stop_gradient[id]);
 	if (active) {
 		const float4 p0 = packed[2 * (size_t)t], p1 = packed[2 * (size_t)t + 1];
 		const float v[2] = {p0.z, p0.w};
 		const float Am[3] = {p1.x, p1.y, p1.z};
 		const float gs = grid_gs(g);
 		const int cx = cell_coord(p0.x, g.lo[0], gs), cy = cell_coord(p0.y, g.lo[1], gs);
-		const float tau = g.tau, h_thr = P.h_thr;
+		const float tau = g.tau, q_thr = P.q_thr;
 		for (int pi = cx; pi <= cx + 2; pi++) {
 			const int base = pi * g.pdims[1] + cy;
 			const int s = __ldg(scs + base), e = __ldg(scs + base + 3);
-			for (int k = s; k < e; k++) {
+			for (int k = s + lane; k < e; k += LPG) {
 				const float4 r0 = __ldg(rec + (size_t)STRIDE * k);
 				const float d[2] = {r0.x - p0.x, r0.y - p0.y};
 				const float w[2] = {Am[0] * d[0] + Am[1] * d[1], Am[1] * d[0] + Am[2] * d[1]};
-				const float h = -.5f * (d[0] * w[0] + d[1] * w[1]);
-				if (h >= h_thr) {
-					const float gg = __expf(h), gm = gg - tau;
+				const float q = d[0] * w[0] + d[1] * w[1];
+				if (q <= q_thr) {
+					const float gg = ex2_approx(q * kNegHalfLog2e), gm = gg - tau;
 					int o = 1;
 					if (HAS_VOR) {
 						const float s_ = __ldg(rec + (size_t)STRIDE * k + o).x;
@@ -387,6 +417,12 @@ __global__ void __launch_bounds__(GA_THREADS) gather2d_kernel(EvalParams P, cons
 				}
 			}
 		}
+	}
+	if (LPG > 1) {
+		if (HAS_DIR) acc7_reduce<LPG>(aD);
+		if (HAS_VOR) acc7_reduce<LPG>(aV);
+		if (HAS_DIV) acc7_reduce<LPG>(aX);
+		if (!valid || lane != 0) return;
 	}
 	const Acc7 *sets[3] = {&aD, &aV, &aX};
 	const bool has[3] = {HAS_DIR, HAS_VOR, HAS_DIV};
@@ -464,19 +500,26 @@ static int launch_adjoint(bool dir, bool vor, const AdjIn &in, int Q, const int3
 	return 0;
 }
 
-#define GATHER_DISPATCH(KERNEL, ...)                                                                       \
-	do {                                                                                               \
-		int sel = (dir ? 4 : 0) | (vor ? 2 : 0) | (dv ? 1 : 0);                                   \
-		switch (sel) {                                                                             \
-		case 1: KERNEL<false, false, true><<<blocks, GA_THREADS, 0, st>>>(__VA_ARGS__); break;     \
-		case 2: KERNEL<false, true, false><<<blocks, GA_THREADS, 0, st>>>(__VA_ARGS__); break;     \
-		case 3: KERNEL<false, true, true><<<blocks, GA_THREADS, 0, st>>>(__VA_ARGS__); break;      \
-		case 4: KERNEL<true, false, false><<<blocks, GA_THREADS, 0, st>>>(__VA_ARGS__); break;     \
-		case 5: KERNEL<true, false, true><<<blocks, GA_THREADS, 0, st>>>(__VA_ARGS__); break;      \
-		case 6: KERNEL<true, true, false><<<blocks, GA_THREADS, 0, st>>>(__VA_ARGS__); break;      \
-		case 7: KERNEL<true, true, true><<<blocks, GA_THREADS, 0, st>>>(__VA_ARGS__); break;       \
-		default: break;                                                                            \
-		}                                                                                          \
+#define GATHER_CASE(KERNEL, A, B, C_, LN, ...) KERNEL<A, B, C_, LN><<<blocks, GA_THREADS, 0, st>>>(__VA_ARGS__)
+#define GATHER_DISPATCH_L(KERNEL, LN, ...)                                          \
+	do {                                                                        \
+		int sel = (dir ? 4 : 0) | (vor ? 2 : 0) | (dv ? 1 : 0);            \
+		switch (sel) {                                                      \
+		case 1: GATHER_CASE(KERNEL, false, false, true, LN, __VA_ARGS__); break;   \
+		case 2: GATHER_CASE(KERNEL, false, true, false, LN, __VA_ARGS__); break;   \
+		case 3: GATHER_CASE(KERNEL, false, true, true, LN, __VA_ARGS__); break;    \
+		case 4: GATHER_CASE(KERNEL, true, false, false, LN, __VA_ARGS__); break;   \
+		case 5: GATHER_CASE(KERNEL, true, false, true, LN, __VA_ARGS__); break;    \
+		case 6: GATHER_CASE(KERNEL, true, true, false, LN, __VA_ARGS__); break;    \
+		case 7: GATHER_CASE(KERNEL, true, true, true, LN, __VA_ARGS__); break;     \
+		default: break;                                                     \
+		}                                                                   \
+	} while (0)
+#define GATHER_DISPATCH(KERNEL, ...)                                                \
+	do {                                                                        \
+		if (lpg == 1) GATHER_DISPATCH_L(KERNEL, 1, __VA_ARGS__);            \
+		else if (lpg == 8) GATHER_DISPATCH_L(KERNEL, 8, __VA_ARGS__);       \
+		else GATHER_DISPATCH_L(KERNEL, 32, __VA_ARGS__);                    \
 	} while (0)
 
 extern "C" int gsr_backward_gather(const gsr_grid_desc *d, const int32_t *cell_start, const int32_t *sorted_id, const float *packed, int64_t N,
@@ -535,13 +578,16 @@ extern "C" int gsr_backward_gather(const gsr_grid_desc *d, const int32_t *cell_s
 	if (cfg->loss_partials && Q > 0) {
 		AdjIn lin = {x, val, grad, cfg->ref_val, cfg->normals, cfg->normal_ref, cfg->ref_grad, cfg->ref_vor, cfg->ref_hel};
 		int lb = (int)((Q + ADJ_THREADS - 1) / ADJ_THREADS);
+		g_launches += 1;
 		if (D == 3) loss_partials_kernel<3><<<lb, ADJ_THREADS, 0, st>>>(lin, (int)Q, cfg->loss_partials);
 		else loss_partials_kernel<2><<<lb, ADJ_THREADS, 0, st>>>(lin, (int)Q, cfg->loss_partials);
 	}
-	EvalParams P;
-	P.g = g;
-	P.h_thr = host_h_threshold(g.tau);
-	int blocks = (int)((N + GA_THREADS - 1) / GA_THREADS);
+	EvalParams P = make_params(g);
+	// lanes per Gaussian: by the amount of parallelism N offers, and more when there are many samples per Gaussian
+	int lpg = pick_lanes(N);
+	if (lpg == 1 && Q >= 8 * N) lpg = 8;
+	int blocks = (int)((N * lpg + GA_THREADS - 1) / GA_THREADS);
+	g_launches += Q > 0 ? 2 : 1;
 	if (Q > 0) {
 		int rc = (D == 3) ? launch_adjoint<3>(dir, vor, in, (int)Q, perm, w, rec, st) : launch_adjoint<2>(dir, vor, in, (int)Q, perm, w, rec, st);
 		if (rc) return rc;
@@ -569,6 +615,7 @@ extern "C" int gsr_sample_losses(const gsr_grid_desc *d, int64_t Q, const float 
 	if (g.D == 3) loss_partials_kernel<3><<<lb, ADJ_THREADS, 0, st>>>(lin, (int)Q, partials);
 	else loss_partials_kernel<2><<<lb, ADJ_THREADS, 0, st>>>(lin, (int)Q, partials);
 	loss_final_kernel<<<1, 256, 0, st>>>(partials, lb, sums);
+	g_launches += 2;
 	GSR_CHECK_LAUNCH();
 	return GSR_OK;
 }
@@ -587,6 +634,7 @@ extern "C" int gsr_backward_epilogue(const gsr_grid_desc *d, const float *scalin
 		}
 	cudaStream_t st = (cudaStream_t)stream;
 	int blocks = (int)((N + 127) / 128);
+	g_launches += 1;
 	if (g.D == 3) epilogue_kernel<3><<<blocks, 128, 0, st>>>(scalings, rotations, (int)N, acc, sets_mask, o);
 	else epilogue_kernel<2><<<blocks, 128, 0, st>>>(scalings, rotations, (int)N, acc, sets_mask, o);
 	GSR_CHECK_LAUNCH();

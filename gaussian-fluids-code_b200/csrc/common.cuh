@@ -6,7 +6,11 @@
 
 #define GSR_CHECK_LAUNCH() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
+#include <atomic>
+
 namespace gsr {
+
+extern std::atomic<unsigned long long> g_launches;	// kernels launched by this library (misc.cu)
 
 constexpr int kSMs = 148;	// B200
 

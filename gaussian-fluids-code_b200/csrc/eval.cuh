@@ -5,24 +5,47 @@
 //
 // Candidates come from the 27 (9) cells around the point's cell.  Because the hash is cell-sorted and the
 // cell key is row-major with z (y in 2D) fastest, the stencil is 9 (3) CONTIGUOUS runs of packed records.
-// Per candidate: 3 FADD + 9 FFMA/FMUL (w = A d) + 3 (q = d.w) + 1 FMUL + compare  = 24 flop;
-// per accepted pair: 1 MUFU.EX2 (+1 FMUL) + 28 flop.
+// Per candidate: 3 FADD + 9 FFMA/FMUL (w = A d) + 3 (q = d.w) + compare  = 24 flop;
+// per accepted pair: 1 FMUL + 1 MUFU.EX2 + 28 flop.
+//
+// LANES lanes cooperate on one point (LANES = 1: one thread per point — the throughput shape for large Q;
+// LANES = 8 / 32: the lanes stride through each run and the 12 partial sums are combined with xor-shuffles —
+// the latency shape for the reference's own sizes, where Q is a few thousand points).
 #pragma once
 #include "common.cuh"
 
 namespace gsr {
 
-// Acceptance is decided on h = -q/2 against h_thr = min{h : expf(h) >= tau} (computed on the host with
-// libm's expf), which is equivalent to the reference's `exp(h) >= tau` for a monotone expf and keeps the
-// MUFU off the rejected 85 % of the candidates.
+// Acceptance is decided on q = d^T Sigma^-1 d against q_thr = -2 h_thr, h_thr = min{h : expf(h) >= tau}
+// (bisection with libm's expf on the host).  Scaling by -1/2 is exact, so `q <= q_thr` is the reference's
+// `exp(-q/2) >= tau` for a monotone expf, and the MUFU stays off the rejected ~85 % of the candidates.
 struct EvalParams {
 	Grid g;
 	float h_thr;
+	float q_thr;
 };
 
-template <bool NEED_GRAD>
+constexpr float kNegHalfLog2e = -0.72134752044448170368f;	// exp(-q/2) = 2^(q * kNegHalfLog2e)
+
+__device__ __forceinline__ float ex2_approx(float x)
+{
+	float y;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+
+template <int LANES>
+__device__ __forceinline__ float lane_sum(float v)
+{
+#pragma unroll
+	for (int o = LANES / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// `lane` in [0, LANES).  With LANES > 1 every lane of the warp must call this (shuffles), valid or not.
+template <bool NEED_GRAD, int LANES>
 __device__ __forceinline__ void eval_point3(const EvalParams &P, const int32_t *__restrict__ cell_start, const float4 *__restrict__ packed,
-					    float x, float y, float z, float u[3], float G[9])
+					    float x, float y, float z, int lane, float u[3], float G[9])
 {
 	const Grid &g = P.g;
 	u[0] = u[1] = u[2] = 0.f;
@@ -33,40 +56,49 @@ __device__ __forceinline__ void eval_point3(const EvalParams &P, const int32_t *
 	const float gs = grid_gs(g);
 	const int cx = cell_coord(x, g.lo[0], gs), cy = cell_coord(y, g.lo[1], gs), cz = cell_coord(z, g.lo[2], gs);
 	const int zlo = max(cz - 1, 0), zhi = min(cz + 1, g.dims[2] - 1);
-	if (zlo > zhi) return;
-	const float tau = g.tau, h_thr = P.h_thr;
-	for (int gi = max(cx - 1, 0); gi <= min(cx + 1, g.dims[0] - 1); gi++) {
-		for (int gj = max(cy - 1, 0); gj <= min(cy + 1, g.dims[1] - 1); gj++) {
-			const int base = (gi * g.dims[1] + gj) * g.dims[2];
-			const int s = __ldg(cell_start + base + zlo), e = __ldg(cell_start + base + zhi + 1);
-			for (int t = s; t < e; t++) {
-				const float4 p0 = __ldg(packed + 3 * t), p1 = __ldg(packed + 3 * t + 1), p2 = __ldg(packed + 3 * t + 2);
-				const float dx = x - p0.x, dy = y - p0.y, dz = z - p0.z;
-				const float wx = p1.x * dx + p1.y * dy + p1.z * dz;
-				const float wy = p1.y * dx + p2.x * dy + p2.y * dz;
-				const float wz = p1.z * dx + p2.y * dy + p2.z * dz;
-				const float h = -.5f * (dx * wx + dy * wy + dz * wz);
-				if (h >= h_thr) {
-					const float gs_ = __expf(h);
-					const float gm = gs_ - tau;
-					u[0] = fmaf(p0.w, gm, u[0]);
-					u[1] = fmaf(p1.w, gm, u[1]);
-					u[2] = fmaf(p2.w, gm, u[2]);
-					if (NEED_GRAD) {
-						const float ax = -gs_ * wx, ay = -gs_ * wy, az = -gs_ * wz;
-						G[0] = fmaf(p0.w, ax, G[0]); G[1] = fmaf(p0.w, ay, G[1]); G[2] = fmaf(p0.w, az, G[2]);
-						G[3] = fmaf(p1.w, ax, G[3]); G[4] = fmaf(p1.w, ay, G[4]); G[5] = fmaf(p1.w, az, G[5]);
-						G[6] = fmaf(p2.w, ax, G[6]); G[7] = fmaf(p2.w, ay, G[7]); G[8] = fmaf(p2.w, az, G[8]);
+	const float tau = g.tau, q_thr = P.q_thr;
+	if (zlo <= zhi) {
+		for (int gi = max(cx - 1, 0); gi <= min(cx + 1, g.dims[0] - 1); gi++) {
+			for (int gj = max(cy - 1, 0); gj <= min(cy + 1, g.dims[1] - 1); gj++) {
+				const int base = (gi * g.dims[1] + gj) * g.dims[2];
+				const int s = __ldg(cell_start + base + zlo), e = __ldg(cell_start + base + zhi + 1);
+				for (int t = s + lane; t < e; t += LANES) {
+					const float4 p0 = __ldg(packed + 3 * t), p1 = __ldg(packed + 3 * t + 1), p2 = __ldg(packed + 3 * t + 2);
+					const float dx = x - p0.x, dy = y - p0.y, dz = z - p0.z;
+					const float wx = p1.x * dx + p1.y * dy + p1.z * dz;
+					const float wy = p1.y * dx + p2.x * dy + p2.y * dz;
+					const float wz = p1.z * dx + p2.y * dy + p2.z * dz;
+					const float q = dx * wx + dy * wy + dz * wz;
+					if (q <= q_thr) {
+						const float gs_ = ex2_approx(q * kNegHalfLog2e);
+						const float gm = gs_ - tau;
+						u[0] = fmaf(p0.w, gm, u[0]);
+						u[1] = fmaf(p1.w, gm, u[1]);
+						u[2] = fmaf(p2.w, gm, u[2]);
+						if (NEED_GRAD) {
+							const float ax = -gs_ * wx, ay = -gs_ * wy, az = -gs_ * wz;
+							G[0] = fmaf(p0.w, ax, G[0]); G[1] = fmaf(p0.w, ay, G[1]); G[2] = fmaf(p0.w, az, G[2]);
+							G[3] = fmaf(p1.w, ax, G[3]); G[4] = fmaf(p1.w, ay, G[4]); G[5] = fmaf(p1.w, az, G[5]);
+							G[6] = fmaf(p2.w, ax, G[6]); G[7] = fmaf(p2.w, ay, G[7]); G[8] = fmaf(p2.w, az, G[8]);
+						}
 					}
 				}
 			}
 		}
 	}
+	if (LANES > 1) {
+#pragma unroll
+		for (int k = 0; k < 3; k++) u[k] = lane_sum<LANES>(u[k]);
+		if (NEED_GRAD) {
+#pragma unroll
+			for (int k = 0; k < 9; k++) G[k] = lane_sum<LANES>(G[k]);
+		}
+	}
 }
 
-template <bool NEED_GRAD>
+template <bool NEED_GRAD, int LANES>
 __device__ __forceinline__ void eval_point2(const EvalParams &P, const int32_t *__restrict__ cell_start, const float4 *__restrict__ packed,
-					    float x, float y, float u[2], float G[4])
+					    float x, float y, int lane, float u[2], float G[4])
 {
 	const Grid &g = P.g;
 	u[0] = u[1] = 0.f;
@@ -74,27 +106,36 @@ __device__ __forceinline__ void eval_point2(const EvalParams &P, const int32_t *
 	const float gs = grid_gs(g);
 	const int cx = cell_coord(x, g.lo[0], gs), cy = cell_coord(y, g.lo[1], gs);
 	const int ylo = max(cy - 1, 0), yhi = min(cy + 1, g.dims[1] - 1);
-	if (ylo > yhi) return;
-	const float tau = g.tau, h_thr = P.h_thr;
-	for (int gi = max(cx - 1, 0); gi <= min(cx + 1, g.dims[0] - 1); gi++) {
-		const int base = gi * g.dims[1];
-		const int s = __ldg(cell_start + base + ylo), e = __ldg(cell_start + base + yhi + 1);
-		for (int t = s; t < e; t++) {
-			const float4 p0 = __ldg(packed + 2 * t), p1 = __ldg(packed + 2 * t + 1);
-			const float dx = x - p0.x, dy = y - p0.y;
-			const float wx = p1.x * dx + p1.y * dy, wy = p1.y * dx + p1.z * dy;
-			const float h = -.5f * (dx * wx + dy * wy);
-			if (h >= h_thr) {
-				const float gs_ = __expf(h);
-				const float gm = gs_ - tau;
-				u[0] = fmaf(p0.z, gm, u[0]);
-				u[1] = fmaf(p0.w, gm, u[1]);
-				if (NEED_GRAD) {
-					const float ax = -gs_ * wx, ay = -gs_ * wy;
-					G[0] = fmaf(p0.z, ax, G[0]); G[1] = fmaf(p0.z, ay, G[1]);
-					G[2] = fmaf(p0.w, ax, G[2]); G[3] = fmaf(p0.w, ay, G[3]);
+	const float tau = g.tau, q_thr = P.q_thr;
+	if (ylo <= yhi) {
+		for (int gi = max(cx - 1, 0); gi <= min(cx + 1, g.dims[0] - 1); gi++) {
+			const int base = gi * g.dims[1];
+			const int s = __ldg(cell_start + base + ylo), e = __ldg(cell_start + base + yhi + 1);
+			for (int t = s + lane; t < e; t += LANES) {
+				const float4 p0 = __ldg(packed + 2 * t), p1 = __ldg(packed + 2 * t + 1);
+				const float dx = x - p0.x, dy = y - p0.y;
+				const float wx = p1.x * dx + p1.y * dy, wy = p1.y * dx + p1.z * dy;
+				const float q = dx * wx + dy * wy;
+				if (q <= q_thr) {
+					const float gs_ = ex2_approx(q * kNegHalfLog2e);
+					const float gm = gs_ - tau;
+					u[0] = fmaf(p0.z, gm, u[0]);
+					u[1] = fmaf(p0.w, gm, u[1]);
+					if (NEED_GRAD) {
+						const float ax = -gs_ * wx, ay = -gs_ * wy;
+						G[0] = fmaf(p0.z, ax, G[0]); G[1] = fmaf(p0.z, ay, G[1]);
+						G[2] = fmaf(p0.w, ax, G[2]); G[3] = fmaf(p0.w, ay, G[3]);
+					}
 				}
 			}
+		}
+	}
+	if (LANES > 1) {
+		u[0] = lane_sum<LANES>(u[0]);
+		u[1] = lane_sum<LANES>(u[1]);
+		if (NEED_GRAD) {
+#pragma unroll
+			for (int k = 0; k < 4; k++) G[k] = lane_sum<LANES>(G[k]);
 		}
 	}
 }
@@ -115,5 +156,17 @@ __device__ __forceinline__ void mm2(const float *A, const float *B, float *C)
 }
 
 float host_h_threshold(float tau);	// defined in eval.cu
+
+inline EvalParams make_params(const Grid &g)
+{
+	EvalParams P;
+	P.g = g;
+	P.h_thr = host_h_threshold(g.tau);
+	P.q_thr = -2.f * P.h_thr;	// exact
+	return P;
+}
+
+// lanes per point (or per Gaussian) for a problem of n items: keep >= ~250k threads in flight when n is small
+inline int pick_lanes(int64_t n) { return n >= (1 << 18) ? 1 : (n >= (1 << 14) ? 8 : 32); }
 
 }  // namespace gsr

@@ -305,6 +305,7 @@ static int radix_sort_index(SortWs &s, int n, uint32_t max_key, uint32_t *out_va
 	if (n <= SB_MAX_N) {
 		size_t sm = sizeof(uint32_t) * (SB_WARPS * 256 + 256);
 		rs_single_block_kernel<<<1, SB_THREADS, sm, st>>>(s.keys0, n, passes, s.kA, vA, s.kB, vB);
+		g_launches += 1;
 		GSR_CHECK_LAUNCH();
 	} else {
 		const uint32_t *kin = s.keys0, *vin = nullptr;
@@ -313,6 +314,7 @@ static int radix_sort_index(SortWs &s, int n, uint32_t max_key, uint32_t *out_va
 			rs_hist_kernel<<<s.nblocks, RS_THREADS, 0, st>>>(kin, n, 8 * p, s.hist, s.nblocks);
 			rs_scan_kernel<<<1, 1024, 0, st>>>(s.hist, 256 * s.nblocks);
 			rs_scatter_kernel<<<s.nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, 8 * p, s.hist, s.nblocks);
+			g_launches += 3;
 			GSR_CHECK_LAUNCH();
 			kin = kout;
 			vin = vout;
@@ -459,6 +461,7 @@ extern "C" int gsr_build_grid(const gsr_grid_desc *d, const float *positions, in
 		int rc = radix_sort_index(s, n, (uint32_t)g.ncell, (uint32_t *)sorted_id, &ks, st);
 		if (rc) return rc;
 	}
+	g_launches += (n > 0 ? 2 : 1) + ((grid_cnt || grid_offset) ? 1 : 0);
 	cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.ncell, cell_start);
 	if (grid_cnt || grid_offset) ref_format_kernel<<<(g.ncell + 255) / 256, 256, 0, st>>>(cell_start, g.ncell, grid_cnt, grid_offset);
 	GSR_CHECK_LAUNCH();
@@ -482,6 +485,7 @@ extern "C" int gsr_bin_samples(const gsr_grid_desc *d, const float *x, int64_t Q
 		int rc = radix_sort_index(s, n, (uint32_t)g.pcell, (uint32_t *)perm, &ks, st);
 		if (rc) return rc;
 	}
+	g_launches += (n > 0 ? 1 : 0) + (sample_cell_start ? 1 : 0);
 	if (sample_cell_start) {
 		cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.pcell, sample_cell_start);
 		GSR_CHECK_LAUNCH();
@@ -497,6 +501,7 @@ extern "C" int gsr_pack_gaussians(const gsr_grid_desc *d, const float *positions
 	if (N == 0) return GSR_OK;
 	cudaStream_t st = (cudaStream_t)stream;
 	int n = (int)N;
+	g_launches += 1;
 	if (g.D == 3) pack3d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed);
 	else pack2d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed);
 	GSR_CHECK_LAUNCH();
@@ -507,6 +512,7 @@ extern "C" int gsr_min_scaling(const float *scalings, int64_t count, float *out_
 {
 	if (!out_min || count < 0) return GSR_EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
+	g_launches += count > 0 ? 2 : 1;
 	min_init_kernel<<<1, 1, 0, st>>>(out_min);
 	if (count > 0) {
 		int blocks = (int)((count + 1023) / 1024);

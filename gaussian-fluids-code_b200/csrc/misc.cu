@@ -4,6 +4,8 @@
 
 namespace gsr {
 
+std::atomic<unsigned long long> g_launches{0};
+
 constexpr int PK_CHAINS = 8;
 
 __global__ void __launch_bounds__(1024) peak_fma_kernel(int iters, float a, float b, float *out)
@@ -84,5 +86,7 @@ extern "C" int gsr_peak_mufu(int iters, double *tops, void *stream)
 	if (tops) *tops = (double)blocks * threads * (double)iters * PK_CHAINS / (ms * 1e-3) / 1e12;
 	return rc;
 }
+
+extern "C" uint64_t gsr_launch_count(void) { return g_launches.load(); }
 
 extern "C" const char *gsr_version(void) { return "gsr_b200 0.1.0 (sm_100a)"; }

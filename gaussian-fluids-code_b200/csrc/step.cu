@@ -382,6 +382,7 @@ extern "C" int gsr_step(const gsr_step_cfg *cfg, int64_t N, float *positions, fl
 		stepB_kernel<2><<<nblk, ST_THREADS, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, state);
 	}
 	stepS_kernel<<<1, 1, 0, st>>>(*cfg, state, nullptr);
+	g_launches += 4;
 	GSR_CHECK_LAUNCH();
 	return GSR_OK;
 }

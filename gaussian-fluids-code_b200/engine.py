@@ -147,12 +147,20 @@ class HashEngine:
 											  ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(perm, torch.int32), C.c_float(dt), dom,
 											  ptr(ref_vor), ptr(ref_hel, allow_none=True), stream()), 'gsr_advected_vorticity')
 
+	def count_pairs(self, x, counts, evals=1, with_accepted=False):
+		"""work census: counts (device int64[2]) += evals * (C(x), P(x)); P only when with_accepted"""
+		x = self._x(x)
+		one = torch.zeros(2, dtype=torch.int64, device=self.device)
+		check(self.lib.gsr_count_pairs(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True) if with_accepted else None,
+									   ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(one, torch.int64), stream()), 'gsr_count_pairs')
+		counts.add_(one, alpha=int(evals))
+
 	def mark_neighbors(self, x, mark):
 		x = self._x(x)
 		check(self.lib.gsr_mark_neighbors(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
 										  ptr(self.packed, align16=True), ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(mark, torch.int32), stream()), 'gsr_mark_neighbors')
 
-	def backward_gather(self, x, perm, scs, val, grad, weights, refs, stop_gradient, Q_norm=None, tag='acc', want_losses=False):
+	def backward_gather(self, x, perm, scs, val, grad, weights, refs, stop_gradient, Q_norm=None, tag='acc', want_losses=False, acc=None, loss_partials=None):
 		"""returns (acc, sets_mask); acc is (3, N, 12|7) in original Gaussian order"""
 		x = self._x(x)
 		Q = x.shape[0]
@@ -172,13 +180,18 @@ class HashEngine:
 			keep.append(stop_gradient)
 			cfg.stop_gradient = ptr(stop_gradient, torch.int32, name='stop_gradient').value
 		self.last_loss_partials = None
-		if want_losses:
+		if want_losses or loss_partials is not None:
 			nblk = self.lib.gsr_loss_blocks(C.c_int64(Q))
-			lp = self.scratch.typed('lp_' + tag, (nblk, 8), torch.float32)
+			lp = loss_partials if loss_partials is not None else self.scratch.typed('lp_' + tag, (nblk, 8), torch.float32)
+			if lp.numel() != nblk * 8:
+				raise _lib.GsrError('loss_partials must hold gsr_loss_blocks(Q) * 8 floats')
 			cfg.loss_partials = ptr(lp).value
 			self.last_loss_partials = (lp, nblk)
 		AF = 12 if self.D == 3 else 7
-		acc = self.scratch.typed(tag, (GSR_NSETS, self.N, AF), torch.float32)
+		if acc is None:
+			acc = self.scratch.typed(tag, (GSR_NSETS, self.N, AF), torch.float32)
+		elif acc.numel() != GSR_NSETS * self.N * AF:
+			raise _lib.GsrError('acc must hold 3 * N * GSR_ACC_FLOATS floats')
 		nbytes = self.lib.gsr_backward_ws_bytes(C.byref(self.desc), C.c_int64(self.N), C.c_int64(Q))
 		ws = self.scratch.get('adjoint', nbytes)
 		mask = C.c_int(0)

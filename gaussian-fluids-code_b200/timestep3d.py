@@ -1,0 +1,177 @@
+"""
+The fixed-work 3D time step used for measurement: the work of one `advance.py` frame with the iteration
+count pinned to the reference's minimum, because the reference's own count is data dependent:
+
+    clone (copy, no split)  ->  advect (RK4 positions only, Q = N)
+    ->  `iters` (600) project iterations, each { RK4 pull-back reference (5 evaluations), forward + backward with the
+        vorticity / helicity / divergence losses on Q = N samples, boundary forward + backward on 8192 samples,
+        PCGrad + regularisers + Adam x4 + scheduler, hash rebuild }
+    ->  a test pass { RK4 pull-back + forward on the test_res^3 lattice } every 100 iterations
+    ->  swap, two forward passes on the lattice (the |vorticity| and divergence fields the reference writes as VTI).
+
+Multi-GPU (one process per GPU): sample points are sharded — every rank draws its own N training and 8192 boundary
+samples (global Q = world * N, the loss normalisers use the global counts) and takes a 1/world slice of the lattice;
+Gaussian parameters, hash and optimiser state are replicated; ONE NCCL all-reduce per iteration sums the compact
+gradient accumulators and the loss partial sums, after which every rank runs the identical fused step, so the
+replicas stay bit-identical without a broadcast.
+"""
+import torch
+
+from . import advance3d, gsr3d
+from .init_cond3d import sample_on_box
+from .synth import make_fast3d, synthetic_field
+
+
+class Census:
+	"""device-side counter of candidate visits (the benchmark's unit of work)"""
+
+	def __init__(self, device):
+		self.c = torch.zeros(2, dtype=torch.int64, device=device)	# [candidate visits C, accepted pairs P]
+
+	def value(self):
+		c = self.c.tolist()
+		return int(c[0]), int(c[1])
+
+
+class ShardedProjector(advance3d.FusedProjector):
+	"""FusedProjector whose accumulators and loss partials live in one flat buffer that is all-reduced once per iteration"""
+
+	def __init__(self, gv, reference_field, boundary_lambda, Q, Qb, world=1, patience=50):
+		super().__init__(gv, reference_field, boundary_lambda, patience=patience)
+		e = gv._engine
+		self.world = world
+		self.Q, self.Qb = Q, Qb
+		N = gv.N
+		nblk, nblkb = e.lib.gsr_loss_blocks(Q), e.lib.gsr_loss_blocks(Qb)
+		self.flat = torch.zeros(3 * N * 12 + (nblk + nblkb) * 8, dtype=torch.float32, device=gsr3d.device)
+		self.acc = self.flat[:3 * N * 12].view(3, N, 12)	# set 0: boundary (direct), sets 1, 2: vorticity / divergence
+		self.lp = self.flat[3 * N * 12:3 * N * 12 + nblk * 8].view(nblk, 8)
+		self.lpb = self.flat[3 * N * 12 + nblk * 8:].view(nblkb, 8)
+		self.nblk, self.nblkb = nblk, nblkb
+
+	def iterate(self, data, boundary=None, census=None):
+		gv, e = self.gv, self.gv._engine
+		cur = self.ref.velocity_field
+		Q, Qg = data.shape[0], data.shape[0] * self.world
+		perm, scs = e.bin_samples(data, True)
+		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
+		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=perm)
+		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
+		e.forward(data, val, grad, accumulate=False, perm=perm)
+		_, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
+									{'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, Q_norm=Qg, acc=self.acc, loss_partials=self.lp)
+		srcs = [(self.lp, self.nblk, [self.w['vor'] / Qg, 0., self.w['div'] / Qg, 0., 0., 0., 0., 0.])]
+		if census is not None:
+			cur._engine.count_pairs(data, census.c, 5, True)
+			e.count_pairs(data, census.c, 2, True)
+		if boundary is not None:
+			bdata, bnormal = boundary
+			Qb, Qbg = bdata.shape[0], bdata.shape[0] * self.world
+			perm_b, scs_b = e.bin_samples(bdata, True, tag='b')
+			valb = self._tmp('valb', (Qb, 3))
+			e.forward(bdata, valb, None, accumulate=False, perm=perm_b)
+			_, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
+										  {'normals': bnormal}, None, Q_norm=Qbg, acc=self.acc, loss_partials=self.lpb)
+			mask |= mask_b
+			srcs.append((self.lpb, self.nblkb, [0., 0., 0., self.boundary_lambda / Qbg, 0., 0., 0., 0.]))
+			if census is not None:
+				e.count_pairs(bdata, census.c, 2, True)
+		if self.world > 1:
+			torch.distributed.all_reduce(self.flat)
+		self.stepper.step(gv._params(), self.acc, mask, loss_srcs=srcs)
+		self._rebuild()
+
+
+class LeapfrogTimestep:
+	def __init__(self, n=10, dt=.02, iters=600, Qb=8192, test_res=128, boundary_lambda=10., rank=0, world=1, seed=42, check_iter=100, use_graph=True):
+		self.n, self.dt, self.iters, self.Qb, self.test_res, self.boundary_lambda = n, dt, iters, Qb, test_res, boundary_lambda
+		self.rank, self.world, self.check_iter, self.use_graph = rank, world, check_iter, use_graph
+		P, S, R, V, mgs, _ = synthetic_field(n, seed)
+		self.params0 = (P, S, R, V)
+		self.cur = make_fast3d(P, S, R, V, 5e-3, mgs)
+		self.new = make_fast3d(P, S, R, V, 5e-3, mgs)
+		self.N = self.cur.N
+		dev = gsr3d.device
+		lattice = gsr3d.get_grid_points(0., 1., 0., 1., 0., 1., test_res, test_res, test_res)
+		per = (lattice.shape[0] + world - 1) // world
+		self.lattice = lattice[rank * per:(rank + 1) * per].contiguous()	# this rank's slice of the test / output lattice
+		torch.cuda.manual_seed(1000 + rank)	# every rank draws its own sample shard (default generator: CUDA-graph safe)
+		self.last_test = None
+		self.graph_launches = 0
+
+	def reset(self, params=None):
+		"""restore both fields to the given (default: initial) parameters — used between timed steps and by the e2e path"""
+		P, S, R, V = params if params is not None else [torch.as_tensor(a) for a in self.params0]
+		with torch.no_grad():
+			for f in (self.cur, self.new):
+				for t, src in zip((f.positions, f.scalings, f.rotations, f.values), (P, S, R, V)):
+					t.copy_(torch.as_tensor(src), non_blocking=True)
+				f.zero_grad()
+
+	def _samples(self):
+		return torch.rand((self.N, 3), device=gsr3d.device)
+
+	def _boundary(self):
+		# sample_on_box with this object's generator (same distribution as init_cond3d.sample_on_box)
+		dev = gsr3d.device
+		n = self.Qb
+		face = torch.randint(0, 6, (n,), device=dev)	# unit cube: the six faces have equal area
+		uvw = torch.rand((n, 3), device=dev)
+		axis, upper = face // 2, (face % 2).to(torch.float32)
+		onehot = torch.nn.functional.one_hot(axis, 3).to(torch.float32)
+		data = uvw * (1. - onehot) + onehot * upper[:, None]
+		normal = onehot * (1. - 2. * upper)[:, None]
+		return data.contiguous(), normal.contiguous()
+
+	def step(self, census=None):
+		cur, new = self.cur, self.new
+		# clone (no Gaussian is over-stretched in the synthetic field: the common path of 3D/advance.py:91-92)
+		with torch.no_grad():
+			for a, b in zip((new.positions, new.scalings, new.rotations, new.values), (cur.positions, cur.scalings, cur.rotations, cur.values)):
+				a.copy_(b)
+		new.zero_grad()
+		# advect
+		advance3d.advect_covector_field(new, cur, self.dt, new.x_min, new.x_max, new.y_min, new.y_max, new.z_min, new.z_max)
+		if census is not None:
+			cur._engine.count_pairs(new.positions.detach(), census.c, 4, True)
+		# project, fixed iteration count; the iteration is captured once into a CUDA graph and replayed
+		ref = advance3d.AdvectedCovectorField(cur, cur, self.dt, 0., 1., 0., 1., 0., 1.)
+		fp = ShardedProjector(new, ref, self.boundary_lambda, self.N, self.Qb, world=self.world)
+		body = lambda: fp.iterate(self._samples(), self._boundary() if self.boundary_lambda else None, None)
+		done = 0
+		graph = None
+		if self.use_graph and census is None:
+			side = torch.cuda.Stream()
+			side.wait_stream(torch.cuda.current_stream())
+			with torch.cuda.stream(side):
+				for _ in range(2):	# eager warm-up iterations (they count): sizes every scratch buffer
+					l0 = new._engine.lib.gsr_launch_count()
+					body()
+					per_iter = new._engine.lib.gsr_launch_count() - l0
+					done += 1
+			torch.cuda.current_stream().wait_stream(side)
+			graph = torch.cuda.CUDAGraph()
+			with torch.cuda.graph(graph):
+				body()
+			self.graph_launches -= per_iter	# the capture pass bumped the host counter without running anything
+		while done < self.iters:
+			if graph is not None:
+				graph.replay()
+				self.graph_launches += per_iter	# kernels of this library inside one replayed iteration
+			else:
+				fp.iterate(self._samples(), self._boundary() if self.boundary_lambda else None, census)
+			done += 1
+			if done % self.check_iter == 0:
+				self.last_test = fp.evaluate(self.lattice, probe=getattr(self, 'probe', None))
+				if census is not None:
+					cur._engine.count_pairs(self.lattice, census.c, 5, True)
+					new._engine.count_pairs(self.lattice, census.c, 1, True)
+		fp.finish()
+		self.cur, self.new = new, cur
+		# the two output fields (|vorticity| and divergence on the lattice)
+		g = self.cur.gradient(self.lattice)
+		vor = advance3d.curl(g).norm(dim=-1)
+		div = self.cur.gradient(self.lattice).diagonal(dim1=-2, dim2=-1).sum(dim=-1)
+		if census is not None:
+			self.cur._engine.count_pairs(self.lattice, census.c, 2, True)
+		return vor, div

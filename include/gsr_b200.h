@@ -212,10 +212,16 @@ int gsr_step(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalin
 	     const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
 	     const float *positions_org, float *state, void *ws, size_t ws_bytes, void *stream);
 
-/* ---- measurement helpers (bench.py roofline denominators) --------------------------------------- */
+/* ---- measurement helpers (bench.py work census and roofline denominators) ------------------------ */
+/* counts[0] (device uint64) += candidate visits C for one evaluation of the Q points (occupancy of each point's 27 (9)-cell
+ * stencil under the reference binning: the unit of work of SURVEY 8d); when packed != NULL also counts[1] += accepted pairs P. */
+int gsr_count_pairs(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed, const float *x, int64_t Q, uint64_t *counts, void *stream);
 /* runs an FFMA-only / ex2.approx-only loop on every SM; returns elapsed ms via *ms (host sync inside) */
 int gsr_peak_fma(int iters, double *tflops, void *stream);
 int gsr_peak_mufu(int iters, double *tops, void *stream);
+
+/* number of kernels this library has launched so far (host-side counter; bench.py's gpu_launches) */
+uint64_t gsr_launch_count(void);
 
 const char *gsr_version(void);
 
