@@ -197,7 +197,7 @@ class HashEngine:
 		mask = C.c_int(0)
 		check(self.lib.gsr_backward_gather(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
 										   ptr(self.packed, align16=True), C.c_int64(self.N), ptr(x, name='x'), C.c_int64(Q),
-										   ptr(perm, torch.int32), ptr(scs, torch.int32), ptr(val, name='val'), ptr(grad, allow_none=True, name='grad'),
+										   ptr(perm, torch.int32), ptr(scs, torch.int32), ptr(val, allow_none=True, name='val'), ptr(grad, allow_none=True, name='grad'),
 										   C.byref(cfg), ptr(acc, align16=True), C.byref(mask), ptr(ws, torch.uint8, align16=True), C.c_size_t(ws.numel()), stream()),
 			  'gsr_backward_gather')
 		return acc, mask.value
