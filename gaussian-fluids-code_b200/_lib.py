@@ -63,6 +63,7 @@ def lib():
 			if hasattr(_lib, name):
 				getattr(_lib, name).restype = C.c_size_t
 		_lib.gsr_padded_cells.restype = C.c_int64
+		_lib.gsr_tile_slots.restype = C.c_int64
 		_lib.gsr_loss_blocks.restype = C.c_int64
 		_lib.gsr_launch_count.restype = C.c_uint64
 		_lib.gsr_version.restype = C.c_char_p

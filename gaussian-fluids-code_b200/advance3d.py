@@ -211,11 +211,12 @@ class FusedProjector:
 		cur = self.ref.velocity_field
 		Q = data.shape[0]
 		data = data.detach()
-		perm, scs = e.bin_samples(data, True)
+		bins = e.bin_samples(data, True)
+		perm, scs = bins
 		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
-		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=perm)
+		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
 		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
-		e.forward(data, val, grad, accumulate=False, perm=perm)
+		e.forward(data, val, grad, accumulate=False, perm=bins)
 		acc, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
 									  {'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, want_losses=True)
 		lp, nblk = e.last_loss_partials
@@ -225,9 +226,10 @@ class FusedProjector:
 			bdata, bnormal = boundary
 			bdata, bnormal = bdata.detach(), bnormal.detach()
 			Qb = bdata.shape[0]
-			perm_b, scs_b = e.bin_samples(bdata, True, tag='b')
+			bins_b = e.bin_samples(bdata, True, tag='b')
+			perm_b, scs_b = bins_b
 			valb = self._tmp('valb', (Qb, 3))
-			e.forward(bdata, valb, None, accumulate=False, perm=perm_b)
+			e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
 			acc_b, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
 											  {'normals': bnormal}, None, tag='acc_b', want_losses=True)
 			lpb, nblkb = e.last_loss_partials
@@ -242,17 +244,18 @@ class FusedProjector:
 		gv, e = self.gv, self.gv._engine
 		data = data.detach()
 		Q = data.shape[0]
-		perm, _ = e.bin_samples(data, False)
+		bins = e.bin_samples(data, False)
+		perm = bins.perm
 		ref_vor, ref_hel = self._tmp('t_ref_vor', (Q, 3)), self._tmp('t_ref_hel', (Q,))
 		if probe is not None:
 			ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 			ev[0].record()
-		self.ref.velocity_field._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=perm)
+		self.ref.velocity_field._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
 		if probe is not None:
 			ev[1].record()
 			probe.append(ev)
 		val, grad = self._tmp('t_val', (Q, 3)), self._tmp('t_grad', (Q, 3, 3))
-		e.forward(data, val, grad, accumulate=False, perm=perm)
+		e.forward(data, val, grad, accumulate=False, perm=bins)
 		return e.sample_losses(val, grad, {'ref_vor': ref_vor, 'ref_hel': ref_hel}, Q) / Q
 
 	def finish(self):

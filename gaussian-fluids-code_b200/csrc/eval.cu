@@ -283,6 +283,14 @@ __global__ void __launch_bounds__(EV_THREADS) count_kernel(EvalParams P_, const 
 
 static inline int blocks_for(int64_t Q, int lanes) { return (int)((Q * lanes + EV_THREADS - 1) / EV_THREADS); }
 
+// eval_tiled.cu
+bool use_tiled(const Grid &g, int64_t Q, const int32_t *perm, const int32_t *scs, const int32_t *tile_row);
+int launch_forward_tiled3(const EvalParams &P, const int32_t *cell_start, const float *packed, const float *cull, const float *x, int64_t Q, const int32_t *perm,
+			  const int32_t *scs, const int32_t *tile_row, float *val, float *grad, bool accumulate, cudaStream_t st);
+int launch_rk4_tiled3(int mode, const EvalParams &P, const int32_t *cell_start, const float *packed, const float *cull, const float *x, int64_t Q, const int32_t *perm,
+		      const int32_t *scs, const int32_t *tile_row, float dt, float *goal_pos, float *deformation, float *goal_val, float *goal_grad,
+		      float *ref_vor, float *ref_hel, cudaStream_t st);
+
 }  // namespace gsr
 
 using namespace gsr;
@@ -305,8 +313,9 @@ static void launch_forward(const EvalParams &P, const int32_t *cs, const float *
 	else forward_kernel<D, false, true, ACC, LN><<<blocks, EV_THREADS, 0, st>>>(P, cs, pk, x, Q, perm, val, grad);
 }
 
-extern "C" int gsr_forward(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed,
-			   const float *x, int64_t Q, const int32_t *perm, float *val, float *grad, int accumulate, void *stream)
+extern "C" int gsr_forward(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,
+			   const float *x, int64_t Q, const int32_t *perm, const int32_t *scs, const int32_t *tile_row,
+			   float *val, float *grad, int accumulate, void *stream)
 {
 	Grid g;
 	if (!make_grid(d, g) || Q < 0 || Q >= ((int64_t)1 << 26) || (!val && !grad) || !cell_start || !packed) return GSR_EINVAL;
@@ -314,6 +323,7 @@ extern "C" int gsr_forward(const gsr_grid_desc *d, const int32_t *cell_start, co
 	cudaStream_t st = (cudaStream_t)stream;
 	EvalParams P = make_params(g);
 	g_launches += 1;
+	if (use_tiled(g, Q, perm, scs, tile_row)) return launch_forward_tiled3(P, cell_start, packed, cull, x, Q, perm, scs, tile_row, val, grad, accumulate != 0, st);
 	const int L = pick_lanes(Q);
 	if (g.D == 3) {
 		if (accumulate) LANES_SWITCH(L, (launch_forward<3, true, LN>(P, cell_start, packed, x, (int)Q, perm, val, grad, st)));
@@ -326,8 +336,8 @@ extern "C" int gsr_forward(const gsr_grid_desc *d, const int32_t *cell_start, co
 	return GSR_OK;
 }
 
-extern "C" int gsr_rk4(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed,
-		       const float *start, int64_t Q, const int32_t *perm, float dt,
+extern "C" int gsr_rk4(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,
+		       const float *start, int64_t Q, const int32_t *perm, const int32_t *scs, const int32_t *tile_row, float dt,
 		       float *goal_pos, float *deformation, float *goal_val, float *goal_grad, void *stream)
 {
 	Grid g;
@@ -341,6 +351,8 @@ extern "C" int gsr_rk4(const gsr_grid_desc *d, const int32_t *cell_start, const 
 	EvalParams P = make_params(g);
 	const float4 *pk = (const float4 *)packed;
 	g_launches += 1;
+	if (use_tiled(g, Q, perm, scs, tile_row))
+		return launch_rk4_tiled3(full ? 1 : 0, P, cell_start, packed, cull, start, Q, perm, scs, tile_row, dt, goal_pos, deformation, goal_val, goal_grad, nullptr, nullptr, st);
 	const int L = pick_lanes(Q);
 	const float4 dom = make_float4(0, 0, 0, 0);
 	if (g.D == 3) {
@@ -354,8 +366,8 @@ extern "C" int gsr_rk4(const gsr_grid_desc *d, const int32_t *cell_start, const 
 	return GSR_OK;
 }
 
-extern "C" int gsr_advected_vorticity(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed,
-				      const float *x, int64_t Q, const int32_t *perm, float dt, const float *domain,
+extern "C" int gsr_advected_vorticity(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,
+				      const float *x, int64_t Q, const int32_t *perm, const int32_t *scs, const int32_t *tile_row, float dt, const float *domain,
 				      float *ref_vor, float *ref_hel, void *stream)
 {
 	Grid g;
@@ -365,6 +377,8 @@ extern "C" int gsr_advected_vorticity(const gsr_grid_desc *d, const int32_t *cel
 	EvalParams P = make_params(g);
 	const float4 *pk = (const float4 *)packed;
 	g_launches += 1;
+	if (use_tiled(g, Q, perm, scs, tile_row))
+		return launch_rk4_tiled3(2, P, cell_start, packed, cull, x, Q, perm, scs, tile_row, dt, nullptr, nullptr, nullptr, nullptr, ref_vor, ref_hel, st);
 	const int L = pick_lanes(Q);
 	if (g.D == 3) {
 		LANES_SWITCH(L, (rk4_3d_kernel<2, LN><<<blocks_for(Q, LN), EV_THREADS, 0, st>>>(P, cell_start, pk, x, (int)Q, perm, dt, nullptr, nullptr, nullptr, nullptr, ref_vor, ref_hel)));

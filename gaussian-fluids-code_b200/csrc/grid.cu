@@ -43,21 +43,30 @@ __global__ void gauss_keys_kernel(const float *__restrict__ pos, int n, Grid g, 
 
 // Sample keys on the padded grid (dims+2): a sample whose cell index is -1 or dims still sees the border
 // cells through the reference's clamped stencil (3D/GSR.py:272-274), anything further out sees nothing.
-template <int D>
+// FINE: the key is extended by 2 bits per axis of sub-cell position (a 4^D raster inside the cell), so that consecutive
+// sorted samples are spatially compact — the warps of the tiled evaluation kernels then reject most candidates as a whole.
+template <int D, bool FINE>
 __global__ void sample_keys_kernel(const float *__restrict__ x, int n, Grid g, uint32_t *__restrict__ keys)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	bool ok = true;
 	int c[3] = {-1, -1, -1};
+	uint32_t sub = 0;
 	const float gs = grid_gs(g);
 #pragma unroll
 	for (int k = 0; k < D; k++) {
-		c[k] = cell_coord(x[(size_t)D * i + k], g.lo[k], gs);
+		const float xv = x[(size_t)D * i + k];
+		c[k] = cell_coord(xv, g.lo[k], gs);
 		ok = ok && c[k] >= -1 && c[k] <= g.dims[k];
+		if (FINE) {
+			const float f = (xv - g.lo[k]) / gs - (float)c[k];	// ordering only: any rounding here is harmless
+			sub = sub * 4u + (uint32_t)min(max((int)(f * 4.f), 0), 3);
+		}
 	}
 	uint32_t key = (uint32_t)g.pcell;
 	if (ok) key = (uint32_t)(((c[0] + 1) * g.pdims[1] + (c[1] + 1)) * g.pdims[2] + (c[2] + 1));
+	if (FINE) key = (key << (2 * D)) | (ok ? sub : 0u);
 	keys[i] = key;
 }
 
@@ -326,12 +335,12 @@ static int radix_sort_index(SortWs &s, int n, uint32_t max_key, uint32_t *out_va
 
 // cell_start[c] = first sorted position whose key >= c, for c in [0, ncell].  Items whose key is ncell (not in
 // the hash) stay at the tail of the sorted order, past cell_start[ncell].
-__global__ void cell_start_kernel(const uint32_t *__restrict__ keys_sorted, int n, int ncell, int32_t *__restrict__ cell_start)
+__global__ void cell_start_kernel(const uint32_t *__restrict__ keys_sorted, int n, int ncell, int32_t *__restrict__ cell_start, int shift)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i > n) return;
-	int prev = (i == 0) ? -1 : min((int)keys_sorted[i - 1], ncell);
-	int cur = (i == n) ? ncell : min((int)keys_sorted[i], ncell);
+	int prev = (i == 0) ? -1 : min((int)(keys_sorted[i - 1] >> shift), ncell);
+	int cur = (i == n) ? ncell : min((int)(keys_sorted[i] >> shift), ncell);
 	for (int c = prev + 1; c <= cur; c++) cell_start[c] = i;
 }
 
@@ -353,8 +362,17 @@ __device__ __forceinline__ float exp2s(float s) { return (float)exp(2.0 * (doubl
 
 // 3D record (3 x float4): {mu.x, mu.y, mu.z, v.x} {A00, A01, A02, v.y} {A11, A12, A22, v.z},  A = Sigma^-1.
 // R(q), S^2 and R S^2 R^T are formed in the reference's operation order (3D/GSR.py:278-289), unfused.
+// cull[t] = (1 + margin) / lambda_min(Sigma^-1) = (1 + margin) exp(-2 min_k s_k): a point farther than sqrt(q_thr * cull) from
+// mu has q = d^T Sigma^-1 d >= lambda_min |d|^2 > q_thr, i.e. is certainly rejected (the tiled kernels' warp-level culling).
+// The margin covers the rounding of Sigma^-1, of q and of the box distance (a few ulp times the condition number).
+__device__ __forceinline__ float cull_coef(float smin, float smax)
+{
+	const float kappa = expf(2.f * (smax - smin));
+	return expf(-2.f * smin) * (1.f + 1e-4f + 8e-6f * kappa);
+}
+
 __global__ void pack3d_kernel(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
-			      int n, const int32_t *__restrict__ sorted_id, float4 *__restrict__ packed)
+			      int n, const int32_t *__restrict__ sorted_id, float4 *__restrict__ packed, float *__restrict__ cull)
 {
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
@@ -389,11 +407,15 @@ __global__ void pack3d_kernel(const float *__restrict__ pos, const float *__rest
 	packed[3 * (size_t)t + 0] = make_float4(p[0], p[1], p[2], v[0]);
 	packed[3 * (size_t)t + 1] = make_float4(A[0][0], A[0][1], A[0][2], v[1]);
 	packed[3 * (size_t)t + 2] = make_float4(A[1][1], A[1][2], A[2][2], v[2]);
+	if (cull) {
+		const float s0 = scal[3 * (size_t)i], s1 = scal[3 * (size_t)i + 1], s2 = scal[3 * (size_t)i + 2];
+		cull[t] = cull_coef(fminf(s0, fminf(s1, s2)), fmaxf(s0, fmaxf(s1, s2)));
+	}
 }
 
 // 2D record (2 x float4): {mu.x, mu.y, v.x, v.y} {A00, A01, A11, 0},  A = R(theta) diag(e^{2s}) R^T (2D/GSR.py:275-277)
 __global__ void pack2d_kernel(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
-			      int n, const int32_t *__restrict__ sorted_id, float4 *__restrict__ packed)
+			      int n, const int32_t *__restrict__ sorted_id, float4 *__restrict__ packed, float *__restrict__ cull)
 {
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
@@ -407,6 +429,10 @@ __global__ void pack2d_kernel(const float *__restrict__ pos, const float *__rest
 	float A11 = __fadd_rn(__fmul_rn(__fmul_rn(R[1][0], S0), R[1][0]), __fmul_rn(__fmul_rn(R[1][1], S1), R[1][1]));
 	packed[2 * (size_t)t + 0] = make_float4(pos[2 * (size_t)i], pos[2 * (size_t)i + 1], vals[2 * (size_t)i], vals[2 * (size_t)i + 1]);
 	packed[2 * (size_t)t + 1] = make_float4(A00, A01, A11, 0.f);
+	if (cull) {
+		const float s0 = scal[2 * (size_t)i], s1 = scal[2 * (size_t)i + 1];
+		cull[t] = cull_coef(fminf(s0, s1), fmaxf(s0, s1));
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -462,39 +488,45 @@ extern "C" int gsr_build_grid(const gsr_grid_desc *d, const float *positions, in
 		if (rc) return rc;
 	}
 	g_launches += (n > 0 ? 2 : 1) + ((grid_cnt || grid_offset) ? 1 : 0);
-	cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.ncell, cell_start);
+	cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.ncell, cell_start, 0);
 	if (grid_cnt || grid_offset) ref_format_kernel<<<(g.ncell + 255) / 256, 256, 0, st>>>(cell_start, g.ncell, grid_cnt, grid_offset);
 	GSR_CHECK_LAUNCH();
 	return GSR_OK;
 }
 
-extern "C" int gsr_bin_samples(const gsr_grid_desc *d, const float *x, int64_t Q, int32_t *perm, int32_t *sample_cell_start,
+extern "C" int gsr_bin_samples(const gsr_grid_desc *d, const float *x, int64_t Q, int32_t *perm, int32_t *sample_cell_start, int fine,
 			       void *ws, size_t ws_bytes, void *stream)
 {
 	Grid g;
 	if (!make_grid(d, g) || Q < 0 || Q >= ((int64_t)1 << 30) || !perm) return GSR_EINVAL;
+	const int shift = (fine && g.pcell < (1 << 25)) ? 2 * g.D : 0;
 	cudaStream_t st = (cudaStream_t)stream;
 	SortWs s;
 	if (!carve_sort_ws(ws, ws_bytes, Q, s)) return GSR_EWS;
 	int n = (int)Q;
 	const uint32_t *ks = s.keys0;
 	if (n > 0) {
-		if (g.D == 3) sample_keys_kernel<3><<<(n + 255) / 256, 256, 0, st>>>(x, n, g, s.keys0);
-		else sample_keys_kernel<2><<<(n + 255) / 256, 256, 0, st>>>(x, n, g, s.keys0);
+		if (g.D == 3) {
+			if (shift) sample_keys_kernel<3, true><<<(n + 255) / 256, 256, 0, st>>>(x, n, g, s.keys0);
+			else sample_keys_kernel<3, false><<<(n + 255) / 256, 256, 0, st>>>(x, n, g, s.keys0);
+		} else {
+			if (shift) sample_keys_kernel<2, true><<<(n + 255) / 256, 256, 0, st>>>(x, n, g, s.keys0);
+			else sample_keys_kernel<2, false><<<(n + 255) / 256, 256, 0, st>>>(x, n, g, s.keys0);
+		}
 		GSR_CHECK_LAUNCH();
-		int rc = radix_sort_index(s, n, (uint32_t)g.pcell, (uint32_t *)perm, &ks, st);
+		int rc = radix_sort_index(s, n, ((uint32_t)g.pcell << shift) | ((1u << shift) - 1u), (uint32_t *)perm, &ks, st);
 		if (rc) return rc;
 	}
 	g_launches += (n > 0 ? 1 : 0) + (sample_cell_start ? 1 : 0);
 	if (sample_cell_start) {
-		cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.pcell, sample_cell_start);
+		cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.pcell, sample_cell_start, shift);
 		GSR_CHECK_LAUNCH();
 	}
 	return GSR_OK;
 }
 
 extern "C" int gsr_pack_gaussians(const gsr_grid_desc *d, const float *positions, const float *scalings, const float *rotations,
-				  const float *values, int64_t N, const int32_t *, const int32_t *sorted_id, float *packed, void *stream)
+				  const float *values, int64_t N, const int32_t *, const int32_t *sorted_id, float *packed, float *cull, void *stream)
 {
 	Grid g;
 	if (!make_grid(d, g) || N < 0 || !packed || !sorted_id) return GSR_EINVAL;
@@ -502,8 +534,8 @@ extern "C" int gsr_pack_gaussians(const gsr_grid_desc *d, const float *positions
 	cudaStream_t st = (cudaStream_t)stream;
 	int n = (int)N;
 	g_launches += 1;
-	if (g.D == 3) pack3d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed);
-	else pack2d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed);
+	if (g.D == 3) pack3d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed, cull);
+	else pack2d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed, cull);
 	GSR_CHECK_LAUNCH();
 	return GSR_OK;
 }

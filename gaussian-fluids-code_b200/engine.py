@@ -32,6 +32,27 @@ class _Scratch:
 		return self.get(name, max(n, 1) * itemsize)[:n * itemsize].view(dtype).view(*shape)
 
 
+class Bins:
+	"""
+	The engine's ordering of a batch of query points: perm (cell-sorted sample indices), scs (sample_cell_start on the
+	padded grid, or None) and tiles (the tile -> row table of the large-Q kernels, or None).  Unpacks as (perm, scs).
+	"""
+	__slots__ = ('perm', 'scs', 'tiles')
+
+	def __init__(self, perm, scs=None, tiles=None):
+		self.perm, self.scs, self.tiles = perm, scs, tiles
+
+	def __iter__(self):
+		yield self.perm
+		yield self.scs
+
+
+def _unbin(b):
+	if b is None or isinstance(b, Bins):
+		return b
+	return Bins(b)
+
+
 class HashEngine:
 	"""
 	State: cell_start (ncell+1) int32, sorted_id (N) int32, packed (N, 12|8) f32 — see include/gsr_b200.h.
@@ -48,7 +69,7 @@ class HashEngine:
 		self.scratch = _Scratch(self.device)
 		self.desc = None
 		self.N = 0
-		self.cell_start = self.sorted_id = self.packed = None
+		self.cell_start = self.sorted_id = self.packed = self.cull = None
 		self._packed_key = None
 
 	# ---- hash -------------------------------------------------------------------------------------
@@ -66,6 +87,7 @@ class HashEngine:
 		if self.sorted_id is None or self.sorted_id.numel() != N:
 			self.sorted_id = torch.empty(N, dtype=torch.int32, device=dev)
 			self.packed = torch.empty((N, 12 if self.D == 3 else 8), dtype=torch.float32, device=dev)
+			self.cull = torch.empty(N, dtype=torch.float32, device=dev)
 		self.N = N
 		nbytes = self.lib.gsr_build_grid_ws_bytes(C.byref(self.desc), C.c_int64(N))
 		ws = self.scratch.get('sort', nbytes)
@@ -95,7 +117,7 @@ class HashEngine:
 		check(self.lib.gsr_pack_gaussians(C.byref(self.desc), ptr(p, name='positions'), ptr(s, name='scalings'),
 										  ptr(r, name='rotations', align16=True), ptr(v, name='values'), C.c_int64(self.N),
 										  ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
-										  ptr(self.packed, align16=True), stream()), 'gsr_pack_gaussians')
+										  ptr(self.packed, align16=True), ptr(self.cull), stream()), 'gsr_pack_gaussians')
 		self._packed_key = key
 
 	def min_scaling(self, scalings):
@@ -104,18 +126,31 @@ class HashEngine:
 		return out
 
 	# ---- samples ----------------------------------------------------------------------------------
+	# smallest Q for which the tiled shared-memory kernels are used (mirrors GSR_TUNE_TILED_MIN_Q)
+	TILED_MIN_Q = 1 << 17
+
+	@classmethod
+	def set_tiled_min_q(cls, q):
+		cls.TILED_MIN_Q = int(q)
+		check(_lib.lib().gsr_set_tuning(C.c_int(1), C.c_int(int(q))), 'gsr_set_tuning')
+
 	def bin_samples(self, x, need_cells, tag='x'):
 		Q = x.shape[0]
 		perm = self.scratch.typed('perm_' + tag, (Q,), torch.int32)
 		scs = None
-		if need_cells:
+		need_tiles = self.D == 3 and Q >= self.TILED_MIN_Q
+		if need_cells or need_tiles:
 			pcell = self.lib.gsr_padded_cells(C.byref(self.desc))
 			scs = self.scratch.typed('scs_' + tag, (pcell + 1,), torch.int32)
 		nbytes = self.lib.gsr_bin_samples_ws_bytes(C.byref(self.desc), C.c_int64(Q))
 		ws = self.scratch.get('sort', nbytes)
-		check(self.lib.gsr_bin_samples(C.byref(self.desc), ptr(x, name='x'), C.c_int64(Q), ptr(perm, torch.int32), ptr(scs, torch.int32, True),
+		check(self.lib.gsr_bin_samples(C.byref(self.desc), ptr(x, name='x'), C.c_int64(Q), ptr(perm, torch.int32), ptr(scs, torch.int32, True), C.c_int(1 if need_tiles else 0),
 									   ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()), 'gsr_bin_samples')
-		return perm, scs
+		tiles = None
+		if need_tiles:
+			tiles = self.scratch.typed('tiles_' + tag, (self.lib.gsr_tile_slots(C.byref(self.desc), C.c_int64(Q)),), torch.int32)
+			check(self.lib.gsr_build_tiles(C.byref(self.desc), ptr(scs, torch.int32), C.c_int64(Q), ptr(tiles, torch.int32), stream()), 'gsr_build_tiles')
+		return Bins(perm, scs, tiles)
 
 	def _x(self, x):
 		if x.dim() != 2 or x.shape[1] != self.D:
@@ -125,26 +160,25 @@ class HashEngine:
 	# ---- kernels ----------------------------------------------------------------------------------
 	def forward(self, x, val, grad, accumulate, perm=None):
 		x = self._x(x)
-		if perm is None:
-			perm, _ = self.bin_samples(x, False)
-		check(self.lib.gsr_forward(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True),
-								   ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(perm, torch.int32),
+		b = _unbin(perm) or self.bin_samples(x, False)
+		check(self.lib.gsr_forward(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True), ptr(self.cull),
+								   ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(b.perm, torch.int32), ptr(b.scs, torch.int32, True), ptr(b.tiles, torch.int32, True),
 								   ptr(val, allow_none=True, name='val'), ptr(grad, allow_none=True, name='grad'), C.c_int(1 if accumulate else 0), stream()), 'gsr_forward')
 
 	def rk4(self, start, dt, goal_pos, deformation=None, goal_val=None, goal_grad=None):
 		start = self._x(start)
-		perm, _ = self.bin_samples(start, False)
-		check(self.lib.gsr_rk4(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True),
-							   ptr(start, name='start_pos'), C.c_int64(start.shape[0]), ptr(perm, torch.int32), C.c_float(dt),
+		b = self.bin_samples(start, False)
+		check(self.lib.gsr_rk4(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True), ptr(self.cull),
+							   ptr(start, name='start_pos'), C.c_int64(start.shape[0]), ptr(b.perm, torch.int32), ptr(b.scs, torch.int32, True), ptr(b.tiles, torch.int32, True), C.c_float(dt),
 							   ptr(goal_pos), ptr(deformation, allow_none=True), ptr(goal_val, allow_none=True), ptr(goal_grad, allow_none=True), stream()), 'gsr_rk4')
 
 	def advected_vorticity(self, x, dt, ref_vor, ref_hel=None, domain=None, perm=None):
 		x = self._x(x)
-		if perm is None:
-			perm, _ = self.bin_samples(x, False)
+		b = _unbin(perm) or self.bin_samples(x, False)
 		dom = (C.c_float * 4)(*domain) if domain is not None else None
-		check(self.lib.gsr_advected_vorticity(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True),
-											  ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(perm, torch.int32), C.c_float(dt), dom,
+		check(self.lib.gsr_advected_vorticity(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True), ptr(self.cull),
+											  ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(b.perm, torch.int32), ptr(b.scs, torch.int32, True), ptr(b.tiles, torch.int32, True),
+											  C.c_float(dt), dom,
 											  ptr(ref_vor), ptr(ref_hel, allow_none=True), stream()), 'gsr_advected_vorticity')
 
 	def count_pairs(self, x, counts, evals=1, with_accepted=False):

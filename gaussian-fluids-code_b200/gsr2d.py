@@ -199,8 +199,9 @@ class GaussianSplattingFast(GaussianSplatting):
 		e.ensure_packed(self._params())
 		backward = weight != 0. or weight_boundary != 0.
 		val = torch.zeros((x.shape[0], self.dim), device=device)
-		perm, scs = e.bin_samples(x.detach(), need_cells=backward)
-		e.forward(x, val, None, accumulate=False, perm=perm)
+		bins = e.bin_samples(x.detach(), need_cells=backward)
+		perm, scs = bins
+		e.forward(x, val, None, accumulate=False, perm=bins)
 		if backward:
 			refs = {'ref_val': ref if weight != 0. else None, 'normals': normals if weight_boundary != 0. else None,
 					'normal_ref': normal_ref if weight_boundary != 0. else None}
@@ -223,8 +224,9 @@ class GaussianSplattingFast(GaussianSplatting):
 		e.ensure_packed(self._params())
 		backward = weight_grad != 0. or weight_vor != 0. or weight_div != 0.
 		grad = torch.zeros((x.shape[0], self.dim, 2), device=device)
-		perm, scs = e.bin_samples(x.detach(), need_cells=backward)
-		e.forward(x, None, grad, accumulate=False, perm=perm)
+		bins = e.bin_samples(x.detach(), need_cells=backward)
+		perm, scs = bins
+		e.forward(x, None, grad, accumulate=False, perm=bins)
 		if backward:
 			refs = {'ref_grad': ref_grad if weight_grad != 0. else None, 'ref_vor': ref_vor if weight_vor != 0. else None}
 			acc, mask = e.backward_gather(x, perm, scs, None, grad, (0., 0., weight_grad, weight_vor, 0., weight_div), refs, stop_gradient)

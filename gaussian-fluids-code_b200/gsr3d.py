@@ -213,8 +213,9 @@ class GaussianSplatting3DFast(GaussianSplatting3D):
 		backward = any(w != 0. for w in (weight_val, weight_boundary, weight_grad, weight_vor, weight_div))
 		if backward and discard_grad:
 			raise GsrError('a backward pass needs grad (discard_grad=False)')
-		perm, scs = e.bin_samples(x.detach(), need_cells=backward)
-		e.forward(x, val, None if discard_grad else grad, accumulate=True, perm=perm)
+		bins = e.bin_samples(x.detach(), need_cells=backward)
+		perm, scs = bins
+		e.forward(x, val, None if discard_grad else grad, accumulate=True, perm=bins)
 		if backward:
 			refs = {'ref_val': ref_val if weight_val != 0. else None, 'normals': normals if weight_boundary != 0. else None,
 					'ref_grad': ref_grad if weight_grad != 0. else None, 'ref_vor': ref_vor if weight_vor != 0. else None,

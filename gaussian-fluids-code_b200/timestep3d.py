@@ -53,11 +53,12 @@ class ShardedProjector(advance3d.FusedProjector):
 		gv, e = self.gv, self.gv._engine
 		cur = self.ref.velocity_field
 		Q, Qg = data.shape[0], data.shape[0] * self.world
-		perm, scs = e.bin_samples(data, True)
+		bins = e.bin_samples(data, True)
+		perm, scs = bins
 		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
-		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=perm)
+		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
 		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
-		e.forward(data, val, grad, accumulate=False, perm=perm)
+		e.forward(data, val, grad, accumulate=False, perm=bins)
 		_, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
 									{'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, Q_norm=Qg, acc=self.acc, loss_partials=self.lp)
 		srcs = [(self.lp, self.nblk, [self.w['vor'] / Qg, 0., self.w['div'] / Qg, 0., 0., 0., 0., 0.])]
@@ -67,9 +68,10 @@ class ShardedProjector(advance3d.FusedProjector):
 		if boundary is not None:
 			bdata, bnormal = boundary
 			Qb, Qbg = bdata.shape[0], bdata.shape[0] * self.world
-			perm_b, scs_b = e.bin_samples(bdata, True, tag='b')
+			bins_b = e.bin_samples(bdata, True, tag='b')
+			perm_b, scs_b = bins_b
 			valb = self._tmp('valb', (Qb, 3))
-			e.forward(bdata, valb, None, accumulate=False, perm=perm_b)
+			e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
 			_, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
 										  {'normals': bnormal}, None, Q_norm=Qbg, acc=self.acc, loss_partials=self.lpb)
 			mask |= mask_b

@@ -60,10 +60,12 @@ int gsr_build_grid(const gsr_grid_desc *g, const float *positions, int64_t N,
 		   void *ws, size_t ws_bytes, void *stream);
 
 /* Per-Gaussian precompute {mu, Sigma^-1 = R diag(e^{2s}) R^T, v}, gathered into cell order
- * (hoists the per-pair recomputation of 3D/GSR.py:277-289, 2D/GSR.py:274-277 out of the pair loop). */
+ * (hoists the per-pair recomputation of 3D/GSR.py:277-289, 2D/GSR.py:274-277 out of the pair loop).
+ * cull (N floats, cell order, may be NULL): (1 + margin) / lambda_min(Sigma^-1) — the bounding-sphere coefficient the
+ * large-Q kernels use to skip, per warp, candidates that no point of the warp can accept. */
 int gsr_pack_gaussians(const gsr_grid_desc *g, const float *positions, const float *scalings, const float *rotations,
 		       const float *values, int64_t N, const int32_t *cell_start, const int32_t *sorted_id,
-		       float *packed, void *stream);
+		       float *packed, float *cull, void *stream);
 
 /* min over all entries of scalings -> *out_min (device float); the reduction behind
  * `self.scalings.min().item()` of reinitialize_grid (3D/GSR.py:249). */
@@ -72,29 +74,48 @@ int gsr_min_scaling(const float *scalings, int64_t count, float *out_min, void *
 /* ---- sample binning (engine-internal ordering of the query points) ------------------------------ */
 size_t gsr_bin_samples_ws_bytes(const gsr_grid_desc *g, int64_t Q);
 /* perm (Q): sample indices ordered by (padded) cell key, stable;  sample_cell_start: (pcell+1)
- * with pcell = prod(dims+2), may be NULL when only the ordering is needed. */
-int gsr_bin_samples(const gsr_grid_desc *g, const float *x, int64_t Q, int32_t *perm, int32_t *sample_cell_start,
+ * with pcell = prod(dims+2), may be NULL when only the ordering is needed.  fine != 0: samples of one cell are further
+ * ordered by their position on a 4^D sub-cell raster (spatially compact warps for the tiled kernels). */
+int gsr_bin_samples(const gsr_grid_desc *g, const float *x, int64_t Q, int32_t *perm, int32_t *sample_cell_start, int fine,
 		    void *ws, size_t ws_bytes, void *stream);
 int64_t gsr_padded_cells(const gsr_grid_desc *g);
 
+/* Tiles of the large-Q evaluation kernels: runs of up to GSR_TILE_SAMPLES cell-sorted samples that share one (x, y)
+ * row of cells, so that their candidate Gaussians are 9 contiguous runs of packed records that one CTA stages in
+ * shared memory with TMA bulk copies (3D; the 2D kernels keep the one-thread-per-point shape).  tile_row (gsr_tile_slots(g, Q) int32) maps a
+ * tile id to its row (-1: unused id); built from sample_cell_start. */
+#define GSR_TILE_SAMPLES 512
+int64_t gsr_tile_slots(const gsr_grid_desc *g, int64_t Q);
+int gsr_build_tiles(const gsr_grid_desc *g, const int32_t *sample_cell_start, int64_t Q, int32_t *tile_row, void *stream);
+
+/* Engine tunables (process-wide; tests use them to force a code path at small sizes). */
+#define GSR_TUNE_TILED_MIN_Q 1	/* smallest Q evaluated by the tiled kernels when a tile table is supplied */
+#define GSR_TUNE_TILED_CAP 2	/* shared-memory staging capacity of a tile, in Gaussians */
+int gsr_set_tuning(int key, int value);
+
 /* ---- a2: forward  (loop 1 of get_losses_ti 3D/GSR.py:270-298; 2D/GSR.py:266-281, :378-395) ------ */
 /* perm may be NULL (process samples in the given order).  val and/or grad may be NULL.
- * accumulate != 0: outputs are += (3D reference semantics); 0: overwritten (2D semantics). */
-int gsr_forward(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed,
-		const float *x, int64_t Q, const int32_t *perm, float *val, float *grad, int accumulate, void *stream);
+ * accumulate != 0: outputs are += (3D reference semantics); 0: overwritten (2D semantics).
+ * sample_cell_start + tile_row (both from gsr_bin_samples / gsr_build_tiles for this x and this grid) may be NULL;
+ * when given and Q is large, the tiled shared-memory kernels are used (same results); cull (from gsr_pack_gaussians, may be
+ * NULL) enables their warp-level candidate culling. */
+int gsr_forward(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed, const float *cull,
+		const float *x, int64_t Q, const int32_t *perm, const int32_t *sample_cell_start, const int32_t *tile_row,
+		float *val, float *grad, int accumulate, void *stream);
 
 /* ---- a4: RK4 advection + pull-back  (advection_rk4_ti 3D/GSR.py:634-665; 2D/GSR.py:549-580) ----- */
 /* deformation / goal_val / goal_grad may be NULL (the reference's size-0 outputs). */
-int gsr_rk4(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed,
-	    const float *start, int64_t Q, const int32_t *perm, float dt,
+int gsr_rk4(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed, const float *cull,
+	    const float *start, int64_t Q, const int32_t *perm, const int32_t *sample_cell_start, const int32_t *tile_row, float dt,
 	    float *goal_pos, float *deformation, float *goal_val, float *goal_grad, void *stream);
 
 /* ---- a5: advected-covector reference  (AdvectedCovectorField.vorticity 3D/advance.py:24-47,
  *          2D/advance.py:46-54): RK4 back-trace fused with curl, 3x3 inverse and helicity -------- */
 /* 3D: ref_vor (Q,3), ref_hel (Q) | NULL.  2D: ref_vor (Q), zeroed where the back-traced point leaves
  * domain[4] = {x_min,x_max,y_min,y_max} (host pointer, may be NULL); ref_hel ignored. */
-int gsr_advected_vorticity(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed,
-			   const float *x, int64_t Q, const int32_t *perm, float dt, const float *domain,
+int gsr_advected_vorticity(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed, const float *cull,
+			   const float *x, int64_t Q, const int32_t *perm, const int32_t *sample_cell_start, const int32_t *tile_row,
+			   float dt, const float *domain,
 			   float *ref_vor, float *ref_hel, void *stream);
 
 /* ---- a6: neighbour marking  (get_all_neighbors_ti 3D/GSR.py:679-690; 2D/GSR.py:620-630) --------- */
@@ -219,6 +240,8 @@ int gsr_count_pairs(const gsr_grid_desc *g, const int32_t *cell_start, const flo
 /* runs an FFMA-only / ex2.approx-only loop on every SM; returns elapsed ms via *ms (host sync inside) */
 int gsr_peak_fma(int iters, double *tflops, void *stream);
 int gsr_peak_mufu(int iters, double *tops, void *stream);
+/* pipe probes (misc.cu): thread-level operations per second of one operand shape; which = 0..6, see misc.cu */
+int gsr_pipe_probe(int which, int iters, double *ops_per_s, void *stream);
 
 /* number of kernels this library has launched so far (host-side counter; bench.py's gpu_launches) */
 uint64_t gsr_launch_count(void);
