@@ -218,44 +218,81 @@ __device__ __forceinline__ void warp_eval3(const TiledArgs &a, const TileSh &sh,
 			Z2[h] = pack2(z[2 * h], z[2 * h + 1]);
 		}
 		const f2 ntau2 = bc(-tau);
+		const int lane = threadIdx.x & 31;
+		// do all active points of the warp sit in ONE cell?  (then every hull cell is in every point's stencil)
+		int k0[3] = {INT_MAX, INT_MAX, INT_MAX}, k1[3] = {INT_MIN, INT_MIN, INT_MIN};
+		float thr[P];
+#pragma unroll
+		for (int p = 0; p < P; p++) {
+			const bool act = cx[p] != -(1 << 24);
+			thr[p] = act ? q_thr : -1.f;
+			if (act) {
+				k0[0] = min(k0[0], cx[p]); k1[0] = max(k1[0], cx[p]);
+				k0[1] = min(k0[1], cy[p]); k1[1] = max(k1[1], cy[p]);
+				k0[2] = min(k0[2], cz[p]); k1[2] = max(k1[2], cz[p]);
+			}
+		}
+		bool mixed = false;
+#pragma unroll
+		for (int k = 0; k < 3; k++) mixed |= __reduce_min_sync(FULL, k0[k]) != __reduce_max_sync(FULL, k1[k]);
 		for (int gi = hx0; gi <= hx1; gi++) {
 			for (int gj = hy0; gj <= hy1; gj++) {
 				bool rowok[P];
-				bool any_row = false;
+				if (mixed) {
+					bool any_row = false;
 #pragma unroll
-				for (int p = 0; p < P; p++) {
-					rowok[p] = abs(gi - cx[p]) <= 1 && abs(gj - cy[p]) <= 1;
-					any_row |= rowok[p];
+					for (int p = 0; p < P; p++) {
+						rowok[p] = abs(gi - cx[p]) <= 1 && abs(gj - cy[p]) <= 1;
+						any_row |= rowok[p];
+					}
+					if (!__any_sync(FULL, any_row)) continue;
 				}
-				if (!__any_sync(FULL, any_row)) continue;
 				const int cb = (gi * g.dims[1] + gj) * g.dims[2];
 				const int dx_ = gi - sh.tcx, dy_ = gj - sh.tcy;
 				const int rr = (sh.staged && abs(dx_) <= 1 && abs(dy_) <= 1) ? (dx_ + 1) * 3 + (dy_ + 1) : -1;
-				int s = __ldg(a.cell_start + cb + hz0);
-				for (int zc = hz0; zc <= hz1; zc++) {
-					const int e = __ldg(a.cell_start + cb + zc + 1);
-					const int n = e - s;
-					float thr[P];
-					bool any_cell = false;
+				const int soff = rr >= 0 ? sh.soff[rr] - sh.gstart[rr] : 0;	// staged slot of sorted index c: soff + c
+				for (int zg = hz0; zg <= hz1; zg += 4) {	// groups of up to 4 z cells: one contiguous run of records
+					const int nz = min(4, hz1 - zg + 1);
+					const int b0 = __ldg(a.cell_start + cb + zg), b1 = __ldg(a.cell_start + cb + zg + min(1, nz)),
+						  b2 = __ldg(a.cell_start + cb + zg + min(2, nz)), b3 = __ldg(a.cell_start + cb + zg + min(3, nz)),
+						  b4 = __ldg(a.cell_start + cb + zg + nz);
+					unsigned cellmask = 0xfu;	// cells of the group that are in some active point's stencil
+					if (mixed) {
+						cellmask = 0;
 #pragma unroll
-					for (int p = 0; p < P; p++) {
-						const bool act = rowok[p] && abs(zc - cz[p]) <= 1;
-						thr[p] = act ? q_thr : -1.f;
-						any_cell |= act;
+						for (int k = 0; k < 4; k++) {
+							bool act = false;
+#pragma unroll
+							for (int p = 0; p < P; p++) act |= rowok[p] && abs(zg + k - cz[p]) <= 1;
+							cellmask |= __any_sync(FULL, act) ? (1u << k) : 0u;
+						}
 					}
-					if (n > 0 && __any_sync(FULL, any_cell)) {
-						const float4 *ptr = (rr >= 0 && zc >= sh.zlo && zc <= sh.zhi) ? srec + 3 * (sh.soff[rr] + (s - sh.gstart[rr]))
-													      : a.packed + 3 * (size_t)s;
-						const float *cl = a.cull ? a.cull + s : nullptr;
-						for (int i = 0; i < n; i++) {
-							const float4 p0 = ld4(ptr + 3 * i);
-							if (cl) {	// warp-uniform: every lane holds the same candidate and the same box
-								const float ex = fmaxf(fmaxf(bx0 - p0.x, p0.x - bx1), 0.f);
-								const float ey = fmaxf(fmaxf(by0 - p0.y, p0.y - by1), 0.f);
-								const float ez = fmaxf(fmaxf(bz0 - p0.z, p0.z - bz1), 0.f);
-								if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > q_thr * __ldg(cl + i)) continue;
+					for (int c0 = b0; c0 < b4; c0 += 32) {
+						// lane-parallel culling: lane l looks at candidate c0 + l
+						const int c = c0 + lane;
+						const int kc = (c >= b1) + (c >= b2) + (c >= b3);
+						const bool st_c = rr >= 0 && zg + kc >= sh.zlo && zg + kc <= sh.zhi;
+						bool keep = c < b4 && ((cellmask >> kc) & 1u);
+						if (keep && a.cull) {
+							const float4 m = ld4(st_c ? srec + 3 * (soff + c) : a.packed + 3 * (size_t)c);
+							const float ex = fmaxf(fmaxf(bx0 - m.x, m.x - bx1), 0.f);
+							const float ey = fmaxf(fmaxf(by0 - m.y, m.y - by1), 0.f);
+							const float ez = fmaxf(fmaxf(bz0 - m.z, m.z - bz1), 0.f);
+							keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= q_thr * __ldg(a.cull + c);
+						}
+						unsigned mask = __ballot_sync(FULL, keep);
+						const unsigned smask = __ballot_sync(FULL, st_c);
+						while (mask) {	// survivors, in cell-sorted order; everything below is warp-uniform
+							const int l = __ffs(mask) - 1;
+							mask &= mask - 1;
+							const int ci = c0 + l;
+							const float4 *ptr = ((smask >> l) & 1u) ? srec + 3 * (soff + ci) : a.packed + 3 * (size_t)ci;
+							const float4 p0 = ld4(ptr), p1 = ld4(ptr + 1), p2 = ld4(ptr + 2);
+							if (mixed) {
+								const int zci = zg + (ci >= b1) + (ci >= b2) + (ci >= b3);
+#pragma unroll
+								for (int p = 0; p < P; p++) thr[p] = (rowok[p] && abs(zci - cz[p]) <= 1) ? q_thr : -1.f;
 							}
-							const float4 p1 = ld4(ptr + 3 * i + 1), p2 = ld4(ptr + 3 * i + 2);
 #pragma unroll
 							for (int h = 0; h < H; h++) {
 								const f2 dx = add2(X2[h], bc(-p0.x)), dy = add2(Y2[h], bc(-p0.y)), dz = add2(Z2[h], bc(-p0.z));
@@ -289,7 +326,6 @@ __device__ __forceinline__ void warp_eval3(const TiledArgs &a, const TileSh &sh,
 							}
 						}
 					}
-					s = e;
 				}
 			}
 		}
