@@ -242,7 +242,7 @@ def run_ours(args):
 			dist.destroy_process_group()
 		return
 
-	# ---- roofline of the dominant kernel: the RK4 pull-back (rk4_3d_kernel<2>) on the test lattice --------------------
+	# ---- roofline of the dominant kernel: the RK4 pull-back (rk4_tiled3_kernel<2, 2>) on the test lattice --------------------
 	fma, mufu = C.c_double(0.), C.c_double(0.)
 	lib.gsr_peak_fma(C.c_int(20000), C.byref(fma), _lib.stream())
 	lib.gsr_peak_mufu(C.c_int(20000), C.byref(mufu), _lib.stream())
@@ -254,7 +254,7 @@ def run_ours(args):
 	k_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
 	flop_per_launch = 5 * (24 * C_lat + 28 * P_lat)
 	achieved = flop_per_launch / (k_ms * 1e-3) / 1e12 if kernel_ms else None
-	roofline = {'bound': 'fp32', 'kernel': 'rk4_3d_kernel<2> (RK4 pull-back of the previous field on the test lattice, 5 field evaluations per point)',
+	roofline = {'bound': 'fp32', 'kernel': 'rk4_tiled3_kernel<2, 2> (RK4 pull-back of the previous field on the test lattice, 5 field evaluations per point)',
 				'achieved': achieved, 'peak': fma.value, 'unit': 'TFLOP/s', 'frac': (achieved / fma.value) if achieved else None, 'traffic': None,
 				'peak_source': 'FP32 FFMA peak measured live by gsr_peak_fma on this GPU (MEASURED_PEAKS.json holds only HBM and bf16 peaks); nominal 74.4 at 1965 MHz',
 				'mufu_peak_Tops': mufu.value, 'mufu_achieved_Tops': (5 * P_lat / (k_ms * 1e-3) / 1e12) if kernel_ms else None,

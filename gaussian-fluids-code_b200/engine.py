@@ -3,6 +3,7 @@ Device-side plumbing shared by the 2D and 3D drop-in classes: owns the hash buff
 turns tensors into raw pointers and calls the C ABI (include/gsr_b200.h).  No arithmetic happens here.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -127,7 +128,7 @@ class HashEngine:
 
 	# ---- samples ----------------------------------------------------------------------------------
 	# smallest Q for which the tiled shared-memory kernels are used (mirrors GSR_TUNE_TILED_MIN_Q)
-	TILED_MIN_Q = 1 << 17
+	TILED_MIN_Q = int(os.environ.get('GSR_TILED_MIN_Q', 1 << 17))
 
 	@classmethod
 	def set_tiled_min_q(cls, q):
@@ -298,9 +299,10 @@ class FusedStepper:
 		N = scalings.shape[0]
 		self.N = N
 		nfl = self.e.lib.gsr_step_state_floats(C.c_int(self.e.D), C.c_int64(N))
-		self.state = torch.empty(nfl, dtype=torch.float32, device=self.e.device)
+		if self.state is None or self.state.numel() != nfl:	# a restart on the same N keeps the buffers (and captured graphs) valid
+			self.state = torch.empty(nfl, dtype=torch.float32, device=self.e.device)
+			self.ws = torch.empty(self.e.lib.gsr_step_ws_bytes(C.c_int(self.e.D), C.c_int64(N)), dtype=torch.uint8, device=self.e.device)
 		check(self.e.lib.gsr_step_init(C.byref(self.cfg), C.c_int64(N), ptr(scalings.detach()), ptr(self.state), stream()), 'gsr_step_init')
-		self.ws = torch.empty(self.e.lib.gsr_step_ws_bytes(C.c_int(self.e.D), C.c_int64(N)), dtype=torch.uint8, device=self.e.device)
 		# from now on the engine's kernels read grid_scale from the device-resident state
 		self.e.desc.grid_scale_dev = self.state.data_ptr() + 4 * _lib.ST_GRID_SCALE
 

@@ -49,6 +49,14 @@ class ShardedProjector(advance3d.FusedProjector):
 		self.lpb = self.flat[3 * N * 12 + nblk * 8:].view(nblkb, 8)
 		self.nblk, self.nblkb = nblk, nblkb
 
+	def restart(self):
+		"""begin a new project phase on the same buffers: fresh optimiser state, fresh hash"""
+		self.stepper.init(self.gv.scalings)
+		self._rebuild()
+		cur = self.ref.velocity_field
+		cur._engine._packed_key = None
+		cur._engine.ensure_packed(cur._params())
+
 	def iterate(self, data, boundary=None, census=None):
 		gv, e = self.gv, self.gv._engine
 		cur = self.ref.velocity_field
@@ -100,6 +108,9 @@ class LeapfrogTimestep:
 		torch.cuda.manual_seed(1000 + rank)	# every rank draws its own sample shard (default generator: CUDA-graph safe)
 		self.last_test = None
 		self.graph_launches = 0
+		self._proj = {}
+		self._lo = torch.tensor([self.new.x_min, self.new.y_min, self.new.z_min], dtype=torch.float32, device=dev)
+		self._hi = torch.tensor([self.new.x_max, self.new.y_max, self.new.z_max], dtype=torch.float32, device=dev)
 
 	def reset(self, params=None):
 		"""restore both fields to the given (default: initial) parameters — used between timed steps and by the e2e path"""
@@ -125,41 +136,55 @@ class LeapfrogTimestep:
 		normal = onehot * (1. - 2. * upper)[:, None]
 		return data.contiguous(), normal.contiguous()
 
+	def _projector(self, new, cur):
+		"""the persistent projector (buffers, optimiser state, captured iteration graph) of one (new, cur) orientation"""
+		key = id(new)
+		ent = self._proj.get(key)
+		if ent is None:
+			ref = advance3d.AdvectedCovectorField(cur, cur, self.dt, 0., 1., 0., 1., 0., 1.)
+			ent = {'fp': ShardedProjector(new, ref, self.boundary_lambda, self.N, self.Qb, world=self.world), 'graph': None, 'per_iter': 0}
+			self._proj[key] = ent
+		else:
+			ent['fp'].restart()
+		return ent
+
 	def step(self, census=None):
 		cur, new = self.cur, self.new
 		# clone (no Gaussian is over-stretched in the synthetic field: the common path of 3D/advance.py:91-92)
 		with torch.no_grad():
 			for a, b in zip((new.positions, new.scalings, new.rotations, new.values), (cur.positions, cur.scalings, cur.rotations, cur.values)):
 				a.copy_(b)
+			# advect (3D/advance.py:167-180), written into the persistent positions tensor so that the captured graph stays valid
+			pos = cur.advection_rk4(new.positions.detach(), self.dt)
+			pos.clamp_(self._lo, self._hi)
+			new.positions.copy_(pos)
 		new.zero_grad()
-		# advect
-		advance3d.advect_covector_field(new, cur, self.dt, new.x_min, new.x_max, new.y_min, new.y_max, new.z_min, new.z_max)
 		if census is not None:
 			cur._engine.count_pairs(new.positions.detach(), census.c, 4, True)
-		# project, fixed iteration count; the iteration is captured once into a CUDA graph and replayed
-		ref = advance3d.AdvectedCovectorField(cur, cur, self.dt, 0., 1., 0., 1., 0., 1.)
-		fp = ShardedProjector(new, ref, self.boundary_lambda, self.N, self.Qb, world=self.world)
+		# project, fixed iteration count; the iteration is captured once per orientation into a CUDA graph and replayed
+		ent = self._projector(new, cur)
+		fp = ent['fp']
 		body = lambda: fp.iterate(self._samples(), self._boundary() if self.boundary_lambda else None, None)
 		done = 0
-		graph = None
-		if self.use_graph and census is None:
+		if self.use_graph and census is None and ent['graph'] is None:
 			side = torch.cuda.Stream()
 			side.wait_stream(torch.cuda.current_stream())
 			with torch.cuda.stream(side):
 				for _ in range(2):	# eager warm-up iterations (they count): sizes every scratch buffer
 					l0 = new._engine.lib.gsr_launch_count()
 					body()
-					per_iter = new._engine.lib.gsr_launch_count() - l0
+					ent['per_iter'] = new._engine.lib.gsr_launch_count() - l0
 					done += 1
 			torch.cuda.current_stream().wait_stream(side)
-			graph = torch.cuda.CUDAGraph()
-			with torch.cuda.graph(graph):
+			ent['graph'] = torch.cuda.CUDAGraph()
+			with torch.cuda.graph(ent['graph']):
 				body()
-			self.graph_launches -= per_iter	# the capture pass bumped the host counter without running anything
+			self.graph_launches -= ent['per_iter']	# the capture pass bumped the host counter without running anything
+		graph = ent['graph'] if (self.use_graph and census is None) else None
 		while done < self.iters:
 			if graph is not None:
 				graph.replay()
-				self.graph_launches += per_iter	# kernels of this library inside one replayed iteration
+				self.graph_launches += ent['per_iter']	# kernels of this library inside one replayed iteration
 			else:
 				fp.iterate(self._samples(), self._boundary() if self.boundary_lambda else None, census)
 			done += 1
