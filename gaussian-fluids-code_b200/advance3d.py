@@ -193,9 +193,7 @@ class FusedProjector:
 	def _rebuild(self):
 		gv = self.gv
 		e = gv._engine
-		e.build(gv.positions.detach())
-		e._packed_key = None
-		e.ensure_packed(gv._params())
+		e.build(gv.positions.detach(), params=[p.detach() for p in gv._params()])	# hash + packed records, one call
 		e._packed_key = None	# parameters are updated in place by raw pointers: never trust the version counters here
 
 	def _tmp(self, name, shape):

@@ -19,10 +19,8 @@ namespace gsr {
 // Gaussian keys: row-major cell index, or ncell for Gaussians outside the extended domain
 // (the reference silently drops those from the hash: 3D/GSR.py:212).
 template <int D>
-__global__ void gauss_keys_kernel(const float *__restrict__ pos, int n, Grid g, uint32_t *__restrict__ keys)
+__device__ __forceinline__ uint32_t gauss_key(const float *__restrict__ pos, int i, const Grid &g)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
 	bool in = true;
 	int c[3] = {0, 0, 0};
 	const float gs = grid_gs(g);
@@ -38,7 +36,15 @@ __global__ void gauss_keys_kernel(const float *__restrict__ pos, int n, Grid g, 
 	for (int k = 0; k < D; k++) in = in && c[k] >= 0 && c[k] < g.dims[k];
 	uint32_t key = (uint32_t)g.ncell;
 	if (in) key = (uint32_t)((c[0] * g.dims[1] + c[1]) * g.dims[2] + c[2]);
-	keys[i] = key;
+	return key;
+}
+
+template <int D>
+__global__ void gauss_keys_kernel(const float *__restrict__ pos, int n, Grid g, uint32_t *__restrict__ keys)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	keys[i] = gauss_key<D>(pos, i, g);
 }
 
 // Sample keys on the padded grid (dims+2): a sample whose cell index is -1 or dims still sees the border
@@ -46,10 +52,8 @@ __global__ void gauss_keys_kernel(const float *__restrict__ pos, int n, Grid g, 
 // FINE: the key is extended by 2 bits per axis of sub-cell position (a 4^D raster inside the cell), so that consecutive
 // sorted samples are spatially compact — the warps of the tiled evaluation kernels then reject most candidates as a whole.
 template <int D, bool FINE>
-__global__ void sample_keys_kernel(const float *__restrict__ x, int n, Grid g, uint32_t *__restrict__ keys)
+__device__ __forceinline__ uint32_t sample_key(const float *__restrict__ x, int i, const Grid &g)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
 	bool ok = true;
 	int c[3] = {-1, -1, -1};
 	uint32_t sub = 0;
@@ -67,7 +71,15 @@ __global__ void sample_keys_kernel(const float *__restrict__ x, int n, Grid g, u
 	uint32_t key = (uint32_t)g.pcell;
 	if (ok) key = (uint32_t)(((c[0] + 1) * g.pdims[1] + (c[1] + 1)) * g.pdims[2] + (c[2] + 1));
 	if (FINE) key = (key << (2 * D)) | (ok ? sub : 0u);
-	keys[i] = key;
+	return key;
+}
+
+template <int D, bool FINE>
+__global__ void sample_keys_kernel(const float *__restrict__ x, int n, Grid g, uint32_t *__restrict__ keys)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	keys[i] = sample_key<D, FINE>(x, i, g);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,12 +383,9 @@ __device__ __forceinline__ float cull_coef(float smin, float smax)
 	return expf(-2.f * smin) * (1.f + 1e-4f + 8e-6f * kappa);
 }
 
-__global__ void pack3d_kernel(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
-			      int n, const int32_t *__restrict__ sorted_id, float4 *__restrict__ packed, float *__restrict__ cull)
+__device__ __forceinline__ void pack3d_one(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot,
+					   const float *__restrict__ vals, int t, int i, float4 *__restrict__ packed, float *__restrict__ cull)
 {
-	int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n) return;
-	int i = sorted_id[t];
 	float4 r = reinterpret_cast<const float4 *>(rot)[i];
 	float len = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.x, r.x), __fmul_rn(r.y, r.y)), __fmul_rn(r.z, r.z)), __fmul_rn(r.w, r.w)));
 	float q0 = __fdiv_rn(r.x, len), q1 = __fdiv_rn(r.y, len), q2 = __fdiv_rn(r.z, len), q3 = __fdiv_rn(r.w, len);
@@ -413,13 +422,18 @@ __global__ void pack3d_kernel(const float *__restrict__ pos, const float *__rest
 	}
 }
 
-// 2D record (2 x float4): {mu.x, mu.y, v.x, v.y} {A00, A01, A11, 0},  A = R(theta) diag(e^{2s}) R^T (2D/GSR.py:275-277)
-__global__ void pack2d_kernel(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
+__global__ void pack3d_kernel(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
 			      int n, const int32_t *__restrict__ sorted_id, float4 *__restrict__ packed, float *__restrict__ cull)
 {
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
-	int i = sorted_id[t];
+	pack3d_one(pos, scal, rot, vals, t, sorted_id[t], packed, cull);
+}
+
+// 2D record (2 x float4): {mu.x, mu.y, v.x, v.y} {A00, A01, A11, 0},  A = R(theta) diag(e^{2s}) R^T (2D/GSR.py:275-277)
+__device__ __forceinline__ void pack2d_one(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot,
+					   const float *__restrict__ vals, int t, int i, float4 *__restrict__ packed, float *__restrict__ cull)
+{
 	double th = (double)rot[i];
 	float c = (float)cos(th), s = (float)sin(th);
 	float S0 = exp2s(scal[2 * (size_t)i]), S1 = exp2s(scal[2 * (size_t)i + 1]);
@@ -433,6 +447,157 @@ __global__ void pack2d_kernel(const float *__restrict__ pos, const float *__rest
 		const float s0 = scal[2 * (size_t)i], s1 = scal[2 * (size_t)i + 1];
 		cull[t] = cull_coef(fminf(s0, s1), fmaxf(s0, s1));
 	}
+}
+
+__global__ void pack2d_kernel(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
+			      int n, const int32_t *__restrict__ sorted_id, float4 *__restrict__ packed, float *__restrict__ cull)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	pack2d_one(pos, scal, rot, vals, t, sorted_id[t], packed, cull);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole hash in ONE single-CTA kernel for small inputs (the latency-bound regime of the reference's own sizes, where
+// the hash of N = 1000..16384 Gaussians and of every sample batch is rebuilt in each optimiser iteration):
+//   keys -> shared-memory histogram -> exclusive scan (= cell_start) -> slot scatter -> canonical intra-cell order
+//   [-> pack {mu, Sigma^-1, v} in cell order].
+// Intra-cell order: an item's final rank is the number of smaller ids in its cell's (unordered) segment, so the result
+// is exactly the stable sort of the radix path, deterministically, without sorting.  The tail bucket (items outside the
+// hash) keeps its arrival order: nothing reads it positionally.
+// ------------------------------------------------------------------------------------------------
+constexpr int SH_THREADS = 1024;
+constexpr int SH_MAX_N = 16384;
+constexpr int SH_MAX_CELLS = 26000;	// 2 x (cells + 1) x 4 B of shared memory
+
+template <int D, bool GAUSS, bool RANK>
+__global__ void __launch_bounds__(SH_THREADS) small_hash_kernel(const float *__restrict__ pts, int n, Grid g, int ncell, int32_t *__restrict__ cell_start,
+								 int32_t *__restrict__ ids_out, uint32_t *__restrict__ keys_tmp, uint32_t *__restrict__ ids_tmp,
+								 const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
+								 float4 *__restrict__ packed, float *__restrict__ cull)
+{
+	extern __shared__ uint32_t sh_mem[];
+	uint32_t *start = sh_mem;		// [ncell + 1] histogram, then exclusive prefix
+	uint32_t *fill = sh_mem + ncell + 1;	// [ncell + 1] slot counters
+	__shared__ uint32_t warp_sums[32];
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	for (int c = tid; c <= ncell; c += SH_THREADS) { start[c] = 0; fill[c] = 0; }
+	__syncthreads();
+	for (int i = tid; i < n; i += SH_THREADS) {
+		const uint32_t key = GAUSS ? gauss_key<D>(pts, i, g) : sample_key<D, false>(pts, i, g);
+		keys_tmp[i] = key;
+		atomicAdd(&start[key], 1u);
+	}
+	__syncthreads();
+	{	// exclusive scan of start[0..ncell]
+		const int m = ncell + 1, chunk = (m + SH_THREADS - 1) / SH_THREADS;
+		const int b = tid * chunk, e = min(b + chunk, m);
+		uint32_t s = 0;
+		for (int c = b; c < e; c++) s += start[c];
+		uint32_t v = s;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+			if (lane >= o) v += t;
+		}
+		if (lane == 31) warp_sums[w] = v;
+		__syncthreads();
+		if (w == 0) {
+			const uint32_t ws = warp_sums[lane];
+			uint32_t t2 = ws;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xffffffffu, t2, o);
+				if (lane >= o) t2 += t;
+			}
+			warp_sums[lane] = t2 - ws;
+		}
+		__syncthreads();
+		uint32_t run = warp_sums[w] + (v - s);
+		for (int c = b; c < e; c++) {
+			const uint32_t t = start[c];
+			start[c] = run;
+			cell_start[c] = (int32_t)run;
+			run += t;
+		}
+	}
+	__syncthreads();
+	for (int i = tid; i < n; i += SH_THREADS) {
+		const uint32_t key = keys_tmp[i];
+		ids_tmp[start[key] + atomicAdd(&fill[key], 1u)] = (uint32_t)i;
+	}
+	if (!RANK) return;	// crowded cells: small_rank_kernel finishes on the whole machine
+	__syncthreads();
+	for (int t = tid; t < n; t += SH_THREADS) {
+		const uint32_t id = ids_tmp[t];
+		const uint32_t key = keys_tmp[id];
+		uint32_t pos = (uint32_t)t;
+		if (key != (uint32_t)ncell) {
+			const uint32_t s = start[key], cnt = fill[key];
+			uint32_t rank = 0;
+			for (uint32_t k = 0; k < cnt; k++) rank += ids_tmp[s + k] < id;
+			pos = s + rank;
+		}
+		ids_out[pos] = (int32_t)id;
+		if (GAUSS && packed) {
+			if (D == 3) pack3d_one(pts, scal, rot, vals, (int)pos, (int)id, packed, cull);
+			else pack2d_one(pts, scal, rot, vals, (int)pos, (int)id, packed, cull);
+		}
+	}
+}
+
+// second half of the small hash when cells are crowded: one thread per item, whole machine
+template <int D, bool GAUSS>
+__global__ void __launch_bounds__(128) small_rank_kernel(const float *__restrict__ pts, int n, int ncell, const int32_t *__restrict__ cell_start,
+							 int32_t *__restrict__ ids_out, const uint32_t *__restrict__ keys_tmp, const uint32_t *__restrict__ ids_tmp,
+							 const float *__restrict__ scal, const float *__restrict__ rot, const float *__restrict__ vals,
+							 float4 *__restrict__ packed, float *__restrict__ cull)
+{
+	const int t = blockIdx.x * 128 + threadIdx.x;
+	if (t >= n) return;
+	const uint32_t id = ids_tmp[t];
+	const uint32_t key = keys_tmp[id];
+	uint32_t pos = (uint32_t)t;
+	if (key != (uint32_t)ncell) {
+		const uint32_t s = (uint32_t)cell_start[key], cnt = (uint32_t)cell_start[key + 1] - s;
+		uint32_t rank = 0;
+		for (uint32_t k = 0; k < cnt; k++) rank += ids_tmp[s + k] < id;
+		pos = s + rank;
+	}
+	ids_out[pos] = (int32_t)id;
+	if (GAUSS && packed) {
+		if (D == 3) pack3d_one(pts, scal, rot, vals, (int)pos, (int)id, packed, cull);
+		else pack2d_one(pts, scal, rot, vals, (int)pos, (int)id, packed, cull);
+	}
+}
+
+template <int D, bool GAUSS>
+static int launch_small_hash(const float *pts, int n, const Grid &g, int ncell, int32_t *cell_start, int32_t *ids_out, uint32_t *keys_tmp, uint32_t *ids_tmp,
+			     const float *scal, const float *rot, const float *vals, float4 *packed, float *cull, cudaStream_t st)
+{
+	const size_t sm = sizeof(uint32_t) * 2 * (size_t)(ncell + 1);
+	const bool fused_rank = (int64_t)n <= 4 * (int64_t)ncell;	// sparse cells: rank inside the single CTA
+	if (sm > 48 * 1024) {
+		cudaError_t e = fused_rank ? cudaFuncSetAttribute(small_hash_kernel<D, GAUSS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+					   : cudaFuncSetAttribute(small_hash_kernel<D, GAUSS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+		if (e != cudaSuccess) return (int)e;
+	}
+	if (fused_rank) {
+		g_launches += 1;
+		small_hash_kernel<D, GAUSS, true><<<1, SH_THREADS, sm, st>>>(pts, n, g, ncell, cell_start, ids_out, keys_tmp, ids_tmp, scal, rot, vals, packed, cull);
+	} else {
+		g_launches += 2;
+		small_hash_kernel<D, GAUSS, false><<<1, SH_THREADS, sm, st>>>(pts, n, g, ncell, cell_start, ids_out, keys_tmp, ids_tmp, scal, rot, vals, packed, cull);
+		small_rank_kernel<D, GAUSS><<<(n + 127) / 128, 128, 0, st>>>(pts, n, ncell, cell_start, ids_out, keys_tmp, ids_tmp, scal, rot, vals, packed, cull);
+	}
+	GSR_CHECK_LAUNCH();
+	return GSR_OK;
+}
+
+static bool small_hash_ok(int64_t n, int64_t ncell)
+{
+	// one CTA, shared-memory histogram, and an intra-cell ranking that is quadratic in the cell occupancy
+	return n > 0 && n <= SH_MAX_N && ncell <= SH_MAX_CELLS && ncell * 48 >= n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -469,28 +634,55 @@ extern "C" int64_t gsr_padded_cells(const gsr_grid_desc *d)
 	return g.pcell;
 }
 
+static int launch_pack(const Grid &g, const float *positions, const float *scalings, const float *rotations, const float *values, int n,
+		       const int32_t *sorted_id, float *packed, float *cull, cudaStream_t st)
+{
+	g_launches += 1;
+	if (g.D == 3) pack3d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed, cull);
+	else pack2d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed, cull);
+	GSR_CHECK_LAUNCH();
+	return GSR_OK;
+}
+
 extern "C" int gsr_build_grid(const gsr_grid_desc *d, const float *positions, int64_t N,
 			      int32_t *cell_start, int32_t *sorted_id, int32_t *grid_cnt, int32_t *grid_offset,
+			      const float *scalings, const float *rotations, const float *values, float *packed, float *cull,
 			      void *ws, size_t ws_bytes, void *stream)
 {
 	Grid g;
 	if (!make_grid(d, g) || N < 0 || N >= ((int64_t)1 << 30) || !cell_start || !sorted_id) return GSR_EINVAL;
+	if (packed && (!scalings || !rotations || !values)) return GSR_EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
 	SortWs s;
 	if (!carve_sort_ws(ws, ws_bytes, N, s)) return GSR_EWS;
 	int n = (int)N;
-	const uint32_t *ks = s.keys0;
-	if (n > 0) {
-		if (g.D == 3) gauss_keys_kernel<3><<<(n + 255) / 256, 256, 0, st>>>(positions, n, g, s.keys0);
-		else gauss_keys_kernel<2><<<(n + 255) / 256, 256, 0, st>>>(positions, n, g, s.keys0);
-		GSR_CHECK_LAUNCH();
-		int rc = radix_sort_index(s, n, (uint32_t)g.ncell, (uint32_t *)sorted_id, &ks, st);
+	if (small_hash_ok(N, g.ncell)) {
+		// one launch: keys, histogram, scan, scatter, canonical order and (optionally) the packed records
+		int rc = (g.D == 3) ? launch_small_hash<3, true>(positions, n, g, g.ncell, cell_start, sorted_id, s.kA, s.vTmp, scalings, rotations, values, (float4 *)packed, cull, st)
+				    : launch_small_hash<2, true>(positions, n, g, g.ncell, cell_start, sorted_id, s.kA, s.vTmp, scalings, rotations, values, (float4 *)packed, cull, st);
 		if (rc) return rc;
+	} else {
+		const uint32_t *ks = s.keys0;
+		if (n > 0) {
+			if (g.D == 3) gauss_keys_kernel<3><<<(n + 255) / 256, 256, 0, st>>>(positions, n, g, s.keys0);
+			else gauss_keys_kernel<2><<<(n + 255) / 256, 256, 0, st>>>(positions, n, g, s.keys0);
+			GSR_CHECK_LAUNCH();
+			int rc = radix_sort_index(s, n, (uint32_t)g.ncell, (uint32_t *)sorted_id, &ks, st);
+			if (rc) return rc;
+		}
+		g_launches += (n > 0 ? 2 : 1);
+		cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.ncell, cell_start, 0);
+		GSR_CHECK_LAUNCH();
+		if (packed && n > 0) {
+			int rc = launch_pack(g, positions, scalings, rotations, values, n, sorted_id, packed, cull, st);
+			if (rc) return rc;
+		}
 	}
-	g_launches += (n > 0 ? 2 : 1) + ((grid_cnt || grid_offset) ? 1 : 0);
-	cell_start_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(ks, n, g.ncell, cell_start, 0);
-	if (grid_cnt || grid_offset) ref_format_kernel<<<(g.ncell + 255) / 256, 256, 0, st>>>(cell_start, g.ncell, grid_cnt, grid_offset);
-	GSR_CHECK_LAUNCH();
+	if (grid_cnt || grid_offset) {
+		g_launches += 1;
+		ref_format_kernel<<<(g.ncell + 255) / 256, 256, 0, st>>>(cell_start, g.ncell, grid_cnt, grid_offset);
+		GSR_CHECK_LAUNCH();
+	}
 	return GSR_OK;
 }
 
@@ -504,6 +696,15 @@ extern "C" int gsr_bin_samples(const gsr_grid_desc *d, const float *x, int64_t Q
 	SortWs s;
 	if (!carve_sort_ws(ws, ws_bytes, Q, s)) return GSR_EWS;
 	int n = (int)Q;
+	if (!shift && small_hash_ok(Q, g.pcell)) {
+		// sample_cell_start is produced as a by-product; when the caller does not want it, it lands in scratch
+		int32_t *scs = sample_cell_start ? sample_cell_start : (int32_t *)s.hist;
+		if (!sample_cell_start && (size_t)(g.pcell + 1) > 256 * (size_t)s.nblocks) scs = nullptr;
+		if (scs) {
+			return (g.D == 3) ? launch_small_hash<3, false>(x, n, g, g.pcell, scs, perm, s.kA, s.vTmp, nullptr, nullptr, nullptr, nullptr, nullptr, st)
+					  : launch_small_hash<2, false>(x, n, g, g.pcell, scs, perm, s.kA, s.vTmp, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+		}
+	}
 	const uint32_t *ks = s.keys0;
 	if (n > 0) {
 		if (g.D == 3) {
@@ -531,13 +732,7 @@ extern "C" int gsr_pack_gaussians(const gsr_grid_desc *d, const float *positions
 	Grid g;
 	if (!make_grid(d, g) || N < 0 || !packed || !sorted_id) return GSR_EINVAL;
 	if (N == 0) return GSR_OK;
-	cudaStream_t st = (cudaStream_t)stream;
-	int n = (int)N;
-	g_launches += 1;
-	if (g.D == 3) pack3d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed, cull);
-	else pack2d_kernel<<<(n + 127) / 128, 128, 0, st>>>(positions, scalings, rotations, values, n, sorted_id, (float4 *)packed, cull);
-	GSR_CHECK_LAUNCH();
-	return GSR_OK;
+	return launch_pack(g, positions, scalings, rotations, values, (int)N, sorted_id, packed, cull, (cudaStream_t)stream);
 }
 
 extern "C" int gsr_min_scaling(const float *scalings, int64_t count, float *out_min, void *stream)

@@ -79,8 +79,9 @@ class HashEngine:
 		self.desc = host.make_desc(self.D, ext_bounds, dims, grid_scale, tau)
 		self.ncell = host.n_cells(self.D, dims)
 
-	def build(self, positions, want_ref_format=False):
-		"""gsr_build_grid: radix sort of the Gaussian cell keys"""
+	def build(self, positions, want_ref_format=False, params=None):
+		"""gsr_build_grid: radix sort of the Gaussian cell keys; with params = (positions, scalings, rotations, values) the packed
+		records are produced by the same call (one launch for small N)"""
 		N = positions.shape[0]
 		dev = self.device
 		if self.cell_start is None or self.cell_start.numel() != self.ncell + 1:
@@ -99,8 +100,11 @@ class HashEngine:
 		check(self.lib.gsr_build_grid(C.byref(self.desc), ptr(positions, name='positions'), C.c_int64(N),
 									  ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
 									  ptr(cnt, torch.int32, True), ptr(off, torch.int32, True),
+									  ptr(params[1], name='scalings') if params else None, ptr(params[2], name='rotations', align16=True) if params else None,
+									  ptr(params[3], name='values') if params else None, ptr(self.packed, align16=True) if params else None,
+									  ptr(self.cull) if params else None,
 									  ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()), 'gsr_build_grid')
-		self._packed_key = None
+		self._packed_key = self._key(params) if params else None
 		return cnt, off
 
 	@staticmethod
@@ -140,7 +144,7 @@ class HashEngine:
 		perm = self.scratch.typed('perm_' + tag, (Q,), torch.int32)
 		scs = None
 		need_tiles = self.D == 3 and Q >= self.TILED_MIN_Q
-		if need_cells or need_tiles:
+		if need_cells or need_tiles or Q <= 16384:	# small batches: the single-launch hash produces the cell table anyway
 			pcell = self.lib.gsr_padded_cells(C.byref(self.desc))
 			scs = self.scratch.typed('scs_' + tag, (pcell + 1,), torch.int32)
 		nbytes = self.lib.gsr_bin_samples_ws_bytes(C.byref(self.desc), C.c_int64(Q))
@@ -248,6 +252,18 @@ class HashEngine:
 				arr[s][k] = ptr(t, name='gradient buffer').value if t is not None else None
 		check(self.lib.gsr_backward_epilogue(C.byref(self.desc), ptr(scalings.detach(), name='scalings'), ptr(rotations.detach(), name='rotations'),
 											 C.c_int64(self.N), ptr(acc, align16=True), C.c_int(mask), arr, stream()), 'gsr_backward_epilogue')
+
+	def sample_box(self, box, out, seed, stream_id, iteration=None):
+		"""gsr_sample_box: out (n,3) uniform in box = (x_min, x_max, y_min, y_max, z_min, z_max); iteration: device float scalar or None"""
+		b = (C.c_float * 6)(*[float(v) for v in box])
+		check(self.lib.gsr_sample_box(b, C.c_int64(out.shape[0]), C.c_uint64(seed), C.c_uint32(stream_id), ptr(iteration, allow_none=True), ptr(out), stream()), 'gsr_sample_box')
+		return out
+
+	def sample_box_surface(self, box, data, normal, seed, stream_id, iteration=None):
+		b = (C.c_float * 6)(*[float(v) for v in box])
+		check(self.lib.gsr_sample_box_surface(b, C.c_int64(data.shape[0]), C.c_uint64(seed), C.c_uint32(stream_id), ptr(iteration, allow_none=True),
+											  ptr(data), ptr(normal), stream()), 'gsr_sample_box_surface')
+		return data, normal
 
 	def sample_losses(self, val, grad, refs, Q):
 		"""gsr_sample_losses: the 8 loss slots of include/gsr_b200.h summed over the samples (device tensor, no sync)"""

@@ -105,10 +105,11 @@ class LeapfrogTimestep:
 		lattice = gsr3d.get_grid_points(0., 1., 0., 1., 0., 1., test_res, test_res, test_res)
 		per = (lattice.shape[0] + world - 1) // world
 		self.lattice = lattice[rank * per:(rank + 1) * per].contiguous()	# this rank's slice of the test / output lattice
-		torch.cuda.manual_seed(1000 + rank)	# every rank draws its own sample shard (default generator: CUDA-graph safe)
 		self.last_test = None
 		self.graph_launches = 0
 		self._proj = {}
+		self._x = torch.empty((self.N, 3), dtype=torch.float32, device=dev)
+		self._xb, self._nb = torch.empty((Qb, 3), dtype=torch.float32, device=dev), torch.empty((Qb, 3), dtype=torch.float32, device=dev)
 		self._lo = torch.tensor([self.new.x_min, self.new.y_min, self.new.z_min], dtype=torch.float32, device=dev)
 		self._hi = torch.tensor([self.new.x_max, self.new.y_max, self.new.z_max], dtype=torch.float32, device=dev)
 
@@ -121,20 +122,13 @@ class LeapfrogTimestep:
 					t.copy_(torch.as_tensor(src), non_blocking=True)
 				f.zero_grad()
 
-	def _samples(self):
-		return torch.rand((self.N, 3), device=gsr3d.device)
+	def _samples(self, fp):
+		"""this rank's training samples of the current iteration: U[0,1]^3, Q = N (3D/advance.py:339-340), one kernel"""
+		return fp.gv._engine.sample_box((0., 1.) * 3, self._x, 42, 2 * self.rank, fp.stepper.state[:1])
 
-	def _boundary(self):
-		# sample_on_box with this object's generator (same distribution as init_cond3d.sample_on_box)
-		dev = gsr3d.device
-		n = self.Qb
-		face = torch.randint(0, 6, (n,), device=dev)	# unit cube: the six faces have equal area
-		uvw = torch.rand((n, 3), device=dev)
-		axis, upper = face // 2, (face % 2).to(torch.float32)
-		onehot = torch.nn.functional.one_hot(axis, 3).to(torch.float32)
-		data = uvw * (1. - onehot) + onehot * upper[:, None]
-		normal = onehot * (1. - 2. * upper)[:, None]
-		return data.contiguous(), normal.contiguous()
+	def _boundary(self, fp):
+		"""sample_on_box(Qb) on the unit cube (3D/init_cond.py:227-249), one kernel"""
+		return fp.gv._engine.sample_box_surface((0., 1.) * 3, self._xb, self._nb, 42, 2 * self.rank + 1, fp.stepper.state[:1])
 
 	def _projector(self, new, cur):
 		"""the persistent projector (buffers, optimiser state, captured iteration graph) of one (new, cur) orientation"""
@@ -164,7 +158,7 @@ class LeapfrogTimestep:
 		# project, fixed iteration count; the iteration is captured once per orientation into a CUDA graph and replayed
 		ent = self._projector(new, cur)
 		fp = ent['fp']
-		body = lambda: fp.iterate(self._samples(), self._boundary() if self.boundary_lambda else None, None)
+		body = lambda: fp.iterate(self._samples(fp), self._boundary(fp) if self.boundary_lambda else None, None)
 		done = 0
 		if self.use_graph and census is None and ent['graph'] is None:
 			side = torch.cuda.Stream()
@@ -186,7 +180,7 @@ class LeapfrogTimestep:
 				graph.replay()
 				self.graph_launches += ent['per_iter']	# kernels of this library inside one replayed iteration
 			else:
-				fp.iterate(self._samples(), self._boundary() if self.boundary_lambda else None, census)
+				fp.iterate(self._samples(fp), self._boundary(fp) if self.boundary_lambda else None, census)
 			done += 1
 			if done % self.check_iter == 0:
 				self.last_test = fp.evaluate(self.lattice, probe=getattr(self, 'probe', None))

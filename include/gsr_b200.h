@@ -54,9 +54,12 @@ typedef struct {
 /* ---- a1: spatial hash  (reinitialize_grid_ti: 3D/GSR.py:205-245, 2D/GSR.py:194-222) ------------ */
 size_t gsr_build_grid_ws_bytes(const gsr_grid_desc *g, int64_t N);
 /* Outputs: cell_start (ncell+1), sorted_id (N; entries past cell_start[ncell] list the Gaussians outside the hash),
- * optionally the reference-format grid_cnt (ncell) and grid_offset (ncell) (may be NULL). */
+ * optionally the reference-format grid_cnt (ncell) and grid_offset (ncell) (may be NULL), and — when `packed` is given
+ * together with scalings / rotations / values — the packed records and cull coefficients of gsr_pack_gaussians (for
+ * small N the whole hash and the packing are ONE single-CTA launch). */
 int gsr_build_grid(const gsr_grid_desc *g, const float *positions, int64_t N,
 		   int32_t *cell_start, int32_t *sorted_id, int32_t *grid_cnt, int32_t *grid_offset,
+		   const float *scalings, const float *rotations, const float *values, float *packed, float *cull,
 		   void *ws, size_t ws_bytes, void *stream);
 
 /* Per-Gaussian precompute {mu, Sigma^-1 = R diag(e^{2s}) R^T, v}, gathered into cell order
@@ -232,6 +235,15 @@ int gsr_step_init(const gsr_step_cfg *cfg, int64_t N, const float *scalings, flo
 int gsr_step(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalings, float *rotations, float *values,
 	     const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
 	     const float *positions_org, float *state, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a7: sample generation  (3D/advance.py:339-340 rand_like(positions) * extent + min; 3D/init_cond.py:227-249
+ *          sample_on_box) — one kernel per sample set, counter-based Philox keyed by (seed, stream_id) and indexed by
+ *          (sample, iteration); the iteration number is read from DEVICE memory (e.g. state + GSR_ST_T, may be NULL = 0)
+ *          so a captured CUDA graph draws fresh samples on every replay. box = {x_min, x_max, y_min, y_max, z_min, z_max} (host). */
+int gsr_sample_box(const float *box, int64_t n, uint64_t seed, uint32_t stream_id, const float *iteration_dev, float *out, void *stream);
+/* area-weighted points on the six faces with inward unit normals: data (n,3), normal (n,3) */
+int gsr_sample_box_surface(const float *box, int64_t n, uint64_t seed, uint32_t stream_id, const float *iteration_dev, float *data, float *normal,
+			   void *stream);
 
 /* ---- measurement helpers (bench.py work census and roofline denominators) ------------------------ */
 /* counts[0] (device uint64) += candidate visits C for one evaluation of the Q points (occupancy of each point's 27 (9)-cell
