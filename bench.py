@@ -237,9 +237,19 @@ def run_ours(args):
 	h2d = sum(p.numel() * 4 for p in host_params)
 	d2h = sum(p.numel() * 4 for p in host_out) + sum(f.numel() * 4 for f in host_fields)
 
-	if rank != 0:
+	def finish():
+		"""leave without tearing NCCL down: the captured iteration graphs hold the communicator's kernels, and destroying the
+		process group under them can block; every rank has synchronised and rank 0 has printed by the time this runs"""
+		sys.stdout.flush()
+		sys.stderr.flush()
 		if world > 1:
-			dist.destroy_process_group()
+			torch.cuda.synchronize()
+			dist.barrier()
+			torch.cuda.synchronize()
+			os._exit(0)
+
+	if rank != 0:
+		finish()
 		return
 
 	# ---- roofline of the dominant kernel: the RK4 pull-back (rk4_tiled3_kernel<2, 2>) on the test lattice --------------------
@@ -270,7 +280,7 @@ def run_ours(args):
 	out = {
 		'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
 		'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-		'config': {'workload': workload_name(args, n), 'sharding': f'samples sharded over {world} rank(s) (global Q = {world}*N per iteration), parameters replicated, 1 NCCL all-reduce / iteration' if world > 1 else 'single GPU',
+		'config': {'workload': workload_name(args, n), 'sharding': f'samples sharded over {world} rank(s): per rank N training + 8192 boundary samples per iteration (global Q = {world}*N, global normalisers) and {args.test_res}^3 of a {args.test_res}x{args.test_res}x{world * args.test_res} test lattice; parameters replicated, 1 NCCL all-reduce / iteration' if world > 1 else 'single GPU',
 				   'l2_policy': 'every step sweeps > 126 MB (test lattice passes write 2.1M x 12 floats; the iterations rewrite all buffers), inputs regenerated each iteration',
 				   'work_census': 'candidate visits counted on the last warm-up step (gsr_count_pairs), RK4 counted as 4 or 5 evaluations of its start points'},
 		'timesteps_per_s': args.steps / (ms * 1e-3), 'project_iters_per_s': args.steps * args.iters / (ms * 1e-3),
@@ -290,8 +300,7 @@ def run_ours(args):
 		out['cpu_baseline'] = {'value': c / tsec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
 							   'sample': f'2 x (RK4 pull-back + fwd + bwd on Q=N={N}, boundary fwd+bwd on 8192, RK4 pull-back + fwd on {lattice_points} lattice points), oracle/ f32 OpenMP'}
 	print(json.dumps(out))
-	if world > 1:
-		dist.destroy_process_group()
+	finish()
 
 
 if __name__ == '__main__':

@@ -10,7 +10,8 @@ count pinned to the reference's minimum, because the reference's own count is da
     ->  swap, two forward passes on the lattice (the |vorticity| and divergence fields the reference writes as VTI).
 
 Multi-GPU (one process per GPU): sample points are sharded — every rank draws its own N training and 8192 boundary
-samples (global Q = world * N, the loss normalisers use the global counts) and takes a 1/world slice of the lattice;
+samples (global Q = world * N, the loss normalisers use the global counts) and its own test_res^3 share of a lattice that
+is world times finer along z (fixed work per rank: weak scaling);
 Gaussian parameters, hash and optimiser state are replicated; ONE NCCL all-reduce per iteration sums the compact
 gradient accumulators and the loss partial sums, after which every rank runs the identical fused step, so the
 replicas stay bit-identical without a broadcast.
@@ -20,6 +21,23 @@ import torch
 from . import advance3d, gsr3d
 from .init_cond3d import sample_on_box
 from .synth import make_fast3d, synthetic_field
+
+
+def shard_lattice(test_res, rank, world, device):
+	"""
+	This rank's share of the test / output lattice, fixed work per rank: the job evaluates a
+	test_res x test_res x (world * test_res) lattice and rank r owns its z planes r, r + world, ...
+	(world = 1: the reference's test_res^3 lattice, 3D/GSR.py:719-725).
+	"""
+	ax = torch.linspace(0., 1., test_res, device=device)
+	az = torch.linspace(0., 1., test_res * world, device=device)[rank::world]
+	return torch.stack(torch.meshgrid(ax, ax, az, indexing='ij'), dim=-1).reshape(-1, 3).contiguous()
+
+
+def flat_layout(N, nblk, nblkb, AF=12):
+	"""offsets of the per-iteration all-reduce buffer: [3 accumulator sets (N, AF) | loss partials | boundary loss partials]"""
+	a = 3 * N * AF
+	return {'acc': (0, a), 'lp': (a, a + nblk * 8), 'lpb': (a + nblk * 8, a + (nblk + nblkb) * 8), 'total': a + (nblk + nblkb) * 8}
 
 
 class Census:
@@ -43,10 +61,11 @@ class ShardedProjector(advance3d.FusedProjector):
 		self.Q, self.Qb = Q, Qb
 		N = gv.N
 		nblk, nblkb = e.lib.gsr_loss_blocks(Q), e.lib.gsr_loss_blocks(Qb)
-		self.flat = torch.zeros(3 * N * 12 + (nblk + nblkb) * 8, dtype=torch.float32, device=gsr3d.device)
-		self.acc = self.flat[:3 * N * 12].view(3, N, 12)	# set 0: boundary (direct), sets 1, 2: vorticity / divergence
-		self.lp = self.flat[3 * N * 12:3 * N * 12 + nblk * 8].view(nblk, 8)
-		self.lpb = self.flat[3 * N * 12 + nblk * 8:].view(nblkb, 8)
+		lay = flat_layout(N, nblk, nblkb)
+		self.flat = torch.zeros(lay['total'], dtype=torch.float32, device=gsr3d.device)
+		self.acc = self.flat[lay['acc'][0]:lay['acc'][1]].view(3, N, 12)	# set 0: boundary (direct), sets 1, 2: vorticity / divergence
+		self.lp = self.flat[lay['lp'][0]:lay['lp'][1]].view(nblk, 8)
+		self.lpb = self.flat[lay['lpb'][0]:lay['lpb'][1]].view(nblkb, 8)
 		self.nblk, self.nblkb = nblk, nblkb
 
 	def restart(self):
@@ -102,9 +121,7 @@ class LeapfrogTimestep:
 		self.new = make_fast3d(P, S, R, V, 5e-3, mgs)
 		self.N = self.cur.N
 		dev = gsr3d.device
-		lattice = gsr3d.get_grid_points(0., 1., 0., 1., 0., 1., test_res, test_res, test_res)
-		per = (lattice.shape[0] + world - 1) // world
-		self.lattice = lattice[rank * per:(rank + 1) * per].contiguous()	# this rank's slice of the test / output lattice
+		self.lattice = shard_lattice(test_res, rank, world, dev)
 		self.last_test = None
 		self.graph_launches = 0
 		self._proj = {}
