@@ -122,3 +122,28 @@ def test_full_size_lattice_properties():
 	g3, v3 = o.gradient(lat, need_val=True)
 	assert rel_err(v3.cpu().numpy(), -2. * v1.cpu().numpy()) < 2e-6
 	assert rel_err(g3.cpu().numpy(), -2. * g1.cpu().numpy()) < 2e-6
+
+
+def test_ordering_from_another_grid_scale(tuning):
+	"""an ordering (perm / cell table / tile table) made under a different grid_scale only costs locality: results unchanged.
+	This is what lets the engine keep the ordering of a static lattice while the optimiser moves grid_scale."""
+	from gaussian_fluids_code_b200.synth import make_fast3d, synthetic_field
+	n, Q = 16, 40000
+	o1, (P, S, R, V, mgs), gen = field(n)
+	o2 = make_fast3d(P, S - .07, R, V, 5e-3, mgs)	# same grid dims, grid_scale larger by e^0.07
+	assert o1.grid_size == o2.grid_size and o2.grid_scale > 1.05 * o1.grid_scale
+	x = (torch.rand((Q, 3), generator=gen) * 1.2 - .1).cuda()
+	tuning(min_q=1)
+	e1 = o1._engine
+	e1.ensure_packed(o1._params())
+	own, other = e1.bin_samples(x, True), o2._engine.bin_samples(x, True)
+	assert other.tiles is not None and not torch.equal(own.perm, other.perm)
+	res = []
+	for b in (own, other):
+		val, grad = torch.empty((Q, 3), device='cuda'), torch.empty((Q, 3, 3), device='cuda')
+		e1.forward(x, val, grad, False, perm=b)
+		vor, hel = torch.empty((Q, 3), device='cuda'), torch.empty((Q,), device='cuda')
+		e1.advected_vorticity(x, -.02, vor, hel, perm=b)
+		res.append((val, grad, vor, hel))
+	for a, b, nm in zip(res[1], res[0], ('val', 'grad', 'vor', 'hel')):
+		same_rows(a.cpu().numpy(), b.cpu().numpy(), nm, flips=0.)
