@@ -166,7 +166,7 @@ class HashEngine:
 			pcell = self.lib.gsr_padded_cells(C.byref(self.desc))
 			scs = alloc('scs_', (pcell + 1,))
 		nbytes = self.lib.gsr_bin_samples_ws_bytes(C.byref(self.desc), C.c_int64(Q))
-		ws = self.scratch.get('sort', nbytes)
+		ws = self.scratch.get('sort_' + tag, nbytes)	# per tag: batches of different tags may be in flight on different streams
 		check(self.lib.gsr_bin_samples(C.byref(self.desc), ptr(x, name='x'), C.c_int64(Q), ptr(perm, torch.int32), ptr(scs, torch.int32, True), C.c_int(1 if need_tiles else 0),
 									   ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()), 'gsr_bin_samples')
 		tiles = None
@@ -255,7 +255,7 @@ class HashEngine:
 		elif acc.numel() != GSR_NSETS * self.N * AF:
 			raise _lib.GsrError('acc must hold 3 * N * GSR_ACC_FLOATS floats')
 		nbytes = self.lib.gsr_backward_ws_bytes(C.byref(self.desc), C.c_int64(self.N), C.c_int64(Q))
-		ws = self.scratch.get('adjoint', nbytes)
+		ws = self.scratch.get('adjoint_' + tag, nbytes)
 		mask = C.c_int(0)
 		check(self.lib.gsr_backward_gather(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
 										   ptr(self.packed, align16=True), C.c_int64(self.N), ptr(x, name='x'), C.c_int64(Q),

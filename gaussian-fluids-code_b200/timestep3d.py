@@ -67,6 +67,7 @@ class ShardedProjector(advance3d.FusedProjector):
 		self.lp = self.flat[lay['lp'][0]:lay['lp'][1]].view(nblk, 8)
 		self.lpb = self.flat[lay['lpb'][0]:lay['lpb'][1]].view(nblkb, 8)
 		self.nblk, self.nblkb = nblk, nblkb
+		self._streams = None
 
 	def restart(self):
 		"""begin a new project phase on the same buffers: fresh optimiser state, fresh hash"""
@@ -77,15 +78,51 @@ class ShardedProjector(advance3d.FusedProjector):
 		cur._engine.ensure_packed(cur._params())
 
 	def iterate(self, data, boundary=None, census=None):
+		"""
+		One optimiser iteration.  Three independent chains run on three streams (fork / join by events, so a captured graph
+		keeps the concurrency): the RK4 pull-back reference (previous field), the forward pass of the current field, and the
+		whole boundary pass; they meet at the adjoint kernel and at the all-reduce.
+		"""
 		gv, e = self.gv, self.gv._engine
 		cur = self.ref.velocity_field
 		Q, Qg = data.shape[0], data.shape[0] * self.world
+		main = torch.cuda.current_stream()
+		if self._streams is None:
+			self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+		s_fwd, s_bnd = self._streams if census is None else (main, main)	# the census pass shares one counter: keep it serial
+		fork = torch.cuda.Event()
+		fork.record(main)
+		mask_b = 0
+		srcs_b = []
+		if boundary is not None:
+			s_bnd.wait_event(fork)
+			with torch.cuda.stream(s_bnd):
+				bdata, bnormal = boundary
+				Qb, Qbg = bdata.shape[0], bdata.shape[0] * self.world
+				bins_b = e.bin_samples(bdata, True, tag='b')
+				perm_b, scs_b = bins_b
+				valb = self._tmp('valb', (Qb, 3))
+				e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
+				_, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
+											  {'normals': bnormal}, None, Q_norm=Qbg, tag='acc_b', acc=self.acc, loss_partials=self.lpb)
+				srcs_b = [(self.lpb, self.nblkb, [0., 0., 0., self.boundary_lambda / Qbg, 0., 0., 0., 0.])]
+				if census is not None:
+					e.count_pairs(bdata, census.c, 2, True)
+				done_b = torch.cuda.Event()
+				done_b.record(s_bnd)
 		bins = e.bin_samples(data, True)
 		perm, scs = bins
 		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
-		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
 		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
-		e.forward(data, val, grad, accumulate=False, perm=bins)
+		binned = torch.cuda.Event()
+		binned.record(main)
+		s_fwd.wait_event(binned)
+		with torch.cuda.stream(s_fwd):
+			e.forward(data, val, grad, accumulate=False, perm=bins)
+			done_f = torch.cuda.Event()
+			done_f.record(s_fwd)
+		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
+		main.wait_event(done_f)
 		_, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
 									{'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, Q_norm=Qg, acc=self.acc, loss_partials=self.lp)
 		srcs = [(self.lp, self.nblk, [self.w['vor'] / Qg, 0., self.w['div'] / Qg, 0., 0., 0., 0., 0.])]
@@ -93,18 +130,9 @@ class ShardedProjector(advance3d.FusedProjector):
 			cur._engine.count_pairs(data, census.c, 5, True)
 			e.count_pairs(data, census.c, 2, True)
 		if boundary is not None:
-			bdata, bnormal = boundary
-			Qb, Qbg = bdata.shape[0], bdata.shape[0] * self.world
-			bins_b = e.bin_samples(bdata, True, tag='b')
-			perm_b, scs_b = bins_b
-			valb = self._tmp('valb', (Qb, 3))
-			e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
-			_, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
-										  {'normals': bnormal}, None, Q_norm=Qbg, acc=self.acc, loss_partials=self.lpb)
+			main.wait_event(done_b)
 			mask |= mask_b
-			srcs.append((self.lpb, self.nblkb, [0., 0., 0., self.boundary_lambda / Qbg, 0., 0., 0., 0.]))
-			if census is not None:
-				e.count_pairs(bdata, census.c, 2, True)
+			srcs += srcs_b
 		if self.world > 1:
 			torch.distributed.all_reduce(self.flat)
 		self.stepper.step(gv._params(), self.acc, mask, loss_srcs=srcs)
