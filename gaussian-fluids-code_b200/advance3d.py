@@ -233,8 +233,7 @@ class FusedProjector:
 			lpb, nblkb = e.last_loss_partials
 			srcs.append((lpb, nblkb, [0., 0., 0., self.boundary_lambda / Qb, 0., 0., 0., 0.]))
 			extra.append(acc_b)
-		self.stepper.step(gv._params(), acc, mask, extra=extra, loss_srcs=srcs)
-		self._rebuild()
+		self.stepper.step([p.detach() for p in gv._params()], acc, mask, extra=extra, loss_srcs=srcs, rebuild=True)	# update + hash + packed records
 
 	def evaluate(self, data, probe=None):
 		"""losses of the current field on `data` without a gradient (the test pass, 3D/advance.py:226-235): device sums.

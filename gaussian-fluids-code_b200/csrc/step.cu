@@ -37,55 +37,62 @@ enum { S_DOT = 0 /* [g]: <g_vor, g_div> */, S_N1 = 4 /* |g_vor|^2 */, S_N2 = 8 /
 
 constexpr int ST_THREADS = 128;
 
+// per-Gaussian contributions to the partial sums of kernel A (added into S)
+template <int D>
+__device__ __forceinline__ void step_moments_one(int i, int N, const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot,
+						 const float *__restrict__ vals, const float *__restrict__ acc, int sets_mask, const float *__restrict__ pos_org,
+						 float aniso_ratio, float (&S)[S_COUNT])
+{
+	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR;
+	float sc[D], r[NR];
+#pragma unroll
+	for (int k = 0; k < D; k++) sc[k] = scal[(size_t)D * i + k];
+#pragma unroll
+	for (int k = 0; k < NR; k++) r[k] = rot[(size_t)NR * i + k];
+	if ((sets_mask & 6) == 6) {
+		float p1[D], s1[D], r1[NR], v1[D], p2[D], s2[D], r2[NR], v2[D];
+		param_grad<D>(acc + ((size_t)1 * N + i) * AF, sc, r, p1, s1, r1, v1);
+		param_grad<D>(acc + ((size_t)2 * N + i) * AF, sc, r, p2, s2, r2, v2);
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			S[S_DOT + 0] += p1[k] * p2[k]; S[S_N1 + 0] += p1[k] * p1[k]; S[S_N2 + 0] += p2[k] * p2[k];
+			S[S_DOT + 1] += s1[k] * s2[k]; S[S_N1 + 1] += s1[k] * s1[k]; S[S_N2 + 1] += s2[k] * s2[k];
+			S[S_DOT + 3] += v1[k] * v2[k]; S[S_N1 + 3] += v1[k] * v1[k]; S[S_N2 + 3] += v2[k] * v2[k];
+		}
+#pragma unroll
+		for (int k = 0; k < NR; k++) { S[S_DOT + 2] += r1[k] * r2[k]; S[S_N1 + 2] += r1[k] * r1[k]; S[S_N2 + 2] += r2[k] * r2[k]; }
+	}
+	// regulariser moments (3D/advance.py:237-242): V = exp(-sum s), rho = exp(max s - min s)
+	float ssum = 0.f, smin = sc[0], smax = sc[0];
+#pragma unroll
+	for (int k = 0; k < D; k++) { ssum += sc[k]; smin = fminf(smin, sc[k]); smax = fmaxf(smax, sc[k]); }
+	const float V = expf(-ssum);
+	S[S_V] += V;
+	S[S_V2] += V * V;
+	const float rho = expf(smax - smin);
+	S[S_ANISO] += (rho >= aniso_ratio ? rho : aniso_ratio) - aniso_ratio;
+#pragma unroll
+	for (int k = 0; k < D; k++) S[S_ABSV] += fabsf(vals[(size_t)D * i + k]);
+	if (pos_org) {
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			const float dlt = pos[(size_t)D * i + k] - pos_org[(size_t)D * i + k];
+			S[S_DPOS] += dlt * dlt;
+		}
+	}
+}
+
 template <int D>
 __global__ void __launch_bounds__(ST_THREADS) stepA_kernel(int N, const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot,
 							   const float *__restrict__ vals, const float *__restrict__ acc, int sets_mask,
 							   const float *__restrict__ pos_org, float aniso_ratio, float *__restrict__ partials)
 {
-	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR;
 	__shared__ float sm[ST_THREADS / 32][S_COUNT];
 	float S[S_COUNT];
 #pragma unroll
 	for (int k = 0; k < S_COUNT; k++) S[k] = 0.f;
 	int i = blockIdx.x * ST_THREADS + threadIdx.x;
-	if (i < N) {
-		float sc[D], r[NR];
-#pragma unroll
-		for (int k = 0; k < D; k++) sc[k] = scal[(size_t)D * i + k];
-#pragma unroll
-		for (int k = 0; k < NR; k++) r[k] = rot[(size_t)NR * i + k];
-		if ((sets_mask & 6) == 6) {
-			float p1[D], s1[D], r1[NR], v1[D], p2[D], s2[D], r2[NR], v2[D];
-			param_grad<D>(acc + ((size_t)1 * N + i) * AF, sc, r, p1, s1, r1, v1);
-			param_grad<D>(acc + ((size_t)2 * N + i) * AF, sc, r, p2, s2, r2, v2);
-#pragma unroll
-			for (int k = 0; k < D; k++) {
-				S[S_DOT + 0] += p1[k] * p2[k]; S[S_N1 + 0] += p1[k] * p1[k]; S[S_N2 + 0] += p2[k] * p2[k];
-				S[S_DOT + 1] += s1[k] * s2[k]; S[S_N1 + 1] += s1[k] * s1[k]; S[S_N2 + 1] += s2[k] * s2[k];
-				S[S_DOT + 3] += v1[k] * v2[k]; S[S_N1 + 3] += v1[k] * v1[k]; S[S_N2 + 3] += v2[k] * v2[k];
-			}
-#pragma unroll
-			for (int k = 0; k < NR; k++) { S[S_DOT + 2] += r1[k] * r2[k]; S[S_N1 + 2] += r1[k] * r1[k]; S[S_N2 + 2] += r2[k] * r2[k]; }
-		}
-		// regulariser moments (3D/advance.py:237-242): V = exp(-sum s), rho = exp(max s - min s)
-		float ssum = 0.f, smin = sc[0], smax = sc[0];
-#pragma unroll
-		for (int k = 0; k < D; k++) { ssum += sc[k]; smin = fminf(smin, sc[k]); smax = fmaxf(smax, sc[k]); }
-		const float V = expf(-ssum);
-		S[S_V] = V;
-		S[S_V2] = V * V;
-		const float rho = expf(smax - smin);
-		S[S_ANISO] = (rho >= aniso_ratio ? rho : aniso_ratio) - aniso_ratio;
-#pragma unroll
-		for (int k = 0; k < D; k++) S[S_ABSV] += fabsf(vals[(size_t)D * i + k]);
-		if (pos_org) {
-#pragma unroll
-			for (int k = 0; k < D; k++) {
-				const float dlt = pos[(size_t)D * i + k] - pos_org[(size_t)D * i + k];
-				S[S_DPOS] += dlt * dlt;
-			}
-		}
-	}
+	if (i < N) step_moments_one<D>(i, N, pos, scal, rot, vals, acc, sets_mask, pos_org, aniso_ratio, S);
 #pragma unroll
 	for (int k = 0; k < S_COUNT; k++) {
 #pragma unroll
@@ -115,34 +122,10 @@ struct LossSrcs {
 	int n;
 };
 
+// everything kernel R does once the global sums T are known: PCGrad coefficients, losses, Adam bias corrections, scheduler
 template <int D>
-__global__ void __launch_bounds__(256) stepR_kernel(gsr_step_cfg cfg, int N, int nblkA, const float *__restrict__ partials, LossSrcs ls, float *__restrict__ st)
+__device__ __forceinline__ void step_reduce_tail(const gsr_step_cfg &cfg, int N, const double *T, float *__restrict__ st)
 {
-	__shared__ double red[S_COUNT + 8][8];
-	// deterministic reduction: 8 strided lanes per slot, then a fixed-order sum
-	const int slot = threadIdx.x >> 3, lane = threadIdx.x & 7;
-	if (slot < S_COUNT) {
-		double s = 0.;
-		for (int b = lane; b < nblkA; b += 8) s += (double)partials[(size_t)b * S_COUNT + slot];
-		red[slot][lane] = s;
-	} else if (slot < S_COUNT + 8) {
-		const int k = slot - S_COUNT;
-		double s = 0.;
-		for (int src = 0; src < ls.n; src++) {
-			double t = 0.;
-			for (int b = lane; b < ls.nblocks[src]; b += 8) t += (double)ls.partials[src][(size_t)b * 8 + k];
-			s += (double)ls.w[src][k] * t;
-		}
-		red[slot][lane] = s;
-	}
-	__syncthreads();
-	if (threadIdx.x != 0) return;
-	double T[S_COUNT + 8];
-	for (int k = 0; k < S_COUNT + 8; k++) {
-		double s = 0.;
-		for (int l = 0; l < 8; l++) s += red[k][l];
-		T[k] = s;
-	}
 	// PCGrad coefficients (3D/advance.py:202-225): g1 -= <g1,n2> n2, g2 -= <g2,n1> n1 when <g1,g2> < 0
 	for (int g = 0; g < 4; g++) {
 		float a1 = 1.f, a2 = 1.f;
@@ -190,10 +173,131 @@ __global__ void __launch_bounds__(256) stepR_kernel(gsr_step_cfg cfg, int N, int
 	st[GSR_ST_BAD] = bad;
 }
 
+template <int D>
+__global__ void __launch_bounds__(256) stepR_kernel(gsr_step_cfg cfg, int N, int nblkA, const float *__restrict__ partials, LossSrcs ls, float *__restrict__ st)
+{
+	__shared__ double red[S_COUNT + 8][8];
+	// deterministic reduction: 8 strided lanes per slot, then a fixed-order sum
+	const int slot = threadIdx.x >> 3, lane = threadIdx.x & 7;
+	if (slot < S_COUNT) {
+		double s = 0.;
+		for (int b = lane; b < nblkA; b += 8) s += (double)partials[(size_t)b * S_COUNT + slot];
+		red[slot][lane] = s;
+	} else if (slot < S_COUNT + 8) {
+		const int k = slot - S_COUNT;
+		double s = 0.;
+		for (int src = 0; src < ls.n; src++) {
+			double t = 0.;
+			for (int b = lane; b < ls.nblocks[src]; b += 8) t += (double)ls.partials[src][(size_t)b * 8 + k];
+			s += (double)ls.w[src][k] * t;
+		}
+		red[slot][lane] = s;
+	}
+	__syncthreads();
+	if (threadIdx.x != 0) return;
+	double T[S_COUNT + 8];
+	for (int k = 0; k < S_COUNT + 8; k++) {
+		double s = 0.;
+		for (int l = 0; l < 8; l++) s += red[k][l];
+		T[k] = s;
+	}
+	step_reduce_tail<D>(cfg, N, T, st);
+}
+
 __device__ __forceinline__ void atomic_min_f(float *addr, float v)
 {
 	if (v >= 0.f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
 	else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+// projected total gradient + regulariser gradients + Adam for Gaussian i; returns min over its new scalings
+template <int D>
+__device__ __forceinline__ float step_update_one(const gsr_step_cfg &cfg, int N, int i, float *__restrict__ pos, float *__restrict__ scal, float *__restrict__ rot,
+						 float *__restrict__ vals, const float *__restrict__ acc, int sets_mask, const float *__restrict__ ex0,
+						 const float *__restrict__ ex1, const float *__restrict__ pos_org, float *__restrict__ st)
+{
+	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR, P = Dim<D>::P;
+	float smin = __int_as_float(0x7f800000);
+	float sc[D], r[NR], p[D], v[D];
+#pragma unroll
+	for (int k = 0; k < D; k++) { sc[k] = scal[(size_t)D * i + k]; p[k] = pos[(size_t)D * i + k]; v[k] = vals[(size_t)D * i + k]; }
+#pragma unroll
+	for (int k = 0; k < NR; k++) r[k] = rot[(size_t)NR * i + k];
+	float g[P];	// total gradient: [pos D][scal D][rot NR][val D]
+#pragma unroll
+	for (int k = 0; k < P; k++) g[k] = 0.f;
+	float gp[D], gs[D], gr[NR], gv[D];
+	auto add = [&](const float *a, float cp, float cs, float cr, float cv) {
+		param_grad<D>(a, sc, r, gp, gs, gr, gv);
+#pragma unroll
+		for (int k = 0; k < D; k++) { g[k] += cp * gp[k]; g[D + k] += cs * gs[k]; g[2 * D + NR + k] += cv * gv[k]; }
+#pragma unroll
+		for (int k = 0; k < NR; k++) g[2 * D + k] += cr * gr[k];
+	};
+	if (sets_mask & 2) add(acc + ((size_t)1 * N + i) * AF, st[C_A1 + 0], st[C_A1 + 1], st[C_A1 + 2], st[C_A1 + 3]);
+	if (sets_mask & 4) add(acc + ((size_t)2 * N + i) * AF, st[C_A2 + 0], st[C_A2 + 1], st[C_A2 + 2], st[C_A2 + 3]);
+	if (sets_mask & 1) add(acc + (size_t)i * AF, 1.f, 1.f, 1.f, 1.f);
+	if (ex0) add(ex0 + (size_t)i * AF, 1.f, 1.f, 1.f, 1.f);
+	if (ex1) add(ex1 + (size_t)i * AF, 1.f, 1.f, 1.f, 1.f);
+	// closed-form regulariser gradients (autograd in the reference, 3D/advance.py:237-244)
+	{
+		float ssum = 0.f;
+		int kmin = 0, kmax = 0;
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			ssum += sc[k];
+			if (sc[k] < sc[kmin]) kmin = k;	// first index on ties, like torch.min / torch.max
+			if (sc[k] > sc[kmax]) kmax = k;
+		}
+		const float rho = expf(sc[kmax] - sc[kmin]);
+		if (rho >= cfg.aniso_ratio && kmin != kmax) {
+			const float c = cfg.w_aniso * rho / (float)N;
+#pragma unroll
+			for (int k = 0; k < D; k++) g[D + k] += (k == kmax ? c : 0.f) - (k == kmin ? c : 0.f);
+		}
+		const float rV = expf(-ssum) / st[C_MEANV];
+		const float cv = -cfg.w_vol * 2.f / (float)N * rV * (rV - st[C_MEANR2]);
+#pragma unroll
+		for (int k = 0; k < D; k++) g[D + k] += cv;
+		if (cfg.w_valreg != 0.f) {
+			const float c = cfg.w_valreg / (float)(N * D);
+#pragma unroll
+			for (int k = 0; k < D; k++) g[2 * D + NR + k] += c * (float)((v[k] > 0.f) - (v[k] < 0.f));
+		}
+		if (pos_org && cfg.w_dpos != 0.f) {
+			const float c = cfg.w_dpos * 2.f / (float)(N * D);
+#pragma unroll
+			for (int k = 0; k < D; k++) g[k] += c * (p[k] - pos_org[(size_t)D * i + k]);
+		}
+	}
+	// Adam (torch.optim.Adam defaults; lr of the group as it was BEFORE this step's scheduler update)
+	float *m = st + GSR_STATE_SCALARS + (size_t)i * P, *vv = st + GSR_STATE_SCALARS + (size_t)N * P + (size_t)i * P;
+	float prm[P];
+#pragma unroll
+	for (int k = 0; k < D; k++) { prm[k] = p[k]; prm[D + k] = sc[k]; prm[2 * D + NR + k] = v[k]; }
+#pragma unroll
+	for (int k = 0; k < NR; k++) prm[2 * D + k] = r[k];
+	const float bc2 = st[C_BC2];
+#pragma unroll
+	for (int k = 0; k < P; k++) {
+		const int grp = k < D ? 0 : (k < 2 * D ? 1 : (k < 2 * D + NR ? 2 : 3));
+		const float mk = m[k] + (g[k] - m[k]) * (1.f - cfg.beta1);		// exp_avg.lerp_(grad, 1 - beta1)
+		const float vk = vv[k] * cfg.beta2 + (1.f - cfg.beta2) * g[k] * g[k];	// exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+		m[k] = mk;
+		vv[k] = vk;
+		const float denom = sqrtf(vk) * bc2 + cfg.eps;
+		prm[k] -= st[C_STEP + grp] * (mk / denom);
+	}
+#pragma unroll
+	for (int k = 0; k < D; k++) {
+		pos[(size_t)D * i + k] = prm[k];
+		scal[(size_t)D * i + k] = prm[D + k];
+		vals[(size_t)D * i + k] = prm[2 * D + NR + k];
+		smin = fminf(smin, prm[D + k]);
+	}
+#pragma unroll
+	for (int k = 0; k < NR; k++) rot[(size_t)NR * i + k] = prm[2 * D + k];
+	return smin;
 }
 
 template <int D>
@@ -201,90 +305,9 @@ __global__ void __launch_bounds__(ST_THREADS) stepB_kernel(gsr_step_cfg cfg, int
 							   const float *__restrict__ acc, int sets_mask, const float *__restrict__ ex0, const float *__restrict__ ex1,
 							   const float *__restrict__ pos_org, float *__restrict__ st)
 {
-	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR, P = Dim<D>::P;
 	int i = blockIdx.x * ST_THREADS + threadIdx.x;
 	float smin = __int_as_float(0x7f800000);
-	if (i < N) {
-		float sc[D], r[NR], p[D], v[D];
-#pragma unroll
-		for (int k = 0; k < D; k++) { sc[k] = scal[(size_t)D * i + k]; p[k] = pos[(size_t)D * i + k]; v[k] = vals[(size_t)D * i + k]; }
-#pragma unroll
-		for (int k = 0; k < NR; k++) r[k] = rot[(size_t)NR * i + k];
-		float g[P];	// total gradient: [pos D][scal D][rot NR][val D]
-#pragma unroll
-		for (int k = 0; k < P; k++) g[k] = 0.f;
-		float gp[D], gs[D], gr[NR], gv[D];
-		auto add = [&](const float *a, float cp, float cs, float cr, float cv) {
-			param_grad<D>(a, sc, r, gp, gs, gr, gv);
-#pragma unroll
-			for (int k = 0; k < D; k++) { g[k] += cp * gp[k]; g[D + k] += cs * gs[k]; g[2 * D + NR + k] += cv * gv[k]; }
-#pragma unroll
-			for (int k = 0; k < NR; k++) g[2 * D + k] += cr * gr[k];
-		};
-		if (sets_mask & 2) add(acc + ((size_t)1 * N + i) * AF, st[C_A1 + 0], st[C_A1 + 1], st[C_A1 + 2], st[C_A1 + 3]);
-		if (sets_mask & 4) add(acc + ((size_t)2 * N + i) * AF, st[C_A2 + 0], st[C_A2 + 1], st[C_A2 + 2], st[C_A2 + 3]);
-		if (sets_mask & 1) add(acc + (size_t)i * AF, 1.f, 1.f, 1.f, 1.f);
-		if (ex0) add(ex0 + (size_t)i * AF, 1.f, 1.f, 1.f, 1.f);
-		if (ex1) add(ex1 + (size_t)i * AF, 1.f, 1.f, 1.f, 1.f);
-		// closed-form regulariser gradients (autograd in the reference, 3D/advance.py:237-244)
-		{
-			float ssum = 0.f;
-			int kmin = 0, kmax = 0;
-#pragma unroll
-			for (int k = 0; k < D; k++) {
-				ssum += sc[k];
-				if (sc[k] < sc[kmin]) kmin = k;	// first index on ties, like torch.min / torch.max
-				if (sc[k] > sc[kmax]) kmax = k;
-			}
-			const float rho = expf(sc[kmax] - sc[kmin]);
-			if (rho >= cfg.aniso_ratio && kmin != kmax) {
-				const float c = cfg.w_aniso * rho / (float)N;
-#pragma unroll
-				for (int k = 0; k < D; k++) g[D + k] += (k == kmax ? c : 0.f) - (k == kmin ? c : 0.f);
-			}
-			const float rV = expf(-ssum) / st[C_MEANV];
-			const float cv = -cfg.w_vol * 2.f / (float)N * rV * (rV - st[C_MEANR2]);
-#pragma unroll
-			for (int k = 0; k < D; k++) g[D + k] += cv;
-			if (cfg.w_valreg != 0.f) {
-				const float c = cfg.w_valreg / (float)(N * D);
-#pragma unroll
-				for (int k = 0; k < D; k++) g[2 * D + NR + k] += c * (float)((v[k] > 0.f) - (v[k] < 0.f));
-			}
-			if (pos_org && cfg.w_dpos != 0.f) {
-				const float c = cfg.w_dpos * 2.f / (float)(N * D);
-#pragma unroll
-				for (int k = 0; k < D; k++) g[k] += c * (p[k] - pos_org[(size_t)D * i + k]);
-			}
-		}
-		// Adam (torch.optim.Adam defaults; lr of the group as it was BEFORE this step's scheduler update)
-		float *m = st + GSR_STATE_SCALARS + (size_t)i * P, *vv = st + GSR_STATE_SCALARS + (size_t)N * P + (size_t)i * P;
-		float prm[P];
-#pragma unroll
-		for (int k = 0; k < D; k++) { prm[k] = p[k]; prm[D + k] = sc[k]; prm[2 * D + NR + k] = v[k]; }
-#pragma unroll
-		for (int k = 0; k < NR; k++) prm[2 * D + k] = r[k];
-		const float bc2 = st[C_BC2];
-#pragma unroll
-		for (int k = 0; k < P; k++) {
-			const int grp = k < D ? 0 : (k < 2 * D ? 1 : (k < 2 * D + NR ? 2 : 3));
-			const float mk = m[k] + (g[k] - m[k]) * (1.f - cfg.beta1);		// exp_avg.lerp_(grad, 1 - beta1)
-			const float vk = vv[k] * cfg.beta2 + (1.f - cfg.beta2) * g[k] * g[k];	// exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-			m[k] = mk;
-			vv[k] = vk;
-			const float denom = sqrtf(vk) * bc2 + cfg.eps;
-			prm[k] -= st[C_STEP + grp] * (mk / denom);
-		}
-#pragma unroll
-		for (int k = 0; k < D; k++) {
-			pos[(size_t)D * i + k] = prm[k];
-			scal[(size_t)D * i + k] = prm[D + k];
-			vals[(size_t)D * i + k] = prm[2 * D + NR + k];
-			smin = fminf(smin, prm[D + k]);
-		}
-#pragma unroll
-		for (int k = 0; k < NR; k++) rot[(size_t)NR * i + k] = prm[2 * D + k];
-	}
+	if (i < N) smin = step_update_one<D>(cfg, N, i, pos, scal, rot, vals, acc, sets_mask, ex0, ex1, pos_org, st);
 #pragma unroll
 	for (int o = 16; o; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
 	if ((threadIdx.x & 31) == 0) atomic_min_f(st + GSR_ST_MIN_S, smin);
@@ -292,14 +315,19 @@ __global__ void __launch_bounds__(ST_THREADS) stepB_kernel(gsr_step_cfg cfg, int
 
 // next grid_scale (3D/GSR.py:248-251), formed in double like the reference's host code, then rounded to f32;
 // re-arms the min accumulator for the next iteration.
-__global__ void stepS_kernel(gsr_step_cfg cfg, float *st, float *min_out)
+__device__ __forceinline__ void step_grid_scale(const gsr_step_cfg &cfg, float *st, float min_s)
 {
-	const float min_s = st[GSR_ST_MIN_S];
 	double gs = cfg.grid_scale_tau0;
 	if (cfg.grid_coef > 0.) gs = fmax(cfg.grid_coef * exp(-(double)min_s), cfg.min_grid_scale);
 	st[GSR_ST_GRID_SCALE] = (float)gs;
-	if (min_out) *min_out = min_s;
 	st[GSR_ST_MIN_S] = __int_as_float(0x7f800000);
+}
+
+__global__ void stepS_kernel(gsr_step_cfg cfg, float *st, float *min_out)
+{
+	const float min_s = st[GSR_ST_MIN_S];
+	if (min_out) *min_out = min_s;
+	step_grid_scale(cfg, st, min_s);
 }
 
 __global__ void init_state_kernel(float *st, size_t n_moments, gsr_step_cfg cfg)
@@ -353,14 +381,20 @@ extern "C" int gsr_step_init(const gsr_step_cfg *cfg, int64_t N, const float *sc
 	return GSR_OK;
 }
 
-extern "C" int gsr_step(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalings, float *rotations, float *values,
-			const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
-			const float *positions_org, float *state, void *ws, size_t ws_bytes, void *stream)
+static int step_impl(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalings, float *rotations, float *values,
+		     const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
+		     const float *positions_org, float *state, void *ws, size_t ws_bytes,
+		     const gsr_grid_desc *gd, int32_t *cell_start, int32_t *sorted_id, float *packed, float *cull, void *hash_ws, size_t hash_ws_bytes, void *stream)
 {
 	if (!cfg || (cfg->D != 2 && cfg->D != 3) || N <= 0 || N >= ((int64_t)1 << 30) || !state || !positions || !scalings || !rotations || !values) return GSR_EINVAL;
 	if ((sets_mask & 7) && !acc) return GSR_EINVAL;
 	if (n_loss_src < 0 || n_loss_src > 3) return GSR_EINVAL;
 	if (ws_bytes < gsr_step_ws_bytes(cfg->D, N)) return GSR_EWS;
+	Grid g;
+	if (gd) {
+		if (!make_grid(gd, g) || g.D != cfg->D || !cell_start || !sorted_id || !packed) return GSR_EINVAL;
+		if (hash_ws_bytes < gsr_build_grid_ws_bytes(gd, N)) return GSR_EWS;
+	}
 	cudaStream_t st = (cudaStream_t)stream;
 	const int n = (int)N, nblk = (n + ST_THREADS - 1) / ST_THREADS;
 	float *partials = (float *)ws;
@@ -384,5 +418,25 @@ extern "C" int gsr_step(const gsr_step_cfg *cfg, int64_t N, float *positions, fl
 	stepS_kernel<<<1, 1, 0, st>>>(*cfg, state, nullptr);
 	g_launches += 4;
 	GSR_CHECK_LAUNCH();
+	if (gd) return gsr_build_grid(gd, positions, N, cell_start, sorted_id, nullptr, nullptr, scalings, rotations, values, packed, cull, hash_ws, hash_ws_bytes, stream);
 	return GSR_OK;
+}
+
+extern "C" int gsr_step(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalings, float *rotations, float *values,
+			const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
+			const float *positions_org, float *state, void *ws, size_t ws_bytes, void *stream)
+{
+	return step_impl(cfg, N, positions, scalings, rotations, values, acc, sets_mask, extra_direct, loss_src, n_loss_src, positions_org, state, ws, ws_bytes,
+			 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int gsr_step_rebuild(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalings, float *rotations, float *values,
+				const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
+				const float *positions_org, float *state, void *ws, size_t ws_bytes,
+				const gsr_grid_desc *g, int32_t *cell_start, int32_t *sorted_id, float *packed, float *cull, void *hash_ws, size_t hash_ws_bytes,
+				void *stream)
+{
+	if (!g) return GSR_EINVAL;
+	return step_impl(cfg, N, positions, scalings, rotations, values, acc, sets_mask, extra_direct, loss_src, n_loss_src, positions_org, state, ws, ws_bytes,
+			 g, cell_start, sorted_id, packed, cull, hash_ws, hash_ws_bytes, stream);
 }

@@ -345,7 +345,9 @@ class FusedStepper:
 		# from now on the engine's kernels read grid_scale from the device-resident state
 		self.e.desc.grid_scale_dev = self.state.data_ptr() + 4 * _lib.ST_GRID_SCALE
 
-	def step(self, params, acc, mask, extra=(), loss_srcs=(), positions_org=None):
+	def step(self, params, acc, mask, extra=(), loss_srcs=(), positions_org=None, rebuild=False):
+		"""one optimiser iteration (gsr_step); rebuild=True also rebuilds the engine's hash and packed records from the updated
+		parameters (gsr_step_rebuild: one launch for small N)"""
 		p, s, r, v = params
 		ex = (C.c_void_p * 2)()
 		for k in range(2):
@@ -356,6 +358,18 @@ class FusedStepper:
 			srcs[k].nblocks = int(nblk)
 			for q in range(8):
 				srcs[k].w[q] = float(w[q])
+		if rebuild:
+			e = self.e
+			if e.N != self.N or e.packed is None:
+				raise _lib.GsrError('rebuild needs an engine that already holds a hash of these Gaussians')
+			hws = e.scratch.get('sort', e.lib.gsr_build_grid_ws_bytes(C.byref(e.desc), C.c_int64(self.N)))
+			check(e.lib.gsr_step_rebuild(C.byref(self.cfg), C.c_int64(self.N), ptr(p), ptr(s), ptr(r, align16=True), ptr(v),
+										 ptr(acc, allow_none=True, align16=True), C.c_int(mask), ex, srcs, C.c_int(len(loss_srcs)),
+										 ptr(positions_org, allow_none=True), ptr(self.state), ptr(self.ws, torch.uint8), C.c_size_t(self.ws.numel()),
+										 C.byref(e.desc), ptr(e.cell_start, torch.int32), ptr(e.sorted_id, torch.int32), ptr(e.packed, align16=True), ptr(e.cull),
+										 ptr(hws, torch.uint8), C.c_size_t(hws.numel()), stream()), 'gsr_step_rebuild')
+			e._packed_key = None
+			return
 		check(self.e.lib.gsr_step(C.byref(self.cfg), C.c_int64(self.N), ptr(p), ptr(s), ptr(r), ptr(v),
 								  ptr(acc, allow_none=True, align16=True), C.c_int(mask), ex, srcs, C.c_int(len(loss_srcs)),
 								  ptr(positions_org, allow_none=True), ptr(self.state), ptr(self.ws, torch.uint8), C.c_size_t(self.ws.numel()), stream()), 'gsr_step')

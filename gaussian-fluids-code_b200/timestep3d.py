@@ -135,8 +135,7 @@ class ShardedProjector(advance3d.FusedProjector):
 			srcs += srcs_b
 		if self.world > 1:
 			torch.distributed.all_reduce(self.flat)
-		self.stepper.step(gv._params(), self.acc, mask, loss_srcs=srcs)
-		self._rebuild()
+		self.stepper.step([p.detach() for p in gv._params()], self.acc, mask, loss_srcs=srcs, rebuild=True)	# update + hash + packed records
 
 
 class LeapfrogTimestep:

@@ -236,6 +236,17 @@ int gsr_step(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalin
 	     const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
 	     const float *positions_org, float *state, void *ws, size_t ws_bytes, void *stream);
 
+/* gsr_step followed by the hash rebuild and the packed records of the UPDATED Gaussians (the reference's step() ->
+ * zero_grad() -> reinitialize_grid(), 3D/GSR.py:704-716) in one call.  (A single-CTA fusion of the five kernels was measured
+ * SLOWER at N = 1000 — 50 us against 35 us: the per-Gaussian dependency chains, not the launches, set the latency.)
+ * g->grid_scale_dev should point at state + GSR_ST_GRID_SCALE so that the rebuilt hash uses the new grid_scale.
+ * hash_ws: gsr_build_grid_ws_bytes(g, N). */
+int gsr_step_rebuild(const gsr_step_cfg *cfg, int64_t N, float *positions, float *scalings, float *rotations, float *values,
+		     const float *acc, int sets_mask, const float *const extra_direct[2], const gsr_loss_src *loss_src, int n_loss_src,
+		     const float *positions_org, float *state, void *ws, size_t ws_bytes,
+		     const gsr_grid_desc *g, int32_t *cell_start, int32_t *sorted_id, float *packed, float *cull, void *hash_ws, size_t hash_ws_bytes,
+		     void *stream);
+
 /* ---- a7: sample generation  (3D/advance.py:339-340 rand_like(positions) * extent + min; 3D/init_cond.py:227-249
  *          sample_on_box) — one kernel per sample set, counter-based Philox keyed by (seed, stream_id) and indexed by
  *          (sample, iteration); the iteration number is read from DEVICE memory (e.g. state + GSR_ST_T, may be NULL = 0)
