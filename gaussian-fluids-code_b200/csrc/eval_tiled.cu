@@ -87,11 +87,11 @@ __device__ __forceinline__ float4 ld4(const float4 *p)
 	return v;
 }
 
-// Tile lookup, staging box, TMA bulk copies.  Returns false for an unused tile slot (whole CTA exits).
-__device__ __forceinline__ bool tile_begin3(const TiledArgs &a, TileSh &sh, float4 *srec, uint64_t *mbar, int &t0, int &t1)
+// Tile lookup: the row and the range [t0, t1) of sorted samples of this CTA.  Returns false for an unused tile slot.
+__device__ __forceinline__ bool tile_locate3(const TiledArgs &a, int &r, int &t0, int &t1)
 {
 	const Grid &g = a.P.g;
-	const int r = __ldg(a.tile_row + blockIdx.x);
+	r = __ldg(a.tile_row + blockIdx.x);
 	if (r < 0) return false;
 	const int rowlen = g.pdims[2];
 	const int nrows = g.pdims[0] * g.pdims[1];
@@ -100,6 +100,15 @@ __device__ __forceinline__ bool tile_begin3(const TiledArgs &a, TileSh &sh, floa
 	const int base = s_r / TL_TILE + r;
 	t0 = s_r + ((int)blockIdx.x - base) * TL_TILE;
 	t1 = min(t0 + TL_TILE, e_r);
+	return true;
+}
+
+// Staging box and TMA bulk copies of the tile (the threads load their points before calling this, so that those
+// loads are in flight while warp 0 walks the dependent chain perm -> x -> cell_start -> bulk copy).
+__device__ __forceinline__ void tile_stage3(const TiledArgs &a, int r, int t0, int t1, TileSh &sh, float4 *srec, uint64_t *mbar)
+{
+	const Grid &g = a.P.g;
+	const int nrows = g.pdims[0] * g.pdims[1];
 	if (threadIdx.x < 32) {
 		const int lane = threadIdx.x;
 		const bool stage = r < nrows;	// the tail "row" holds the samples outside the padded grid: nothing to stage
@@ -142,7 +151,6 @@ __device__ __forceinline__ bool tile_begin3(const TiledArgs &a, TileSh &sh, floa
 	}
 	__syncthreads();
 	if (sh.staged) mbar_wait(mbar, 0);
-	return true;
 }
 
 // order-preserving float <-> int map (for redux.sync min / max on floats)
@@ -160,7 +168,7 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >>
 //     cull = (1 + margin) / lambda_min(Sigma^-1), from gsr_pack_gaussians) misses the bounding box of the warp's 32 P
 //     points is skipped by a uniform branch before its covariance is even loaded;
 //   * the survivors are tested on point PAIRS with packed FP32 (f32x2.cuh): 14 FFMA2/FMUL2/FADD2 per two points.
-template <int P, bool NEED_GRAD>
+template <int P, bool NEED_GRAD, bool PREFETCH>
 __device__ __forceinline__ void warp_eval3(const TiledArgs &a, const TileSh &sh, const float4 *srec, const float (&x)[P], const float (&y)[P],
 					   const float (&z)[P], const bool (&ok)[P], float (&u)[P][3], float (&G)[P][9])
 {
@@ -282,14 +290,28 @@ __device__ __forceinline__ void warp_eval3(const TiledArgs &a, const TileSh &sh,
 						}
 						unsigned mask = __ballot_sync(FULL, keep);
 						const unsigned smask = __ballot_sync(FULL, st_c);
-						while (mask) {	// survivors, in cell-sorted order; everything below is warp-uniform
+						// survivors, in cell-sorted order; everything below is warp-uniform.  The record of the NEXT survivor
+						// is requested before the current one is evaluated (the loads are the only long-latency step left).
+						int ci = 0;
+						float4 n0, n1, n2;
+						if (mask) {
 							const int l = __ffs(mask) - 1;
-							mask &= mask - 1;
-							const int ci = c0 + l;
+							ci = c0 + l;
 							const float4 *ptr = ((smask >> l) & 1u) ? srec + 3 * (soff + ci) : a.packed + 3 * (size_t)ci;
-							const float4 p0 = ld4(ptr), p1 = ld4(ptr + 1), p2 = ld4(ptr + 2);
+							n0 = ld4(ptr); n1 = ld4(ptr + 1); n2 = ld4(ptr + 2);
+						}
+						while (mask) {
+							const float4 p0 = n0, p1 = n1, p2 = n2;
+							const int ci_cur = ci;
+							mask &= mask - 1;
+							if (PREFETCH && mask) {
+								const int l = __ffs(mask) - 1;
+								ci = c0 + l;
+								const float4 *ptr = ((smask >> l) & 1u) ? srec + 3 * (soff + ci) : a.packed + 3 * (size_t)ci;
+								n0 = ld4(ptr); n1 = ld4(ptr + 1); n2 = ld4(ptr + 2);
+							}
 							if (mixed) {
-								const int zci = zg + (ci >= b1) + (ci >= b2) + (ci >= b3);
+								const int zci = zg + (ci_cur >= b1) + (ci_cur >= b2) + (ci_cur >= b3);
 #pragma unroll
 								for (int p = 0; p < P; p++) thr[p] = (rowok[p] && abs(zci - cz[p]) <= 1) ? q_thr : -1.f;
 							}
@@ -324,6 +346,12 @@ __device__ __forceinline__ void warp_eval3(const TiledArgs &a, const TileSh &sh,
 									}
 								}
 							}
+							if (!PREFETCH && mask) {
+								const int l = __ffs(mask) - 1;
+								ci = c0 + l;
+								const float4 *ptr = ((smask >> l) & 1u) ? srec + 3 * (soff + ci) : a.packed + 3 * (size_t)ci;
+								n0 = ld4(ptr); n1 = ld4(ptr + 1); n2 = ld4(ptr + 2);
+							}
 						}
 					}
 				}
@@ -351,13 +379,13 @@ __device__ __forceinline__ int slot_pos(int t0, int p)
 }
 
 template <int P, bool NEED_VAL, bool NEED_GRAD, bool ACCUM>
-__global__ void __launch_bounds__(TL_TILE / P) forward_tiled3_kernel(TiledArgs a, float *__restrict__ val, float *__restrict__ grad)
+__global__ void __launch_bounds__(TL_TILE / P, P == 4 ? (NEED_GRAD ? 4 : 5) : 2) forward_tiled3_kernel(TiledArgs a, float *__restrict__ val, float *__restrict__ grad)
 {
 	__shared__ TileSh sh;
 	__shared__ __align__(8) uint64_t mbar;
 	float4 *srec = reinterpret_cast<float4 *>(tl_smem);
-	int t0, t1;
-	if (!tile_begin3(a, sh, srec, &mbar, t0, t1)) return;
+	int r, t0, t1;
+	if (!tile_locate3(a, r, t0, t1)) return;
 	float x[P], y[P], z[P], u[P][3], G[P][9];
 	bool ok[P];
 	size_t j[P];
@@ -370,7 +398,8 @@ __global__ void __launch_bounds__(TL_TILE / P) forward_tiled3_kernel(TiledArgs a
 		y[p] = ok[p] ? a.x[3 * j[p] + 1] : 0.f;
 		z[p] = ok[p] ? a.x[3 * j[p] + 2] : 0.f;
 	}
-	warp_eval3<P, NEED_GRAD>(a, sh, srec, x, y, z, ok, u, G);
+	tile_stage3(a, r, t0, t1, sh, srec, &mbar);
+	warp_eval3<P, NEED_GRAD, NEED_GRAD>(a, sh, srec, x, y, z, ok, u, G);
 #pragma unroll
 	for (int p = 0; p < P; p++) {
 		if (!ok[p]) continue;
@@ -401,8 +430,8 @@ __global__ void __launch_bounds__(TL_TILE / P) rk4_tiled3_kernel(TiledArgs a, fl
 	__shared__ TileSh sh;
 	__shared__ __align__(8) uint64_t mbar;
 	float4 *srec = reinterpret_cast<float4 *>(tl_smem);
-	int t0, t1;
-	if (!tile_begin3(a, sh, srec, &mbar, t0, t1)) return;
+	int r, t0, t1;
+	if (!tile_locate3(a, r, t0, t1)) return;
 	float x0[P], x1[P], x2[P], px[P], py[P], pz[P], v[P][3], dv[P][9], vs[P][3], A[P][9], S[P][9];
 	bool ok[P];
 	size_t j[P];
@@ -416,10 +445,11 @@ __global__ void __launch_bounds__(TL_TILE / P) rk4_tiled3_kernel(TiledArgs a, fl
 		pz[p] = x2[p] = ok[p] ? a.x[3 * j[p] + 2] : 0.f;
 		vs[p][0] = vs[p][1] = vs[p][2] = 0.f;
 	}
+	tile_stage3(a, r, t0, t1, sh, srec, &mbar);
 	const float hdt = dt * .5f, dt6 = dt / 6.f;
 #pragma unroll 1
 	for (int st = 0; st < 4; st++) {
-		warp_eval3<P, FULLM>(a, sh, srec, px, py, pz, ok, v, dv);
+		warp_eval3<P, FULLM, false>(a, sh, srec, px, py, pz, ok, v, dv);
 		const float wgt = (st == 0 || st == 3) ? 1.f : 2.f;	// RK4 weights 1 2 2 1
 		const float step = (st < 2) ? hdt : dt;			// the NEXT stage point: x + step * v
 #pragma unroll
@@ -450,7 +480,7 @@ __global__ void __launch_bounds__(TL_TILE / P) rk4_tiled3_kernel(TiledArgs a, fl
 		}
 	}
 	if (FULLM) {
-		warp_eval3<P, true>(a, sh, srec, px, py, pz, ok, v, dv);
+		warp_eval3<P, true, false>(a, sh, srec, px, py, pz, ok, v, dv);
 #pragma unroll
 		for (int p = 0; p < P; p++) {
 			if (!ok[p]) continue;
@@ -479,6 +509,103 @@ __global__ void __launch_bounds__(TL_TILE / P) rk4_tiled3_kernel(TiledArgs a, fl
 	}
 }
 
+// RK4 with the deformation chain, 4 points per thread: the per-point integrator state (start point, velocity sum, S and
+// dphi: 24 floats) lives in SHARED memory between the evaluations, [slot][thread] so that lanes touch consecutive banks;
+// only the evaluation itself (the forward kernel's register footprint) is in registers.
+constexpr int RKS_P = 4;
+constexpr int RKS_STATE = 24;	// x0 3 | vs 3 | S 9 | A 9
+
+template <int MODE>
+__global__ void __launch_bounds__(TL_TILE / RKS_P, 3) rk4_tiled3s_kernel(TiledArgs a, float dt, float *__restrict__ goal_pos, float *__restrict__ deformation,
+									  float *__restrict__ goal_val, float *__restrict__ goal_grad, float *__restrict__ ref_vor,
+									  float *__restrict__ ref_hel)
+{
+	constexpr int P = RKS_P, T = TL_TILE / RKS_P;
+	__shared__ TileSh sh;
+	__shared__ __align__(8) uint64_t mbar;
+	float4 *srec = reinterpret_cast<float4 *>(tl_smem);
+	float *state = reinterpret_cast<float *>(tl_smem + (size_t)a.cap * 48) + threadIdx.x;	// + (p * RKS_STATE + k) * T
+	int r, t0, t1;
+	if (!tile_locate3(a, r, t0, t1)) return;
+	float px[P], py[P], pz[P], v[P][3], dv[P][9];
+	bool ok[P];
+#pragma unroll
+	for (int p = 0; p < P; p++) {
+		const int t = slot_pos<P>(t0, p);
+		ok[p] = t < t1;
+		const size_t j = ok[p] ? (size_t)a.perm[t] : 0;
+		px[p] = ok[p] ? a.x[3 * j] : 0.f;
+		py[p] = ok[p] ? a.x[3 * j + 1] : 0.f;
+		pz[p] = ok[p] ? a.x[3 * j + 2] : 0.f;
+		float *sp = state + (p * RKS_STATE) * T;
+		sp[0] = px[p]; sp[T] = py[p]; sp[2 * T] = pz[p];
+		sp[3 * T] = 0.f; sp[4 * T] = 0.f; sp[5 * T] = 0.f;
+	}
+	tile_stage3(a, r, t0, t1, sh, srec, &mbar);
+	const float hdt = dt * .5f, dt6 = dt / 6.f;
+#pragma unroll 1
+	for (int st = 0; st < 4; st++) {
+		warp_eval3<P, true, true>(a, sh, srec, px, py, pz, ok, v, dv);
+		const float wgt = (st == 0 || st == 3) ? 1.f : 2.f;
+		const float step = (st < 2) ? hdt : dt;
+#pragma unroll
+		for (int p = 0; p < P; p++) {
+			float *sp = state + (p * RKS_STATE) * T;
+#pragma unroll
+			for (int k = 0; k < 3; k++) sp[(3 + k) * T] += wgt * v[p][k];
+			float B[9];
+			if (st == 0) {
+#pragma unroll
+				for (int k = 0; k < 9; k++) B[k] = dv[p][k];
+			} else {
+				float A[9];
+#pragma unroll
+				for (int k = 0; k < 9; k++) A[k] = sp[(15 + k) * T];
+				mm3(dv[p], A, B);	// dv_st @ dphi_st
+			}
+#pragma unroll
+			for (int k = 0; k < 9; k++) {
+				sp[(6 + k) * T] = (st == 0) ? B[k] : sp[(6 + k) * T] + wgt * B[k];
+				sp[(15 + k) * T] = ((k % 4 == 0) ? 1.f : 0.f) + step * B[k];	// dphi_{st+1}
+			}
+			px[p] = sp[0] + step * v[p][0]; py[p] = sp[T] + step * v[p][1]; pz[p] = sp[2 * T] + step * v[p][2];
+		}
+	}
+#pragma unroll
+	for (int p = 0; p < P; p++) {
+		const float *sp = state + (p * RKS_STATE) * T;
+		px[p] = sp[0] + dt6 * sp[3 * T]; py[p] = sp[T] + dt6 * sp[4 * T]; pz[p] = sp[2 * T] + dt6 * sp[5 * T];
+	}
+	warp_eval3<P, true, true>(a, sh, srec, px, py, pz, ok, v, dv);
+#pragma unroll
+	for (int p = 0; p < P; p++) {
+		if (!ok[p]) continue;
+		const float *sp = state + (p * RKS_STATE) * T;
+		const size_t jj = (size_t)a.perm[slot_pos<P>(t0, p)];
+		float D[9];
+#pragma unroll
+		for (int k = 0; k < 9; k++) D[k] = ((k % 4 == 0) ? 1.f : 0.f) + dt6 * sp[(6 + k) * T];	// dphi
+		if (MODE == 1) {
+			goal_pos[3 * jj] = px[p]; goal_pos[3 * jj + 1] = py[p]; goal_pos[3 * jj + 2] = pz[p];
+#pragma unroll
+			for (int k = 0; k < 9; k++) { deformation[9 * jj + k] = D[k]; goal_grad[9 * jj + k] = dv[p][k]; }
+			goal_val[3 * jj] = v[p][0]; goal_val[3 * jj + 1] = v[p][1]; goal_val[3 * jj + 2] = v[p][2];
+		} else {
+			const float *d = dv[p];
+			const float w0 = d[7] - d[5], w1 = d[2] - d[6], w2 = d[3] - d[1];
+			if (ref_hel) ref_hel[jj] = v[p][0] * w0 + v[p][1] * w1 + v[p][2] * w2;
+			const float c00 = D[4] * D[8] - D[5] * D[7], c01 = D[2] * D[7] - D[1] * D[8], c02 = D[1] * D[5] - D[2] * D[4];
+			const float c10 = D[5] * D[6] - D[3] * D[8], c11 = D[0] * D[8] - D[2] * D[6], c12 = D[2] * D[3] - D[0] * D[5];
+			const float c20 = D[3] * D[7] - D[4] * D[6], c21 = D[1] * D[6] - D[0] * D[7], c22 = D[0] * D[4] - D[1] * D[3];
+			const float det = D[0] * c00 + D[1] * c10 + D[2] * c20;
+			const float inv = 1.f / det;
+			ref_vor[3 * jj] = (c00 * w0 + c01 * w1 + c02 * w2) * inv;
+			ref_vor[3 * jj + 1] = (c10 * w0 + c11 * w1 + c12 * w2) * inv;
+			ref_vor[3 * jj + 2] = (c20 * w0 + c21 * w1 + c22 * w2) * inv;
+		}
+	}
+}
+
 // ---- tile -> row table ----------------------------------------------------------------------------
 // Row r (a fixed (x, y) pair of the padded sample grid; r == nrows: the samples outside it) owns the tile ids
 // [s_r / T + r, s_r / T + r + ceil(n_r / T)), s_r = first sorted sample of the row.  The ranges of different rows
@@ -502,14 +629,19 @@ static int64_t tile_slots(const Grid &g, int64_t Q)
 
 // tunables (gsr_set_tuning)
 int g_tiled_min_q = 1 << 17;
-int g_tiled_cap = 768;
+int g_tiled_cap = 512;
+int g_fw_p4_min_spc = 0;	// samples per cell above which the forward kernel takes 4 points per thread (else 2)
+int g_rk4_smem_state = 1;	// 1: RK4 with the deformation chain keeps its state in shared memory (4 points / thread)
 
 static size_t tiled_smem(int cap) { return (size_t)cap * 48; }
 
 template <typename K>
-static int prep(K kernel, int cap)
+static int prep(K kernel, int cap, bool max_shared)
 {
 	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem(cap));
+	// forward: 4-5 CTAs per SM are register-feasible, so ask for the large shared-memory carve-out; the RK4 kernels are
+	// register-limited to 2 CTAs and keep the default split (their few spilled values live in L1)
+	if (e == cudaSuccess && max_shared) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -542,6 +674,8 @@ extern "C" int gsr_set_tuning(int key, int value)
 {
 	switch (key) {
 	case GSR_TUNE_TILED_MIN_Q: g_tiled_min_q = value; return GSR_OK;
+	case GSR_TUNE_RK4_SMEM_STATE: g_rk4_smem_state = value; return GSR_OK;
+	case GSR_TUNE_FW_P4_MIN_SPC: g_fw_p4_min_spc = value; return GSR_OK;
 	case GSR_TUNE_TILED_CAP:
 		if (value < 0 || tiled_smem(value) > 200 * 1024) return GSR_EINVAL;
 		g_tiled_cap = value;
@@ -568,7 +702,7 @@ static TiledArgs make_targs(const EvalParams &P, const int32_t *cell_start, cons
 
 #define TL_LAUNCH(PP, KERNEL, ...)                                                              \
 	do {                                                                                    \
-		int rc__ = prep(KERNEL, a.cap);                                                 \
+		int rc__ = prep(KERNEL, a.cap, (PP) == FW_P);                                   \
 		if (rc__) return rc__;                                                          \
 		KERNEL<<<blocks, TL_TILE / (PP), tiled_smem(a.cap), st>>>(__VA_ARGS__);         \
 	} while (0)
@@ -581,15 +715,22 @@ int launch_forward_tiled3(const EvalParams &P, const int32_t *cell_start, const 
 {
 	TiledArgs a = make_targs(P, cell_start, packed, cull, x, Q, perm, scs, tile_row);
 	const int blocks = (int)tile_slots(P.g, Q);
-	if (accumulate) {
-		if (val && grad) TL_LAUNCH(FW_P, (forward_tiled3_kernel<FW_P, true, true, true>), a, val, grad);
-		else if (val) TL_LAUNCH(FW_P, (forward_tiled3_kernel<FW_P, true, false, true>), a, val, grad);
-		else TL_LAUNCH(FW_P, (forward_tiled3_kernel<FW_P, false, true, true>), a, val, grad);
-	} else {
-		if (val && grad) TL_LAUNCH(FW_P, (forward_tiled3_kernel<FW_P, true, true, false>), a, val, grad);
-		else if (val) TL_LAUNCH(FW_P, (forward_tiled3_kernel<FW_P, true, false, false>), a, val, grad);
-		else TL_LAUNCH(FW_P, (forward_tiled3_kernel<FW_P, false, true, false>), a, val, grad);
-	}
+	const bool dense = (double)Q >= (double)g_fw_p4_min_spc * (double)P.g.ncell;	// samples per cell: see launch_rk4_tiled3
+#define FW_DISPATCH(PP)                                                                                                 \
+	do {                                                                                                            \
+		if (accumulate) {                                                                                       \
+			if (val && grad) TL_LAUNCH(PP, (forward_tiled3_kernel<PP, true, true, true>), a, val, grad);    \
+			else if (val) TL_LAUNCH(PP, (forward_tiled3_kernel<PP, true, false, true>), a, val, grad);      \
+			else TL_LAUNCH(PP, (forward_tiled3_kernel<PP, false, true, true>), a, val, grad);               \
+		} else {                                                                                                \
+			if (val && grad) TL_LAUNCH(PP, (forward_tiled3_kernel<PP, true, true, false>), a, val, grad);   \
+			else if (val) TL_LAUNCH(PP, (forward_tiled3_kernel<PP, true, false, false>), a, val, grad);     \
+			else TL_LAUNCH(PP, (forward_tiled3_kernel<PP, false, true, false>), a, val, grad);              \
+		}                                                                                                       \
+	} while (0)
+	if (dense) FW_DISPATCH(4);
+	else FW_DISPATCH(2);
+#undef FW_DISPATCH
 	GSR_CHECK_LAUNCH();
 	return GSR_OK;
 }
@@ -600,6 +741,21 @@ int launch_rk4_tiled3(int mode, const EvalParams &P, const int32_t *cell_start, 
 {
 	TiledArgs a = make_targs(P, cell_start, packed, cull, x, Q, perm, scs, tile_row);
 	const int blocks = (int)tile_slots(P.g, Q);
+	// many samples per cell: warps of 128 points are still compact, and 4 points per thread halve the per-candidate overhead;
+	// fewer: 64-point warps cull better
+	if (mode != 0 && g_rk4_smem_state && (double)Q >= 1024. * (double)P.g.ncell) {
+		const size_t sm = tiled_smem(a.cap) + sizeof(float) * RKS_STATE * RKS_P * (TL_TILE / RKS_P);
+		cudaError_t e = (mode == 1) ? cudaFuncSetAttribute(rk4_tiled3s_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+					    : cudaFuncSetAttribute(rk4_tiled3s_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+		if (e == cudaSuccess)
+			e = (mode == 1) ? cudaFuncSetAttribute(rk4_tiled3s_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+					: cudaFuncSetAttribute(rk4_tiled3s_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		if (e != cudaSuccess) return (int)e;
+		if (mode == 1) rk4_tiled3s_kernel<1><<<blocks, TL_TILE / RKS_P, sm, st>>>(a, dt, goal_pos, deformation, goal_val, goal_grad, ref_vor, ref_hel);
+		else rk4_tiled3s_kernel<2><<<blocks, TL_TILE / RKS_P, sm, st>>>(a, dt, goal_pos, deformation, goal_val, goal_grad, ref_vor, ref_hel);
+		GSR_CHECK_LAUNCH();
+		return GSR_OK;
+	}
 	if (mode == 0) TL_LAUNCH(FW_P, (rk4_tiled3_kernel<0, FW_P>), a, dt, goal_pos, deformation, goal_val, goal_grad, ref_vor, ref_hel);
 	else if (mode == 1) TL_LAUNCH(RK_P, (rk4_tiled3_kernel<1, RK_P>), a, dt, goal_pos, deformation, goal_val, goal_grad, ref_vor, ref_hel);
 	else TL_LAUNCH(RK_P, (rk4_tiled3_kernel<2, RK_P>), a, dt, goal_pos, deformation, goal_val, goal_grad, ref_vor, ref_hel);

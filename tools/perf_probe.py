@@ -20,7 +20,8 @@ def timeit(fn, reps=10, warm=3):
 n = int(sys.argv[1]); N = n ** 3
 Q = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else N
 if len(sys.argv) > 3: HashEngine.set_tiled_min_q(int(sys.argv[3]))
-if len(sys.argv) > 4: _lib.check(_lib.lib().gsr_set_tuning(C.c_int(2), C.c_int(int(sys.argv[4]))), 'cap')
+if len(sys.argv) > 4 and int(sys.argv[4]) >= 0: _lib.check(_lib.lib().gsr_set_tuning(C.c_int(2), C.c_int(int(sys.argv[4]))), 'cap')
+if len(sys.argv) > 5: _lib.check(_lib.lib().gsr_set_tuning(C.c_int(4), C.c_int(int(sys.argv[5]))), 'fwp4')
 gsr3d.device = torch.device('cuda', 0)
 P, S, R, V, mgs, gen = synthetic_field(n)
 o = make_fast3d(P, S, R, V, 5e-3, mgs)
