@@ -315,22 +315,28 @@ __device__ __forceinline__ void warp_eval3(const TiledArgs &a, const TileSh &sh,
 #pragma unroll
 								for (int p = 0; p < P; p++) thr[p] = (rowok[p] && abs(zci - cz[p]) <= 1) ? q_thr : -1.f;
 							}
+							// test all pairs first, then ONE branch for the whole survivor: its accepted block runs the pairs'
+							// chains interleaved (a pair or a half that is not accepted contributes exact zeros)
+							f2 wx[H], wy[H], wz[H];
+							float g0[H], g1[H];
+							bool any = false;
 #pragma unroll
 							for (int h = 0; h < H; h++) {
 								const f2 dx = add2(X2[h], bc(-p0.x)), dy = add2(Y2[h], bc(-p0.y)), dz = add2(Z2[h], bc(-p0.z));
-								const f2 wx = fma2(bc(p1.z), dz, fma2(bc(p1.y), dy, mul2(bc(p1.x), dx)));
-								const f2 wy = fma2(bc(p2.y), dz, fma2(bc(p2.x), dy, mul2(bc(p1.y), dx)));
-								const f2 wz = fma2(bc(p2.z), dz, fma2(bc(p2.y), dy, mul2(bc(p1.z), dx)));
-								const f2 q2 = fma2(dz, wz, fma2(dy, wy, mul2(dx, wx)));
-								float q0, q1;
-								unpack2(q2, q0, q1);
-								const bool a0 = q0 <= thr[2 * h], a1 = q1 <= thr[2 * h + 1];
-								if (a0 || a1) {
-									// a half that is not accepted contributes exact zeros
-									float g0 = ex2_approx(q0 * kNegHalfLog2e), g1 = ex2_approx(q1 * kNegHalfLog2e);
-									g0 = a0 ? g0 : 0.f;
-									g1 = a1 ? g1 : 0.f;
-									f2 gm = add2(pack2(g0, g1), ntau2);
+								wx[h] = fma2(bc(p1.z), dz, fma2(bc(p1.y), dy, mul2(bc(p1.x), dx)));
+								wy[h] = fma2(bc(p2.y), dz, fma2(bc(p2.x), dy, mul2(bc(p1.y), dx)));
+								wz[h] = fma2(bc(p2.z), dz, fma2(bc(p2.y), dy, mul2(bc(p1.z), dx)));
+								const f2 q2 = fma2(dz, wz[h], fma2(dy, wy[h], mul2(dx, wx[h])));
+								unpack2(q2, g0[h], g1[h]);
+								any |= g0[h] <= thr[2 * h] || g1[h] <= thr[2 * h + 1];
+							}
+							if (any) {
+#pragma unroll
+								for (int h = 0; h < H; h++) {
+									const bool a0 = g0[h] <= thr[2 * h], a1 = g1[h] <= thr[2 * h + 1];
+									const float e0 = ex2_approx(g0[h] * kNegHalfLog2e), e1 = ex2_approx(g1[h] * kNegHalfLog2e);
+									const float ga = a0 ? e0 : 0.f, gb = a1 ? e1 : 0.f;
+									f2 gm = add2(pack2(ga, gb), ntau2);
 									float m0, m1;
 									unpack2(gm, m0, m1);
 									gm = pack2(a0 ? m0 : 0.f, a1 ? m1 : 0.f);
@@ -338,8 +344,8 @@ __device__ __forceinline__ void warp_eval3(const TiledArgs &a, const TileSh &sh,
 									U[h][1] = fma2(bc(p1.w), gm, U[h][1]);
 									U[h][2] = fma2(bc(p2.w), gm, U[h][2]);
 									if (NEED_GRAD) {
-										const f2 ng = pack2(-g0, -g1);
-										const f2 ax = mul2(ng, wx), ay = mul2(ng, wy), az = mul2(ng, wz);
+										const f2 ng = pack2(-ga, -gb);
+										const f2 ax = mul2(ng, wx[h]), ay = mul2(ng, wy[h]), az = mul2(ng, wz[h]);
 										GG[h][0] = fma2(bc(p0.w), ax, GG[h][0]); GG[h][1] = fma2(bc(p0.w), ay, GG[h][1]); GG[h][2] = fma2(bc(p0.w), az, GG[h][2]);
 										GG[h][3] = fma2(bc(p1.w), ax, GG[h][3]); GG[h][4] = fma2(bc(p1.w), ay, GG[h][4]); GG[h][5] = fma2(bc(p1.w), az, GG[h][5]);
 										GG[h][6] = fma2(bc(p2.w), ax, GG[h][6]); GG[h][7] = fma2(bc(p2.w), ay, GG[h][7]); GG[h][8] = fma2(bc(p2.w), az, GG[h][8]);
