@@ -96,7 +96,7 @@ def run_reference(args):
 	n = SIZES[args.size]
 	cores = os.cpu_count() or 1
 	cpu_sample(n, cores, lattice_points=2048)	# warm-up (builds the oracle, pages memory in)
-	lattice_points = 16384 if n <= 40 else 4096
+	lattice_points = 131072 if n <= 40 else 16384
 	for _ in range(max(args.warmup - 1, 0)):
 		cpu_sample(n, cores, lattice_points=lattice_points)
 	t_tot, c_tot = 0., 0
@@ -294,7 +294,7 @@ def run_ours(args):
 	}
 	if world == 1 and not args.no_cpu_baseline:
 		cores = os.cpu_count() or 1
-		lattice_points = 16384 if n <= 40 else 4096
+		lattice_points = 131072 if n <= 40 else 16384
 		cpu_sample(n, cores, lattice_points=2048)
 		c, tsec = cpu_sample(n, cores, lattice_points=lattice_points, reps=2)
 		out['cpu_baseline'] = {'value': c / tsec, 'unit': UNIT, 'cores': cores, 'kind': 'port',

@@ -134,10 +134,12 @@ class HashEngine:
 	# ---- samples ----------------------------------------------------------------------------------
 	# smallest Q for which the tiled shared-memory kernels are used (mirrors GSR_TUNE_TILED_MIN_Q)
 	TILED_MIN_Q = int(os.environ.get('GSR_TILED_MIN_Q', 1 << 17))
+	TILED_MIN_SPC = float(os.environ.get('GSR_TILED_MIN_SPC', 48))	# samples per hash cell
 
 	@classmethod
-	def set_tiled_min_q(cls, q):
+	def set_tiled_min_q(cls, q, min_spc=None):
 		cls.TILED_MIN_Q = int(q)
+		cls.TILED_MIN_SPC = (0. if int(q) <= 1 else 48.) if min_spc is None else float(min_spc)	# forcing the tiled path (tests) lifts the density rule
 		check(_lib.lib().gsr_set_tuning(C.c_int(1), C.c_int(int(q))), 'gsr_set_tuning')
 
 	BIN_CACHE_AGE = 16	# uses of a cached ordering before it is refreshed while grid_scale lives on the device
@@ -150,7 +152,9 @@ class HashEngine:
 		evaluates with orderings of a different grid).  Batches that feed the backward gather are always ordered afresh.
 		"""
 		Q = x.shape[0]
-		need_tiles = self.D == 3 and Q >= self.TILED_MIN_Q
+		# tiled kernels: large batches with enough samples per cell for compact warps (measured: below ~48 samples per cell the
+		# one-point-per-thread kernels win: profiles/README.md)
+		need_tiles = self.D == 3 and Q >= self.TILED_MIN_Q and Q >= self.TILED_MIN_SPC * self.ncell
 		key = None
 		if need_tiles and not need_cells:
 			key = (x.data_ptr(), x._version, Q, tuple(self.dims))
