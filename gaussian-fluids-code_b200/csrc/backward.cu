@@ -125,11 +125,38 @@ __global__ void __launch_bounds__(256) loss_final_kernel(const float *__restrict
 	}
 }
 
-template <int D, bool HAS_DIR, bool HAS_VOR>
-__global__ void adjoint_kernel(AdjIn in, int Q, const int32_t *__restrict__ perm, LossW w, float4 *__restrict__ rec)
+// DIR_MODE: 0 no direct set; 1 direct set without a gradient loss (A = 0: value / boundary losses only — the boundary pass of
+// every project iteration) -> one float4 {a, 0}; 2 full direct set
+template <int D, int DIR_MODE, bool HAS_VOR>
+__global__ void __launch_bounds__(ADJ_THREADS) adjoint_kernel(AdjIn in, int Q, const int32_t *__restrict__ perm, LossW w, float4 *__restrict__ rec, AdjIn lin,
+							      float *__restrict__ partials)
 {
-	constexpr int STRIDE = 1 + (HAS_VOR ? Rec<D>::VOR : 0) + (HAS_DIR ? Rec<D>::DIR : 0);
+	constexpr bool HAS_DIR = DIR_MODE != 0;
+	constexpr int STRIDE = 1 + (HAS_VOR ? Rec<D>::VOR : 0) + (DIR_MODE == 2 ? Rec<D>::DIR : (DIR_MODE == 1 ? 1 : 0));
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (partials) {	// the sample losses of this block's samples (what loss_partials_kernel computes), fused into this pass
+		__shared__ float sm[ADJ_THREADS / 32][6];
+		float L[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+		if (t < Q) sample_losses<D>(lin, (size_t)(perm ? perm[t] : t), L);
+#pragma unroll
+		for (int k = 0; k < 6; k++) {
+#pragma unroll
+			for (int o = 16; o; o >>= 1) L[k] += __shfl_xor_sync(0xffffffffu, L[k], o);
+		}
+		if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+			for (int k = 0; k < 6; k++) sm[threadIdx.x >> 5][k] = L[k];
+		}
+		__syncthreads();
+		if (threadIdx.x < 8) {
+			float s = 0.f;
+			if (threadIdx.x < 6) {
+#pragma unroll
+				for (int wv = 0; wv < ADJ_THREADS / 32; wv++) s += sm[wv][threadIdx.x];
+			}
+			partials[(size_t)blockIdx.x * 8 + threadIdx.x] = s;
+		}
+	}
 	if (t >= Q) return;
 	size_t j = perm ? perm[t] : t;
 	float4 *r = rec + (size_t)STRIDE * t;
@@ -172,7 +199,9 @@ __global__ void adjoint_kernel(AdjIn in, int Q, const int32_t *__restrict__ perm
 			a[k] = w.val * sgnf(u[k] - (in.ref_val ? in.ref_val[D * j + k] : 0.f)) + sb * (in.normals ? in.normals[D * j + k] : 0.f);
 #pragma unroll
 		for (int k = 0; k < D * D; k++) A[k] = w.grad * sgnf(G[k] - (in.ref_grad ? in.ref_grad[D * D * j + k] : 0.f));
-		if (D == 3) {
+		if (DIR_MODE == 1) {
+			r[o] = make_float4(a[0], a[1], D == 3 ? a[D - 1] : 0.f, 0.f);
+		} else if (D == 3) {
 			r[o] = make_float4(a[0], a[1], a[2], A[0]);
 			r[o + 1] = make_float4(A[1], A[2], A[3], A[4]);
 			r[o + 2] = make_float4(A[5], A[6], A[7], A[8]);
@@ -231,13 +260,28 @@ __device__ __forceinline__ void acc12_reduce(Acc12 &a)
 }
 
 // LPG lanes cooperate on one Gaussian (1: throughput shape for large N; 8 / 32: latency shape for small N or Q >> N)
-template <bool HAS_DIR, bool HAS_VOR, bool HAS_DIV, int LPG>
+// a pair of the direct set when A = 0 (t = 0, c = a.v): ~40 flop instead of 115
+__device__ __forceinline__ void pair_accum3_value(Acc12 &acc, const float a[3], const float v[3], const float w[3], const float dd[6], float g, float gm)
+{
+	const float c = a[0] * v[0] + a[1] * v[1] + a[2] * v[2];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		acc.dv[k] += a[k] * gm;
+		acc.dm[k] += g * (c * w[k]);
+	}
+	const float hc = -.5f * g * c;
+#pragma unroll
+	for (int k = 0; k < 6; k++) acc.G[k] += hc * dd[k];
+}
+
+template <int DIR_MODE, bool HAS_VOR, bool HAS_DIV, int LPG>
 __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_id,
 							      const float4 *__restrict__ packed, int N, const int32_t *__restrict__ scs /* sample_cell_start */,
 							      const float4 *__restrict__ rec, const int32_t *__restrict__ stop_gradient, float tscale,
 							      float *__restrict__ acc_out)
 {
-	constexpr int STRIDE = 1 + (HAS_VOR ? 2 : 0) + (HAS_DIR ? 3 : 0);
+	constexpr bool HAS_DIR = DIR_MODE != 0;
+	constexpr int STRIDE = 1 + (HAS_VOR ? 2 : 0) + (DIR_MODE == 2 ? 3 : (DIR_MODE == 1 ? 1 : 0));
 	const int gt = blockIdx.x * GA_THREADS + threadIdx.x;
 	const int tq = gt / LPG, lane = gt % LPG;
 	if (LPG == 1 && tq >= N) return;
@@ -258,51 +302,88 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 		const float gs = grid_gs(g);
 		const int cx = cell_coord(p0.x, g.lo[0], gs), cy = cell_coord(p0.y, g.lo[1], gs), cz = cell_coord(p0.z, g.lo[2], gs);
 		const float tau = g.tau, q_thr = P.q_thr;
-		for (int pi = cx; pi <= cx + 2; pi++) {
-			for (int pj = cy; pj <= cy + 2; pj++) {
-				const int base = (pi * g.pdims[1] + pj) * g.pdims[2] + cz;
-				const int s = __ldg(scs + base), e = __ldg(scs + base + 3);
-				for (int k = s + lane; k < e; k += LPG) {
-					const float4 r0 = __ldg(rec + (size_t)STRIDE * k);
-					const float d[3] = {r0.x - p0.x, r0.y - p0.y, r0.z - p0.z};
-					const float w[3] = {Am[0] * d[0] + Am[1] * d[1] + Am[2] * d[2], Am[1] * d[0] + Am[3] * d[1] + Am[4] * d[2], Am[2] * d[0] + Am[4] * d[1] + Am[5] * d[2]};
-					const float q = d[0] * w[0] + d[1] * w[1] + d[2] * w[2];
-					if (q <= q_thr) {
-						const float gg = ex2_approx(q * kNegHalfLog2e), gm = gg - tau;
-						const float dd[6] = {d[0] * d[0], d[0] * d[1], d[0] * d[2], d[1] * d[1], d[1] * d[2], d[2] * d[2]};
-						int o = 1;
-						if (HAS_VOR) {
-							const float4 r1 = __ldg(rec + (size_t)STRIDE * k + o), r2 = __ldg(rec + (size_t)STRIDE * k + o + 1);
-							const float a[3] = {r1.x, r1.y, r1.z}, m[3] = {r1.w, r2.x, r2.y};
-							const float tt[3] = {v[1] * m[2] - v[2] * m[1], v[2] * m[0] - v[0] * m[2], v[0] * m[1] - v[1] * m[0]};	// v x m
-							const float Aw[3] = {m[1] * w[2] - m[2] * w[1], m[2] * w[0] - m[0] * w[2], m[0] * w[1] - m[1] * w[0]};	// m x w
-							pair_accum3(aV, a, tt, Aw, tscale, v, d, w, Am, dd, gg, gm);
-							o += 2;
-						}
-						if (HAS_DIV) {
-							const float gk = gg * r0.w, vw = v[0] * w[0] + v[1] * w[1] + v[2] * w[2];
-							const float hk = -.5f * gk;
+		// one accepted-or-not visit of sorted sample k
+		auto visit = [&](int k) {
+			const float4 r0 = __ldg(rec + (size_t)STRIDE * k);
+			const float d[3] = {r0.x - p0.x, r0.y - p0.y, r0.z - p0.z};
+			const float w[3] = {Am[0] * d[0] + Am[1] * d[1] + Am[2] * d[2], Am[1] * d[0] + Am[3] * d[1] + Am[4] * d[2], Am[2] * d[0] + Am[4] * d[1] + Am[5] * d[2]};
+			const float q = d[0] * w[0] + d[1] * w[1] + d[2] * w[2];
+			if (q <= q_thr) {
+				const float gg = ex2_approx(q * kNegHalfLog2e), gm = gg - tau;
+				const float dd[6] = {d[0] * d[0], d[0] * d[1], d[0] * d[2], d[1] * d[1], d[1] * d[2], d[2] * d[2]};
+				int o = 1;
+				if (HAS_VOR) {
+					const float4 r1 = __ldg(rec + (size_t)STRIDE * k + o), r2 = __ldg(rec + (size_t)STRIDE * k + o + 1);
+					const float a[3] = {r1.x, r1.y, r1.z}, m[3] = {r1.w, r2.x, r2.y};
+					const float tt[3] = {v[1] * m[2] - v[2] * m[1], v[2] * m[0] - v[0] * m[2], v[0] * m[1] - v[1] * m[0]};	// v x m
+					const float Aw[3] = {m[1] * w[2] - m[2] * w[1], m[2] * w[0] - m[0] * w[2], m[0] * w[1] - m[1] * w[0]};	// m x w
+					pair_accum3(aV, a, tt, Aw, tscale, v, d, w, Am, dd, gg, gm);
+					o += 2;
+				}
+				if (HAS_DIV) {
+					const float gk = gg * r0.w, vw = v[0] * w[0] + v[1] * w[1] + v[2] * w[2];
+					const float hk = -.5f * gk;
 #pragma unroll
-							for (int q = 0; q < 3; q++) {
-								aX.dv[q] -= gk * w[q];
-								aX.dm[q] += gk * (Av[q] - vw * w[q]);
-							}
-							aX.G[0] += hk * (2.f * v[0] * d[0] - vw * dd[0]);
-							aX.G[1] += hk * (v[0] * d[1] + d[0] * v[1] - vw * dd[1]);
-							aX.G[2] += hk * (v[0] * d[2] + d[0] * v[2] - vw * dd[2]);
-							aX.G[3] += hk * (2.f * v[1] * d[1] - vw * dd[3]);
-							aX.G[4] += hk * (v[1] * d[2] + d[1] * v[2] - vw * dd[4]);
-							aX.G[5] += hk * (2.f * v[2] * d[2] - vw * dd[5]);
-						}
-						if (HAS_DIR) {
-							const float4 r1 = __ldg(rec + (size_t)STRIDE * k + o), r2 = __ldg(rec + (size_t)STRIDE * k + o + 1), r3 = __ldg(rec + (size_t)STRIDE * k + o + 2);
-							const float a[3] = {r1.x, r1.y, r1.z};
-							const float A[9] = {r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-							const float tt[3] = {v[0] * A[0] + v[1] * A[3] + v[2] * A[6], v[0] * A[1] + v[1] * A[4] + v[2] * A[7], v[0] * A[2] + v[1] * A[5] + v[2] * A[8]};
-							const float Aw[3] = {A[0] * w[0] + A[1] * w[1] + A[2] * w[2], A[3] * w[0] + A[4] * w[1] + A[5] * w[2], A[6] * w[0] + A[7] * w[1] + A[8] * w[2]};
-							pair_accum3(aD, a, tt, Aw, tscale, v, d, w, Am, dd, gg, gm);
-						}
+					for (int q = 0; q < 3; q++) {
+						aX.dv[q] -= gk * w[q];
+						aX.dm[q] += gk * (Av[q] - vw * w[q]);
 					}
+					aX.G[0] += hk * (2.f * v[0] * d[0] - vw * dd[0]);
+					aX.G[1] += hk * (v[0] * d[1] + d[0] * v[1] - vw * dd[1]);
+					aX.G[2] += hk * (v[0] * d[2] + d[0] * v[2] - vw * dd[2]);
+					aX.G[3] += hk * (2.f * v[1] * d[1] - vw * dd[3]);
+					aX.G[4] += hk * (v[1] * d[2] + d[1] * v[2] - vw * dd[4]);
+					aX.G[5] += hk * (2.f * v[2] * d[2] - vw * dd[5]);
+				}
+				if (DIR_MODE == 1) {
+					const float4 r1 = __ldg(rec + (size_t)STRIDE * k + o);
+					const float a[3] = {r1.x, r1.y, r1.z};
+					pair_accum3_value(aD, a, v, w, dd, gg, gm);
+				}
+				if (DIR_MODE == 2) {
+					const float4 r1 = __ldg(rec + (size_t)STRIDE * k + o), r2 = __ldg(rec + (size_t)STRIDE * k + o + 1), r3 = __ldg(rec + (size_t)STRIDE * k + o + 2);
+					const float a[3] = {r1.x, r1.y, r1.z};
+					const float A[9] = {r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+					const float tt[3] = {v[0] * A[0] + v[1] * A[3] + v[2] * A[6], v[0] * A[1] + v[1] * A[4] + v[2] * A[7], v[0] * A[2] + v[1] * A[5] + v[2] * A[8]};
+					const float Aw[3] = {A[0] * w[0] + A[1] * w[1] + A[2] * w[2], A[3] * w[0] + A[4] * w[1] + A[5] * w[2], A[6] * w[0] + A[7] * w[1] + A[8] * w[2]};
+					pair_accum3(aD, a, tt, Aw, tscale, v, d, w, Am, dd, gg, gm);
+				}
+			}
+		};
+		if (LPG == 32) {
+			// a whole warp on one Gaussian (small N): the 9 sample runs are looked up by 9 lanes at once, concatenated by a warp
+			// scan, and the lanes stride through the flat list (one round trip instead of nine dependent ones, every lane busy)
+			int s = 0, n = 0;
+			if (lane < 9) {
+				const int base = ((cx + lane / 3) * g.pdims[1] + (cy + lane % 3)) * g.pdims[2] + cz;
+				s = __ldg(scs + base);
+				n = __ldg(scs + base + 3) - s;
+			}
+			int incl = n;
+#pragma unroll
+			for (int o = 1; o < 16; o <<= 1) {
+				const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o) incl += t2;
+			}
+			const int total = __shfl_sync(0xffffffffu, incl, 8);
+			int pre[9], off[9];
+#pragma unroll
+			for (int r = 0; r < 9; r++) {
+				pre[r] = __shfl_sync(0xffffffffu, incl - n, r);
+				off[r] = __shfl_sync(0xffffffffu, s, r) - pre[r];
+			}
+			for (int f = lane; f < total; f += 32) {
+				int dlt = off[0];
+#pragma unroll
+				for (int r = 1; r < 9; r++) dlt = (f >= pre[r]) ? off[r] : dlt;
+				visit(f + dlt);
+			}
+		} else {
+			for (int pi = cx; pi <= cx + 2; pi++) {
+				for (int pj = cy; pj <= cy + 2; pj++) {
+					const int base = (pi * g.pdims[1] + pj) * g.pdims[2] + cz;
+					const int s = __ldg(scs + base), e = __ldg(scs + base + 3);
+					for (int k = s + lane; k < e; k += LPG) visit(k);
 				}
 			}
 		}
@@ -356,12 +437,13 @@ __device__ __forceinline__ void acc7_reduce(Acc7 &a)
 	a.G[0] = lane_sum<LPG>(a.G[0]); a.G[1] = lane_sum<LPG>(a.G[1]); a.G[2] = lane_sum<LPG>(a.G[2]);
 }
 
-template <bool HAS_DIR, bool HAS_VOR, bool HAS_DIV, int LPG>
+template <int DIR_MODE, bool HAS_VOR, bool HAS_DIV, int LPG>
 __global__ void __launch_bounds__(GA_THREADS) gather2d_kernel(EvalParams P, const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_id,
 							      const float4 *__restrict__ packed, int N, const int32_t *__restrict__ scs,
 							      const float4 *__restrict__ rec, const int32_t *__restrict__ stop_gradient, float *__restrict__ acc_out)
 {
-	constexpr int STRIDE = 1 + (HAS_VOR ? 1 : 0) + (HAS_DIR ? 2 : 0);
+	constexpr bool HAS_DIR = DIR_MODE != 0;
+	constexpr int STRIDE = 1 + (HAS_VOR ? 1 : 0) + (DIR_MODE == 2 ? 2 : (DIR_MODE == 1 ? 1 : 0));
 	const int gt = blockIdx.x * GA_THREADS + threadIdx.x;
 	const int tq = gt / LPG, lane = gt % LPG;
 	if (LPG == 1 && tq >= N) return;
@@ -406,7 +488,12 @@ __global__ void __launch_bounds__(GA_THREADS) gather2d_kernel(EvalParams P, cons
 						const float Aw[2] = {kap * w[0], kap * w[1]};
 						pair_accum2(aX, a, tt, Aw, v, d, w, Am, gg, gm);
 					}
-					if (HAS_DIR) {
+					if (DIR_MODE == 1) {
+						const float4 r1 = __ldg(rec + (size_t)STRIDE * k + o);
+						const float a[2] = {r1.x, r1.y}, zero2[2] = {0.f, 0.f};
+						pair_accum2(aD, a, zero2, zero2, v, d, w, Am, gg, gm);	// t = 0, A w = 0: the compiler folds the dead terms
+					}
+					if (DIR_MODE == 2) {
 						const float4 r1 = __ldg(rec + (size_t)STRIDE * k + o), r2 = __ldg(rec + (size_t)STRIDE * k + o + 1);
 						const float a[2] = {r1.x, r1.y};
 						const float A[4] = {r1.z, r1.w, r2.x, r2.y};
@@ -489,13 +576,16 @@ extern "C" size_t gsr_backward_ws_bytes(const gsr_grid_desc *d, int64_t, int64_t
 }
 
 template <int D>
-static int launch_adjoint(bool dir, bool vor, const AdjIn &in, int Q, const int32_t *perm, const LossW &w, float4 *rec, cudaStream_t st)
+static int launch_adjoint(int dir, bool vor, const AdjIn &in, int Q, const int32_t *perm, const LossW &w, float4 *rec, const AdjIn &lin, float *partials,
+			  cudaStream_t st)
 {
-	int blocks = (Q + 127) / 128;
-	if (dir && vor) adjoint_kernel<D, true, true><<<blocks, 128, 0, st>>>(in, Q, perm, w, rec);
-	else if (dir) adjoint_kernel<D, true, false><<<blocks, 128, 0, st>>>(in, Q, perm, w, rec);
-	else if (vor) adjoint_kernel<D, false, true><<<blocks, 128, 0, st>>>(in, Q, perm, w, rec);
-	else adjoint_kernel<D, false, false><<<blocks, 128, 0, st>>>(in, Q, perm, w, rec);
+	int blocks = (Q + ADJ_THREADS - 1) / ADJ_THREADS;
+	if (dir == 2 && vor) adjoint_kernel<D, 2, true><<<blocks, ADJ_THREADS, 0, st>>>(in, Q, perm, w, rec, lin, partials);
+	else if (dir == 2) adjoint_kernel<D, 2, false><<<blocks, ADJ_THREADS, 0, st>>>(in, Q, perm, w, rec, lin, partials);
+	else if (dir == 1 && vor) adjoint_kernel<D, 1, true><<<blocks, ADJ_THREADS, 0, st>>>(in, Q, perm, w, rec, lin, partials);
+	else if (dir == 1) adjoint_kernel<D, 1, false><<<blocks, ADJ_THREADS, 0, st>>>(in, Q, perm, w, rec, lin, partials);
+	else if (vor) adjoint_kernel<D, 0, true><<<blocks, ADJ_THREADS, 0, st>>>(in, Q, perm, w, rec, lin, partials);
+	else adjoint_kernel<D, 0, false><<<blocks, ADJ_THREADS, 0, st>>>(in, Q, perm, w, rec, lin, partials);
 	GSR_CHECK_LAUNCH();
 	return 0;
 }
@@ -503,15 +593,19 @@ static int launch_adjoint(bool dir, bool vor, const AdjIn &in, int Q, const int3
 #define GATHER_CASE(KERNEL, A, B, C_, LN, ...) KERNEL<A, B, C_, LN><<<blocks, GA_THREADS, 0, st>>>(__VA_ARGS__)
 #define GATHER_DISPATCH_L(KERNEL, LN, ...)                                          \
 	do {                                                                        \
-		int sel = (dir ? 4 : 0) | (vor ? 2 : 0) | (dv ? 1 : 0);            \
+		int sel = dirmode * 4 + (vor ? 2 : 0) + (dv ? 1 : 0);              \
 		switch (sel) {                                                      \
-		case 1: GATHER_CASE(KERNEL, false, false, true, LN, __VA_ARGS__); break;   \
-		case 2: GATHER_CASE(KERNEL, false, true, false, LN, __VA_ARGS__); break;   \
-		case 3: GATHER_CASE(KERNEL, false, true, true, LN, __VA_ARGS__); break;    \
-		case 4: GATHER_CASE(KERNEL, true, false, false, LN, __VA_ARGS__); break;   \
-		case 5: GATHER_CASE(KERNEL, true, false, true, LN, __VA_ARGS__); break;    \
-		case 6: GATHER_CASE(KERNEL, true, true, false, LN, __VA_ARGS__); break;    \
-		case 7: GATHER_CASE(KERNEL, true, true, true, LN, __VA_ARGS__); break;     \
+		case 1: GATHER_CASE(KERNEL, 0, false, true, LN, __VA_ARGS__); break;       \
+		case 2: GATHER_CASE(KERNEL, 0, true, false, LN, __VA_ARGS__); break;       \
+		case 3: GATHER_CASE(KERNEL, 0, true, true, LN, __VA_ARGS__); break;        \
+		case 4: GATHER_CASE(KERNEL, 1, false, false, LN, __VA_ARGS__); break;      \
+		case 5: GATHER_CASE(KERNEL, 1, false, true, LN, __VA_ARGS__); break;       \
+		case 6: GATHER_CASE(KERNEL, 1, true, false, LN, __VA_ARGS__); break;       \
+		case 7: GATHER_CASE(KERNEL, 1, true, true, LN, __VA_ARGS__); break;        \
+		case 8: GATHER_CASE(KERNEL, 2, false, false, LN, __VA_ARGS__); break;      \
+		case 9: GATHER_CASE(KERNEL, 2, false, true, LN, __VA_ARGS__); break;       \
+		case 10: GATHER_CASE(KERNEL, 2, true, false, LN, __VA_ARGS__); break;      \
+		case 11: GATHER_CASE(KERNEL, 2, true, true, LN, __VA_ARGS__); break;       \
 		default: break;                                                     \
 		}                                                                   \
 	} while (0)
@@ -575,21 +669,18 @@ extern "C" int gsr_backward_gather(const gsr_grid_desc *d, const int32_t *cell_s
 		    cfg->w_boundary != 0.f ? cfg->normal_ref : nullptr, cfg->w_grad != 0.f ? cfg->ref_grad : nullptr,
 		    cfg->w_vor != 0.f ? cfg->ref_vor : nullptr, cfg->w_hel != 0.f ? cfg->ref_hel : nullptr};
 	float4 *rec = (float4 *)ws;
-	if (cfg->loss_partials && Q > 0) {
-		AdjIn lin = {x, val, grad, cfg->ref_val, cfg->normals, cfg->normal_ref, cfg->ref_grad, cfg->ref_vor, cfg->ref_hel};
-		int lb = (int)((Q + ADJ_THREADS - 1) / ADJ_THREADS);
-		g_launches += 1;
-		if (D == 3) loss_partials_kernel<3><<<lb, ADJ_THREADS, 0, st>>>(lin, (int)Q, cfg->loss_partials);
-		else loss_partials_kernel<2><<<lb, ADJ_THREADS, 0, st>>>(lin, (int)Q, cfg->loss_partials);
-	}
+	const AdjIn lin = {x, val, grad, cfg->ref_val, cfg->normals, cfg->normal_ref, cfg->ref_grad, cfg->ref_vor, cfg->ref_hel};
+	if (cfg->loss_partials && Q == 0) cudaMemsetAsync(cfg->loss_partials, 0, 8 * sizeof(float), st);
 	EvalParams P = make_params(g);
 	// lanes per Gaussian: by the amount of parallelism N offers, and more when there are many samples per Gaussian
 	int lpg = pick_lanes(N);
 	if (lpg == 1 && Q >= 8 * N) lpg = 8;
 	int blocks = (int)((N * lpg + GA_THREADS - 1) / GA_THREADS);
 	g_launches += Q > 0 ? 2 : 1;
+	const int dirmode = !dir ? 0 : (cfg->w_grad != 0.f ? 2 : 1);	// no gradient loss: A = 0 in the direct set
 	if (Q > 0) {
-		int rc = (D == 3) ? launch_adjoint<3>(dir, vor, in, (int)Q, perm, w, rec, st) : launch_adjoint<2>(dir, vor, in, (int)Q, perm, w, rec, st);
+		int rc = (D == 3) ? launch_adjoint<3>(dirmode, vor, in, (int)Q, perm, w, rec, lin, cfg->loss_partials, st)
+				  : launch_adjoint<2>(dirmode, vor, in, (int)Q, perm, w, rec, lin, cfg->loss_partials, st);
 		if (rc) return rc;
 	}
 	if (D == 3)

@@ -57,7 +57,58 @@ __device__ __forceinline__ void eval_point3(const EvalParams &P, const int32_t *
 	const int cx = cell_coord(x, g.lo[0], gs), cy = cell_coord(y, g.lo[1], gs), cz = cell_coord(z, g.lo[2], gs);
 	const int zlo = max(cz - 1, 0), zhi = min(cz + 1, g.dims[2] - 1);
 	const float tau = g.tau, q_thr = P.q_thr;
-	if (zlo <= zhi) {
+	if (LANES == 32) {
+		// Latency shape for a whole warp on ONE point (the reference's own sizes: a few thousand points, ~200 candidates each).
+		// The 9 runs are looked up by 9 lanes at once (one round trip instead of nine dependent ones), concatenated by a
+		// warp scan, and the lanes then stride through the FLAT candidate list — every lane busy, all record loads independent.
+		int s = 0, n = 0;
+		if (lane < 9 && zlo <= zhi) {
+			const int gi = cx - 1 + lane / 3, gj = cy - 1 + lane % 3;
+			if (gi >= 0 && gi < g.dims[0] && gj >= 0 && gj < g.dims[1]) {
+				const int base = (gi * g.dims[1] + gj) * g.dims[2];
+				s = __ldg(cell_start + base + zlo);
+				n = __ldg(cell_start + base + zhi + 1) - s;
+			}
+		}
+		int incl = n;
+#pragma unroll
+		for (int o = 1; o < 16; o <<= 1) {
+			const int t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		const int total = __shfl_sync(0xffffffffu, incl, 8);
+		int pre[9], off[9];	// first flat index of run r, and (sorted index - flat index) inside it
+#pragma unroll
+		for (int r = 0; r < 9; r++) {
+			pre[r] = __shfl_sync(0xffffffffu, incl - n, r);
+			off[r] = __shfl_sync(0xffffffffu, s, r) - pre[r];
+		}
+		for (int f = lane; f < total; f += 32) {
+			int d = off[0];
+#pragma unroll
+			for (int r = 1; r < 9; r++) d = (f >= pre[r]) ? off[r] : d;
+			const int t = f + d;
+			const float4 p0 = __ldg(packed + 3 * t), p1 = __ldg(packed + 3 * t + 1), p2 = __ldg(packed + 3 * t + 2);
+			const float dx = x - p0.x, dy = y - p0.y, dz = z - p0.z;
+			const float wx = p1.x * dx + p1.y * dy + p1.z * dz;
+			const float wy = p1.y * dx + p2.x * dy + p2.y * dz;
+			const float wz = p1.z * dx + p2.y * dy + p2.z * dz;
+			const float q = dx * wx + dy * wy + dz * wz;
+			if (q <= q_thr) {
+				const float gs_ = ex2_approx(q * kNegHalfLog2e);
+				const float gm = gs_ - tau;
+				u[0] = fmaf(p0.w, gm, u[0]);
+				u[1] = fmaf(p1.w, gm, u[1]);
+				u[2] = fmaf(p2.w, gm, u[2]);
+				if (NEED_GRAD) {
+					const float ax = -gs_ * wx, ay = -gs_ * wy, az = -gs_ * wz;
+					G[0] = fmaf(p0.w, ax, G[0]); G[1] = fmaf(p0.w, ay, G[1]); G[2] = fmaf(p0.w, az, G[2]);
+					G[3] = fmaf(p1.w, ax, G[3]); G[4] = fmaf(p1.w, ay, G[4]); G[5] = fmaf(p1.w, az, G[5]);
+					G[6] = fmaf(p2.w, ax, G[6]); G[7] = fmaf(p2.w, ay, G[7]); G[8] = fmaf(p2.w, az, G[8]);
+				}
+			}
+		}
+	} else if (zlo <= zhi) {
 		for (int gi = max(cx - 1, 0); gi <= min(cx + 1, g.dims[0] - 1); gi++) {
 			for (int gj = max(cy - 1, 0); gj <= min(cy + 1, g.dims[1] - 1); gj++) {
 				const int base = (gi * g.dims[1] + gj) * g.dims[2];
