@@ -21,6 +21,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture: (size, test_res, world) -> bytes
+NCU_TRAFFIC = {('S1', 128, 1): 33694720 + 1133056}
+
 METRIC = 'gaussian_sample_pair_evals_per_s'
 UNIT = 'pair-evals/s'
 
@@ -252,7 +255,7 @@ def run_ours(args):
 		finish()
 		return
 
-	# ---- roofline of the dominant kernel: the RK4 pull-back (rk4_tiled3_kernel<2, 2>) on the test lattice --------------------
+	# ---- roofline of the dominant kernel: the RK4 pull-back (rk4_tiled3s_kernel<2>) on the test lattice --------------------
 	fma, mufu = C.c_double(0.), C.c_double(0.)
 	lib.gsr_peak_fma(C.c_int(20000), C.byref(fma), _lib.stream())
 	lib.gsr_peak_mufu(C.c_int(20000), C.byref(mufu), _lib.stream())
@@ -264,8 +267,9 @@ def run_ours(args):
 	k_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
 	flop_per_launch = 5 * (24 * C_lat + 28 * P_lat)
 	achieved = flop_per_launch / (k_ms * 1e-3) / 1e12 if kernel_ms else None
-	roofline = {'bound': 'fp32', 'kernel': 'rk4_tiled3_kernel<2, 2> (RK4 pull-back of the previous field on the test lattice, 5 field evaluations per point)',
-				'achieved': achieved, 'peak': fma.value, 'unit': 'TFLOP/s', 'frac': (achieved / fma.value) if achieved else None, 'traffic': None,
+	roofline = {'bound': 'fp32', 'kernel': 'rk4_tiled3s_kernel<2> (RK4 pull-back of the previous field on the test lattice, 5 field evaluations per point)',
+				'achieved': achieved, 'peak': fma.value, 'unit': 'TFLOP/s', 'frac': (achieved / fma.value) if achieved else None,
+				'traffic': NCU_TRAFFIC.get((args.size, args.test_res, world)), 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (profiles/ncu_full_rk4_tiled3s_r01.csv); null for workloads that were not captured',
 				'peak_source': 'FP32 FFMA peak measured live by gsr_peak_fma on this GPU (MEASURED_PEAKS.json holds only HBM and bf16 peaks); nominal 74.4 at 1965 MHz',
 				'mufu_peak_Tops': mufu.value, 'mufu_achieved_Tops': (5 * P_lat / (k_ms * 1e-3) / 1e12) if kernel_ms else None,
 				'pair_evals_per_s': (5 * C_lat / (k_ms * 1e-3)) if kernel_ms else None,

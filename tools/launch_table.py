@@ -4,7 +4,13 @@ rows = []
 with open(sys.argv[1]) as f:
 	lines = [l for l in f if not l.startswith('==')]
 for row in csv.DictReader(lines):
-	rows.append((row['Kernel Name'], float(row['Metric Value'].replace(',', '')), row['Grid Size'], row['Block Size']))
+	try:
+		ns = float(row['Metric Value'].replace(',', ''))
+	except ValueError:
+		ns = float('nan')
+	if ns != ns:
+		continue	# a launch ncu could not time
+	rows.append((row['Kernel Name'], ns, row['Grid Size'], row['Block Size']))
 agg = {}
 for nm, ns, grid, block in rows:
 	key = re.sub(r'\(.*', '', nm).replace('void ', '')
