@@ -1,0 +1,105 @@
+"""
+GPU tests of the pieces added around the per-iteration step: the Philox sample kernels
+(3D/advance.py:339-340, 3D/init_cond.py:227-249) and gsr_step_rebuild (step() -> zero_grad() -> reinitialize_grid()).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import NAMES, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_field(n=8):
+	from gaussian_fluids_code_b200 import gsr3d
+	from gaussian_fluids_code_b200.synth import make_fast3d, synthetic_field
+	gsr3d.device = torch.device('cuda', 0)
+	P, S, R, V, mgs, gen = synthetic_field(n)
+	return make_fast3d(P, S, R, V, 5e-3, mgs), gen
+
+
+def test_sample_box_uniform_and_counter_based():
+	o, _ = engine_field()
+	e = o._engine
+	box = (-.5, 1.5, 0., 2., 1., 4.)
+	it = torch.zeros(1, device='cuda')
+	a = e.sample_box(box, torch.empty((200000, 3), device='cuda'), 42, 0, it).clone()
+	b = e.sample_box(box, torch.empty((200000, 3), device='cuda'), 42, 0, it).clone()
+	assert torch.equal(a, b)					# counter-based: same (seed, stream, iteration) -> same samples
+	it.fill_(1.)
+	c = e.sample_box(box, torch.empty((200000, 3), device='cuda'), 42, 0, it).clone()
+	d = e.sample_box(box, torch.empty((200000, 3), device='cuda'), 42, 1, it).clone()
+	assert not torch.equal(a, c) and not torch.equal(c, d)	# the iteration (read from device memory) and the stream id both advance it
+	lo, hi = torch.tensor(box[0::2], device='cuda'), torch.tensor(box[1::2], device='cuda')
+	assert (a >= lo).all() and (a < hi).all()
+	u = ((a - lo) / (hi - lo)).cpu().numpy()
+	assert np.abs(u.mean(0) - .5).max() < 5e-3 and np.abs(u.var(0) - 1. / 12.).max() < 2e-3
+	assert np.abs(np.corrcoef(u.T) - np.eye(3)).max() < 1e-2
+	# replaying a captured graph draws fresh samples: the iteration counter lives on the device
+	out = torch.empty((1000, 3), device='cuda')
+	g = torch.cuda.CUDAGraph()
+	s = torch.cuda.Stream()
+	s.wait_stream(torch.cuda.current_stream())
+	with torch.cuda.stream(s):
+		e.sample_box(box, out, 7, 0, it)
+	torch.cuda.current_stream().wait_stream(s)
+	with torch.cuda.graph(g):
+		e.sample_box(box, out, 7, 0, it)
+	it.fill_(5.); g.replay(); r5 = out.clone()
+	it.fill_(6.); g.replay(); r6 = out.clone()
+	assert not torch.equal(r5, r6)
+
+
+def test_sample_box_surface_matches_reference_semantics():
+	"""3D/init_cond.py:227-249: area-weighted faces in the order x_min, x_max, y_min, y_max, z_min, z_max; inward normals"""
+	o, _ = engine_field()
+	e = o._engine
+	box = (0., 1., 0., 2., 0., 3.)	# face areas: yz 6, zx 3, xy 2 (each twice)
+	n = 400000
+	data, normal = torch.empty((n, 3), device='cuda'), torch.empty((n, 3), device='cuda')
+	e.sample_box_surface(box, data, normal, 1, 3, None)
+	d, nm = data.cpu().numpy(), normal.cpu().numpy()
+	assert np.allclose(np.abs(nm).sum(1), 1.) and set(np.unique(nm)) <= {-1., 0., 1.}
+	axis = np.abs(nm).argmax(1)
+	sign = nm[np.arange(n), axis]
+	lo, hi = np.array(box[0::2]), np.array(box[1::2])
+	on_face = d[np.arange(n), axis]
+	assert np.all(np.where(sign > 0, on_face == lo[axis], on_face == hi[axis]))	# inward normal: +1 on the min face, -1 on the max face
+	assert (d >= lo - 1e-6).all() and (d <= hi + 1e-6).all()
+	freq = np.array([(axis == k).mean() for k in range(3)])
+	assert np.abs(freq - np.array([6., 3., 2.]) / 11.).max() < 5e-3
+	for k in range(3):		# the two faces of an axis are equally likely, and points are uniform on a face
+		m = axis == k
+		assert abs((sign[m] > 0).mean() - .5) < 1e-2
+		others = [j for j in range(3) if j != k]
+		u = (d[m][:, others] - lo[others]) / (hi[others] - lo[others])
+		assert np.abs(u.mean(0) - .5).max() < 1e-2
+
+
+def test_step_rebuild_equals_step_then_build():
+	"""gsr_step_rebuild == gsr_step followed by gsr_build_grid + gsr_pack_gaussians on the updated parameters"""
+	from gaussian_fluids_code_b200.engine import FusedStepper
+	res = []
+	for rebuild in (False, True):
+		o, gen = engine_field(8)
+		e = o._engine
+		x = torch.rand((o.N, 3), generator=torch.Generator().manual_seed(3)).cuda()
+		e.ensure_packed(o._params())
+		bins = e.bin_samples(x, True)
+		val, grad = torch.empty((o.N, 3), device='cuda'), torch.empty((o.N, 3, 3), device='cuda')
+		e.forward(x, val, grad, False, perm=bins)
+		ref_vor = torch.randn((o.N, 3), generator=torch.Generator().manual_seed(4)).cuda() * .1
+		st = FusedStepper(e, [3e-4, 1e-5, 3e-4, 1e-5], 50, 10., 10., tau=o.clamp_threshold, min_grid_scale=o.min_grid_scale, ext_bounds=o._ext())
+		st.init(o.scalings)
+		acc, mask = e.backward_gather(x, bins.perm, bins.scs, val, grad, (0., 0., 0., 1., 0., 1.), {'ref_vor': ref_vor}, None, want_losses=True)
+		lp, nblk = e.last_loss_partials
+		params = [p.detach() for p in o._params()]
+		st.step(params, acc, mask, loss_srcs=[(lp, nblk, [1. / o.N, 0., 1. / o.N, 0., 0., 0., 0., 0.])], rebuild=rebuild)
+		if not rebuild:
+			e.build(o.positions.detach(), params=params)
+		torch.cuda.synchronize()
+		res.append([p.cpu().numpy().copy() for p in params] + [e.cell_start.cpu().numpy().copy(), e.sorted_id.cpu().numpy().copy(), e.packed.cpu().numpy().copy(),
+																   e.cull.cpu().numpy().copy(), np.array(st.scalars()[:14])])
+	for a, b in zip(*res):
+		np.testing.assert_array_equal(a, b)
