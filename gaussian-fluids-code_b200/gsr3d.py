@@ -117,11 +117,11 @@ class GaussianSplatting3D:
 		return (grad, per.sum(dim=1)) if need_val else grad
 
 	def freeze(self):
-		for p in self.parameters().values():
+		for p in GaussianSplatting3D.parameters(self).values():	# the Fast subclass adds scalars to parameters()
 			p.requires_grad_(False)
 
 	def unfreeze(self):
-		for p in self.parameters().values():
+		for p in GaussianSplatting3D.parameters(self).values():
 			p.requires_grad_()
 
 	def zero_grad(self):
