@@ -351,28 +351,15 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 			}
 		};
 		if (LPG == 32) {
-			// a whole warp on one Gaussian (small N): the 9 sample runs are looked up by 9 lanes at once, concatenated by a warp
-			// scan, and the lanes stride through the flat list (one round trip instead of nine dependent ones, every lane busy)
-			int s = 0, n = 0;
-			if (lane < 9) {
-				const int base = ((cx + lane / 3) * g.pdims[1] + (cy + lane % 3)) * g.pdims[2] + cz;
+			// a warp (or 8 lanes) on one Gaussian: the 9 sample runs are looked up by the lanes at once, concatenated by a scan
+			// inside the lane group, and the lanes stride through the flat list (one round trip instead of nine dependent ones)
+			int pre[9], off[9], total;
+			flat_runs3<(LPG >= 8 ? LPG : 8)>(lane, true, [&](int r, int &s, int &n) {
+				const int base = ((cx + r / 3) * g.pdims[1] + (cy + r % 3)) * g.pdims[2] + cz;
 				s = __ldg(scs + base);
 				n = __ldg(scs + base + 3) - s;
-			}
-			int incl = n;
-#pragma unroll
-			for (int o = 1; o < 16; o <<= 1) {
-				const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= o) incl += t2;
-			}
-			const int total = __shfl_sync(0xffffffffu, incl, 8);
-			int pre[9], off[9];
-#pragma unroll
-			for (int r = 0; r < 9; r++) {
-				pre[r] = __shfl_sync(0xffffffffu, incl - n, r);
-				off[r] = __shfl_sync(0xffffffffu, s, r) - pre[r];
-			}
-			for (int f = lane; f < total; f += 32) {
+			}, pre, off, total);
+			for (int f = lane; f < total; f += LPG) {
 				int dlt = off[0];
 #pragma unroll
 				for (int r = 1; r < 9; r++) dlt = (f >= pre[r]) ? off[r] : dlt;

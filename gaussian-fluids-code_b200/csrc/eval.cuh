@@ -42,6 +42,36 @@ __device__ __forceinline__ float lane_sum(float v)
 	return v;
 }
 
+// Flatten 9 runs [s_r, s_r + n_r) into one list for a group of LANES (8 or 32) lanes: run r is looked up by lane r % LANES
+// (`lookup(r, s, n)` leaves s = n = 0 for an absent run), a scan inside the group orders them; every lane receives
+// pre[r] = first flat index of run r and off[r] = s_r - pre[r], so that flat index f of run r is sorted index f + off[r].
+template <int LANES, typename F>
+__device__ __forceinline__ void flat_runs3(int lane, bool any, F lookup, int (&pre)[9], int (&off)[9], int &total)
+{
+	static_assert(LANES == 8 || LANES == 32, "lane groups of 8 or 32");
+	int sa = 0, na = 0, sb = 0, nb = 0;
+	if (any && lane < 9) lookup(lane, sa, na);
+	if (any && LANES == 8 && lane == 0) lookup(8, sb, nb);
+	int incl = na;
+#pragma unroll
+	for (int o = 1; o < (LANES == 8 ? 8 : 16); o <<= 1) {
+		const int t = __shfl_up_sync(0xffffffffu, incl, o, LANES);
+		if (lane >= o) incl += t;
+	}
+	const int tot_a = __shfl_sync(0xffffffffu, incl, LANES == 8 ? 7 : 8, LANES);
+#pragma unroll
+	for (int r = 0; r < (LANES == 8 ? 8 : 9); r++) {
+		pre[r] = __shfl_sync(0xffffffffu, incl - na, r, LANES);
+		off[r] = __shfl_sync(0xffffffffu, sa, r, LANES) - pre[r];
+	}
+	total = tot_a;
+	if (LANES == 8) {
+		pre[8] = tot_a;
+		off[8] = __shfl_sync(0xffffffffu, sb, 0, LANES) - tot_a;
+		total = tot_a + __shfl_sync(0xffffffffu, nb, 0, LANES);
+	}
+}
+
 // `lane` in [0, LANES).  With LANES > 1 every lane of the warp must call this (shuffles), valid or not.
 template <bool NEED_GRAD, int LANES>
 __device__ __forceinline__ void eval_point3(const EvalParams &P, const int32_t *__restrict__ cell_start, const float4 *__restrict__ packed,
@@ -57,33 +87,21 @@ __device__ __forceinline__ void eval_point3(const EvalParams &P, const int32_t *
 	const int cx = cell_coord(x, g.lo[0], gs), cy = cell_coord(y, g.lo[1], gs), cz = cell_coord(z, g.lo[2], gs);
 	const int zlo = max(cz - 1, 0), zhi = min(cz + 1, g.dims[2] - 1);
 	const float tau = g.tau, q_thr = P.q_thr;
-	if (LANES == 32) {
-		// Latency shape for a whole warp on ONE point (the reference's own sizes: a few thousand points, ~200 candidates each).
-		// The 9 runs are looked up by 9 lanes at once (one round trip instead of nine dependent ones), concatenated by a
-		// warp scan, and the lanes then stride through the FLAT candidate list — every lane busy, all record loads independent.
-		int s = 0, n = 0;
-		if (lane < 9 && zlo <= zhi) {
-			const int gi = cx - 1 + lane / 3, gj = cy - 1 + lane % 3;
+	if (LANES == 32) {	// (measured: for 8-lane groups the run lookup per candidate costs more than the dependent loads it saves)
+		// Latency shape: LANES lanes (a warp, or 8 lanes) on ONE point (the reference's own sizes: up to ~10^5 points with
+		// ~200-300 candidates each).  The 9 runs are looked up by the lanes at once (one round trip instead of nine dependent
+		// ones), concatenated by a scan inside the lane group, and the lanes then stride through the FLAT candidate list —
+		// every lane busy, all record loads independent.
+		int pre[9], off[9], total;
+		flat_runs3<(LANES >= 8 ? LANES : 8)>(lane, zlo <= zhi, [&](int r, int &s, int &n) {
+			const int gi = cx - 1 + r / 3, gj = cy - 1 + r % 3;
 			if (gi >= 0 && gi < g.dims[0] && gj >= 0 && gj < g.dims[1]) {
 				const int base = (gi * g.dims[1] + gj) * g.dims[2];
 				s = __ldg(cell_start + base + zlo);
 				n = __ldg(cell_start + base + zhi + 1) - s;
 			}
-		}
-		int incl = n;
-#pragma unroll
-		for (int o = 1; o < 16; o <<= 1) {
-			const int t = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o) incl += t;
-		}
-		const int total = __shfl_sync(0xffffffffu, incl, 8);
-		int pre[9], off[9];	// first flat index of run r, and (sorted index - flat index) inside it
-#pragma unroll
-		for (int r = 0; r < 9; r++) {
-			pre[r] = __shfl_sync(0xffffffffu, incl - n, r);
-			off[r] = __shfl_sync(0xffffffffu, s, r) - pre[r];
-		}
-		for (int f = lane; f < total; f += 32) {
+		}, pre, off, total);
+		for (int f = lane; f < total; f += LANES) {
 			int d = off[0];
 #pragma unroll
 			for (int r = 1; r < 9; r++) d = (f >= pre[r]) ? off[r] : d;
