@@ -292,6 +292,14 @@ class HashEngine:
 											  ptr(data), ptr(normal), stream()), 'gsr_sample_box_surface')
 		return data, normal
 
+	def advect_density(self, axes, domain, dt, density_a, out_a, density_b=None, out_b=None):
+		"""gsr_advect_density: semi-Lagrangian step of one or two density fields on the lattice spanned by `axes` = (xs, ys, zs)"""
+		xs, ys, zs = axes
+		dom = (C.c_float * 6)(*[float(v) for v in domain])
+		check(self.lib.gsr_advect_density(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True), ptr(self.cull),
+										  ptr(xs), ptr(ys), ptr(zs), C.c_int(xs.numel()), C.c_int(ys.numel()), C.c_int(zs.numel()), dom, C.c_float(dt),
+										  ptr(density_a, name='density'), ptr(density_b, allow_none=True), ptr(out_a), ptr(out_b, allow_none=True), stream()), 'gsr_advect_density')
+
 	def sample_losses(self, val, grad, refs, Q):
 		"""gsr_sample_losses: the 8 loss slots of include/gsr_b200.h summed over the samples (device tensor, no sync)"""
 		cfg = LossCfg()

@@ -258,6 +258,15 @@ int gsr_sample_box(const float *box, int64_t n, uint64_t seed, uint32_t stream_i
 int gsr_sample_box_surface(const float *box, int64_t n, uint64_t seed, uint32_t stream_id, const float *iteration_dev, float *data, float *normal,
 			   void *stream);
 
+/* ---- N1: passive density advection on a regular lattice  (advected_density + ti_get_interp_val, 3D/advance_density.py:25-63):
+ *          per voxel, RK4 back-trace by `dt` (callers pass -dt) through the field, clamp to `domain`, trilinear resampling of the
+ *          old density — one kernel, no lattice or back-traced coordinates in memory.  xs/ys/zs: the lattice's axis coordinates
+ *          (device, nx / ny / nz floats, the reference's torch.linspace); domain = {x_min, x_max, y_min, y_max, z_min, z_max} (host);
+ *          density_* / out_* (nx, ny, nz) float32, out must not alias in; the second field is optional (both NULL). */
+int gsr_advect_density(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed, const float *cull,
+		       const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, const float *domain, float dt,
+		       const float *density_a, const float *density_b, float *out_a, float *out_b, void *stream);
+
 /* ---- measurement helpers (bench.py work census and roofline denominators) ------------------------ */
 /* counts[0] (device uint64) += candidate visits C for one evaluation of the Q points (occupancy of each point's 27 (9)-cell
  * stencil under the reference binning: the unit of work of SURVEY 8d); when packed != NULL also counts[1] += accepted pairs P. */
