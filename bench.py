@@ -284,7 +284,7 @@ def run_ours(args):
 	out = {
 		'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
 		'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-		'config': {'workload': workload_name(args, n), 'sharding': f'samples sharded over {world} rank(s): per rank N training + 8192 boundary samples per iteration (global Q = {world}*N, global normalisers) and {args.test_res}^3 of a {args.test_res}x{args.test_res}x{world * args.test_res} test lattice; parameters replicated, 1 NCCL all-reduce / iteration' if world > 1 else 'single GPU',
+		'config': {'workload': workload_name(args, n), 'sharding': f'samples sharded over {world} rank(s): per rank N training + 8192 boundary samples per iteration (global Q = {world}*N, global normalisers) and {args.test_res}^3 of a {args.test_res}x{args.test_res}x{world * args.test_res} test lattice; parameters replicated; per iteration one exchange of the 3*N*12 gradient accumulators + loss sums: ' + ('a single kernel summing all ranks\' buffers over NVLink peer memory (csrc/xrank.cu)' if os.environ.get('GSR_EXCHANGE', 'p2p') == 'p2p' else 'NCCL all-reduce') if world > 1 else 'single GPU',
 				   'l2_policy': 'every step sweeps > 126 MB (test lattice passes write 2.1M x 12 floats; the iterations rewrite all buffers), inputs regenerated each iteration',
 				   'work_census': 'candidate visits counted on the last warm-up step (gsr_count_pairs), RK4 counted as 4 or 5 evaluations of its start points'},
 		'timesteps_per_s': args.steps / (ms * 1e-3), 'project_iters_per_s': args.steps * args.iters / (ms * 1e-3),

@@ -17,10 +17,16 @@ class _Scratch:
 	def __init__(self, device):
 		self.device = device
 		self.bufs = {}
+		self.retired = []
 
 	def get(self, name, nbytes):
 		b = self.bufs.get(name)
 		if b is None or b.numel() < nbytes:
+			if b is not None:
+				# A captured CUDA graph may still hold this buffer's address (the iteration graph is captured once and replayed for
+				# the rest of the run, while a later, larger batch — the test lattice — outgrows the buffer).  Never hand the old
+				# block back to the allocator: a replay would scribble over whoever received it.
+				self.retired.append(b)
 			b = torch.empty(max(int(nbytes * 1.25), 256), dtype=torch.uint8, device=self.device)
 			self.bufs[name] = b
 		return b

@@ -16,9 +16,12 @@ Gaussian parameters, hash and optimiser state are replicated; ONE NCCL all-reduc
 gradient accumulators and the loss partial sums, after which every rank runs the identical fused step, so the
 replicas stay bit-identical without a broadcast.
 """
+import ctypes as C
+import os
+
 import torch
 
-from . import advance3d, gsr3d
+from . import _lib, advance3d, gsr3d
 from .init_cond3d import sample_on_box
 from .synth import make_fast3d, synthetic_field
 
@@ -51,6 +54,52 @@ class Census:
 		return int(c[0]), int(c[1])
 
 
+class PeerExchange:
+	"""
+	The per-iteration exchange of the sharded optimisation as ONE kernel over NVLink peer memory (csrc/xrank.cu): every rank's
+	accumulator buffer lives in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into every
+	rank of the node), in two parities, and gsr_xrank_sum adds the peers' buffers in rank order after a signal-pad handshake.
+	"""
+	SIGNAL_WORD0 = 256	# first uint32 of the signal pad used here (torch's own barriers use the low words)
+
+	def __init__(self, n_floats, device):
+		import torch.distributed as dist
+		import torch.distributed._symmetric_memory as symm_mem
+		self.n = (int(n_floats) + 3) // 4 * 4
+		self.rank, self.world = dist.get_rank(), dist.get_world_size()
+		self.bufs, self.hdls = [], []
+		for _ in range(2):
+			b = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+			b.zero_()
+			self.hdls.append(symm_mem.rendezvous(b, dist.group.WORLD))
+			self.bufs.append(b)
+		h = self.hdls[0]
+		if h.signal_pad_size < 4 * (self.SIGNAL_WORD0 + self.world):
+			raise _lib.GsrError('signal pad too small')
+		self.out = torch.zeros(self.n, dtype=torch.float32, device=device)
+		self.err = torch.zeros(1, dtype=torch.int32, device=device)
+		self.base = torch.zeros(1, dtype=torch.int32, device=device)
+		self._base_host = 0
+		self._ptrs = [(C.c_void_p * self.world)(*[int(p) for p in hd.buffer_ptrs]) for hd in self.hdls]
+		self._sigs = (C.c_void_p * self.world)(*[int(p) + 4 * self.SIGNAL_WORD0 for p in h.signal_pad_ptrs])
+		torch.cuda.synchronize()
+		dist.barrier()	# every rank's buffers are zeroed and mapped before anyone signals
+
+	def new_phase(self):
+		"""epochs are base + iteration + 1: a new optimisation phase (iteration counter back to 0) moves the base past the old ones"""
+		self._base_host += 100000
+		self.base.fill_(self._base_host)
+
+	def sum(self, parity, iteration_dev):
+		lib = _lib.lib()
+		_lib.check(lib.gsr_xrank_sum(self._ptrs[parity], self._sigs, C.c_int(self.rank), C.c_int(self.world), C.c_int64(self.n), _lib.ptr(iteration_dev),
+									 _lib.ptr(self.base, torch.int32), _lib.ptr(self.out), _lib.ptr(self.err, torch.int32), _lib.stream()), 'gsr_xrank_sum')
+
+	def check(self):
+		if int(self.err.item()):
+			raise _lib.GsrError('gsr_xrank_sum: a peer did not publish its buffer in time')
+
+
 class ShardedProjector(advance3d.FusedProjector):
 	"""FusedProjector whose accumulators and loss partials live in one flat buffer that is all-reduced once per iteration"""
 
@@ -62,22 +111,38 @@ class ShardedProjector(advance3d.FusedProjector):
 		N = gv.N
 		nblk, nblkb = e.lib.gsr_loss_blocks(Q), e.lib.gsr_loss_blocks(Qb)
 		lay = flat_layout(N, nblk, nblkb)
-		self.flat = torch.zeros(lay['total'], dtype=torch.float32, device=gsr3d.device)
-		self.acc = self.flat[lay['acc'][0]:lay['acc'][1]].view(3, N, 12)	# set 0: boundary (direct), sets 1, 2: vorticity / divergence
-		self.lp = self.flat[lay['lp'][0]:lay['lp'][1]].view(nblk, 8)
-		self.lpb = self.flat[lay['lpb'][0]:lay['lpb'][1]].view(nblkb, 8)
+		# exchange: 'p2p' = one kernel over NVLink peer memory (default when sharded), 'nccl' = torch.distributed.all_reduce
+		self.exchange = os.environ.get('GSR_EXCHANGE', 'p2p') if world > 1 else 'none'
+		self.peer = None
+		if self.exchange == 'p2p':
+			try:
+				self.peer = PeerExchange(lay['total'], gsr3d.device)
+			except Exception as ex:	# no symmetric memory on this system: say so and use the library collective
+				print(f'[gsr] peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL all_reduce', flush=True)
+				self.exchange = 'nccl'
+		flats = self.peer.bufs if self.peer else [torch.zeros(lay['total'], dtype=torch.float32, device=gsr3d.device)]
+		view = lambda f: (f[lay['acc'][0]:lay['acc'][1]].view(3, N, 12), f[lay['lp'][0]:lay['lp'][1]].view(nblk, 8), f[lay['lpb'][0]:lay['lpb'][1]].view(nblkb, 8))
+		self.flats = flats
+		self.views = [view(f) for f in flats]	# per parity: (acc, lp, lpb) the gather kernels write
+		self.reduced = view(self.peer.out) if self.peer else self.views[0]	# what the fused step reads
+		self.flat = flats[0]
+		self.acc, self.lp, self.lpb = self.views[0]	# set 0: boundary (direct), sets 1, 2: vorticity / divergence
 		self.nblk, self.nblkb = nblk, nblkb
 		self._streams = None
+		if self.peer:
+			self.peer.new_phase()
 
 	def restart(self):
 		"""begin a new project phase on the same buffers: fresh optimiser state, fresh hash"""
+		if self.peer:
+			self.peer.new_phase()
 		self.stepper.init(self.gv.scalings)
 		self._rebuild()
 		cur = self.ref.velocity_field
 		cur._engine._packed_key = None
 		cur._engine.ensure_packed(cur._params())
 
-	def iterate(self, data, boundary=None, census=None):
+	def iterate(self, data, boundary=None, census=None, parity=0):
 		"""
 		One optimiser iteration.  Three independent chains run on three streams (fork / join by events, so a captured graph
 		keeps the concurrency): the RK4 pull-back reference (previous field), the forward pass of the current field, and the
@@ -86,6 +151,8 @@ class ShardedProjector(advance3d.FusedProjector):
 		gv, e = self.gv, self.gv._engine
 		cur = self.ref.velocity_field
 		Q, Qg = data.shape[0], data.shape[0] * self.world
+		acc_w, lp_w, lpb_w = self.views[parity if self.peer else 0]
+		acc_r, lp_r, lpb_r = self.reduced
 		main = torch.cuda.current_stream()
 		if self._streams is None:
 			self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
@@ -104,8 +171,8 @@ class ShardedProjector(advance3d.FusedProjector):
 				valb = self._tmp('valb', (Qb, 3))
 				e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
 				_, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
-											  {'normals': bnormal}, None, Q_norm=Qbg, tag='acc_b', acc=self.acc, loss_partials=self.lpb)
-				srcs_b = [(self.lpb, self.nblkb, [0., 0., 0., self.boundary_lambda / Qbg, 0., 0., 0., 0.])]
+											  {'normals': bnormal}, None, Q_norm=Qbg, tag='acc_b', acc=acc_w, loss_partials=lpb_w)
+				srcs_b = [(lpb_r, self.nblkb, [0., 0., 0., self.boundary_lambda / Qbg, 0., 0., 0., 0.])]
 				if census is not None:
 					e.count_pairs(bdata, census.c, 2, True)
 				done_b = torch.cuda.Event()
@@ -124,8 +191,8 @@ class ShardedProjector(advance3d.FusedProjector):
 		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
 		main.wait_event(done_f)
 		_, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
-									{'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, Q_norm=Qg, acc=self.acc, loss_partials=self.lp)
-		srcs = [(self.lp, self.nblk, [self.w['vor'] / Qg, 0., self.w['div'] / Qg, 0., 0., 0., 0., 0.])]
+									{'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, Q_norm=Qg, acc=acc_w, loss_partials=lp_w)
+		srcs = [(lp_r, self.nblk, [self.w['vor'] / Qg, 0., self.w['div'] / Qg, 0., 0., 0., 0., 0.])]
 		if census is not None:
 			cur._engine.count_pairs(data, census.c, 5, True)
 			e.count_pairs(data, census.c, 2, True)
@@ -133,9 +200,11 @@ class ShardedProjector(advance3d.FusedProjector):
 			main.wait_event(done_b)
 			mask |= mask_b
 			srcs += srcs_b
-		if self.world > 1:
+		if self.peer:
+			self.peer.sum(parity, self.stepper.state[:1])	# one kernel: handshake + sum of all ranks' buffers over NVLink
+		elif self.world > 1:
 			torch.distributed.all_reduce(self.flat)
-		self.stepper.step([p.detach() for p in gv._params()], self.acc, mask, loss_srcs=srcs, rebuild=True)	# update + hash + packed records
+		self.stepper.step([p.detach() for p in gv._params()], acc_r, mask, loss_srcs=srcs, rebuild=True)	# update + hash + packed records
 
 
 class LeapfrogTimestep:
@@ -202,17 +271,21 @@ class LeapfrogTimestep:
 		# project, fixed iteration count; the iteration is captured once per orientation into a CUDA graph and replayed
 		ent = self._projector(new, cur)
 		fp = ent['fp']
-		body = lambda: fp.iterate(self._samples(fp), self._boundary(fp) if self.boundary_lambda else None, None)
+		one = lambda parity, cen=None: fp.iterate(self._samples(fp), self._boundary(fp) if self.boundary_lambda else None, cen, parity=parity)
+		unit = 2 if fp.peer else 1	# the peer-memory exchange alternates between two buffers: a graph holds one iteration of each parity
+		if self.iters % unit or self.check_iter % unit:
+			raise ValueError('iters and check_iter must be even with the peer-memory exchange')
+		body = lambda: [one(k) for k in range(unit)]
 		done = 0
 		if self.use_graph and census is None and ent['graph'] is None:
 			side = torch.cuda.Stream()
 			side.wait_stream(torch.cuda.current_stream())
 			with torch.cuda.stream(side):
-				for _ in range(2):	# eager warm-up iterations (they count): sizes every scratch buffer
+				for _ in range(2 // unit):	# eager warm-up iterations (they count): sizes every scratch buffer
 					l0 = new._engine.lib.gsr_launch_count()
 					body()
 					ent['per_iter'] = new._engine.lib.gsr_launch_count() - l0
-					done += 1
+					done += unit
 			torch.cuda.current_stream().wait_stream(side)
 			ent['graph'] = torch.cuda.CUDAGraph()
 			with torch.cuda.graph(ent['graph']):
@@ -222,16 +295,19 @@ class LeapfrogTimestep:
 		while done < self.iters:
 			if graph is not None:
 				graph.replay()
-				self.graph_launches += ent['per_iter']	# kernels of this library inside one replayed iteration
+				self.graph_launches += ent['per_iter']	# kernels of this library inside one replay
 			else:
-				fp.iterate(self._samples(fp), self._boundary(fp) if self.boundary_lambda else None, census)
-			done += 1
+				for k in range(unit):
+					one(k, census)
+			done += unit
 			if done % self.check_iter == 0:
 				self.last_test = fp.evaluate(self.lattice, probe=getattr(self, 'probe', None))
 				if census is not None:
 					cur._engine.count_pairs(self.lattice, census.c, 5, True)
 					new._engine.count_pairs(self.lattice, census.c, 1, True)
 		fp.finish()
+		if fp.peer:
+			fp.peer.check()
 		self.cur, self.new = new, cur
 		# the two output fields (|vorticity| and divergence on the lattice)
 		g = self.cur.gradient(self.lattice)

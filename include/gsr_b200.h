@@ -249,6 +249,15 @@ int gsr_step_rebuild(const gsr_step_cfg *cfg, int64_t N, float *positions, float
 		     const gsr_grid_desc *g, int32_t *cell_start, int32_t *sorted_id, float *packed, float *cull, void *hash_ws, size_t hash_ws_bytes,
 		     void *stream);
 
+/* ---- multi-GPU exchange: out[i] = sum over ranks r = 0..world-1, in rank order, of peer_bufs[r][i] — ONE kernel over
+ *          NVLink peer memory instead of a library all-reduce.  peer_bufs / peer_signal_pads: HOST arrays of `world` device pointers
+ *          (this rank's own included) into symmetric memory; a signal pad holds >= world uint32, zero-initialised.  The epoch of a call
+ *          is *epoch_base_dev + (uint32)*iteration_dev + 1 and must grow by one per call on every rank (buffers alternate between two
+ *          parities in the caller).  n_floats a multiple of 4, buffers 16-byte aligned.  *err_flag (device) is set to 1 when a peer
+ *          did not arrive within ~1 s (the kernel never hangs). */
+int gsr_xrank_sum(const void *const *peer_bufs, void *const *peer_signal_pads, int rank, int world, int64_t n_floats, const float *iteration_dev,
+		  const int32_t *epoch_base_dev, float *out, int32_t *err_flag, void *stream);
+
 /* ---- a7: sample generation  (3D/advance.py:339-340 rand_like(positions) * extent + min; 3D/init_cond.py:227-249
  *          sample_on_box) — one kernel per sample set, counter-based Philox keyed by (seed, stream_id) and indexed by
  *          (sample, iteration); the iteration number is read from DEVICE memory (e.g. state + GSR_ST_T, may be NULL = 0)

@@ -103,3 +103,28 @@ def test_step_rebuild_equals_step_then_build():
 																   e.cull.cpu().numpy().copy(), np.array(st.scalars()[:14])])
 	for a, b in zip(*res):
 		np.testing.assert_array_equal(a, b)
+
+
+def test_xrank_sum_single_rank():
+	"""gsr_xrank_sum with world = 1 (a single GPU cannot host kernels that wait for one another): the handshake with itself, the
+	epoch arithmetic over two parities, and the copy-out.  The 2-rank behaviour is checked by tools/exchange_check.py under torchrun
+	(bit-identical replicas, equality with NCCL) and the summation identity by tests/test_multirank_cpu.py."""
+	import ctypes as C
+	from gaussian_fluids_code_b200 import _lib
+	lib = _lib.lib()
+	n = 4096
+	bufs = [torch.randn(n, device='cuda') for _ in range(2)]
+	pad = torch.zeros(64, dtype=torch.int32, device='cuda')
+	out = torch.zeros(n, device='cuda')
+	err = torch.zeros(1, dtype=torch.int32, device='cuda')
+	base = torch.full((1,), 1000, dtype=torch.int32, device='cuda')
+	it = torch.zeros(1, device='cuda')
+	sig = (C.c_void_p * 1)(pad.data_ptr())
+	for k in range(4):
+		it.fill_(float(k))
+		ptrs = (C.c_void_p * 1)(bufs[k % 2].data_ptr())
+		rc = lib.gsr_xrank_sum(ptrs, sig, C.c_int(0), C.c_int(1), C.c_int64(n), _lib.ptr(it), _lib.ptr(base, torch.int32), _lib.ptr(out), _lib.ptr(err, torch.int32), _lib.stream())
+		assert rc == 0
+		torch.cuda.synchronize()
+		assert torch.equal(out, bufs[k % 2]) and int(err.item()) == 0 and int(pad[0].item()) == 1000 + k + 1
+	assert lib.gsr_xrank_sum(ptrs, sig, C.c_int(0), C.c_int(1), C.c_int64(n + 1), _lib.ptr(it), _lib.ptr(base, torch.int32), _lib.ptr(out), _lib.ptr(err, torch.int32), _lib.stream()) == -1
