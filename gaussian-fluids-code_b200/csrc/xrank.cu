@@ -30,7 +30,7 @@ __device__ __forceinline__ float4 ld_peer4(const float4 *p)
 
 constexpr int XR_THREADS = 256;
 constexpr int XR_MAX_WORLD = 16;
-constexpr unsigned XR_SPIN_LIMIT = 1u << 26;	// polls of the local signal pad (~1 s) before giving up
+constexpr unsigned XR_SPIN_LIMIT = 1u << 21;	// polls of the local signal pad (~1 s) before giving up; once the flag is up nobody waits again
 
 struct XrankArgs {
 	const float4 *peer[XR_MAX_WORLD];	// every rank's buffer of this parity (own rank included), n4 float4 each
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(XR_THREADS) xrank_sum_kernel(XrankArgs a, size
 		__threadfence_system();	// the gather kernels of this stream finished before this launch: make their stores visible system-wide
 		st_release_sys(a.sig[threadIdx.x] + a.rank, epoch);
 	}
-	if (threadIdx.x < a.world) {
+	if (threadIdx.x < a.world && *((volatile int32_t *)err) == 0) {
 		const uint32_t *mine = a.sig[a.rank] + threadIdx.x;
 		unsigned spins = 0;
 		while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
