@@ -281,6 +281,8 @@ static int64_t tile_slots(const Grid &g, int64_t Q)
 	return Q / TL_TILE + g.pcell / rowlen + 2;
 }
 
+extern int g_force_radix;	// grid.cu
+
 // tunables (gsr_set_tuning)
 int g_tiled_min_q = 1 << 17;
 int g_tiled_cap = 512;
@@ -329,6 +331,7 @@ extern "C" int gsr_set_tuning(int key, int value)
 	switch (key) {
 	case GSR_TUNE_TILED_MIN_Q: g_tiled_min_q = value; return GSR_OK;
 	case GSR_TUNE_RK4_SMEM_STATE: g_rk4_smem_state = value; return GSR_OK;
+	case GSR_TUNE_FORCE_RADIX: g_force_radix = value; return GSR_OK;
 	case GSR_TUNE_FW_P4_MIN_SPC: g_fw_p4_min_spc = value; return GSR_OK;
 	case GSR_TUNE_TILED_CAP:
 		if (value < 0 || tiled_smem(value) > 200 * 1024) return GSR_EINVAL;

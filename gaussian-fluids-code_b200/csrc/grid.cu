@@ -239,17 +239,19 @@ static inline int key_passes(uint32_t max_key)
 }
 
 struct SortWs {
-	uint32_t *keys0, *kA, *kB, *vTmp, *hist;
+	uint32_t *keys0, *kA, *kB, *vTmp, *hist, *cells;
+	size_t cells_cap;
 	int nblocks;
 };
 
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-static size_t sort_ws_bytes(int64_t n)
+static size_t sort_ws_bytes(int64_t n, int64_t cells = 0)
 {
 	int64_t nb = (n + RS_TILE - 1) / RS_TILE;
 	if (nb < 1) nb = 1;
-	return 4 * align256(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1)) + align256(sizeof(uint32_t) * 256 * (size_t)nb);
+	// 4 arrays of n, the radix histograms, and one per-cell counter array (the counting-sort path)
+	return 4 * align256(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1)) + align256(sizeof(uint32_t) * 256 * (size_t)nb) + align256(sizeof(uint32_t) * (size_t)(cells + 2));
 }
 
 static bool carve_sort_ws(void *ws, size_t ws_bytes, int64_t n, SortWs &s)
@@ -264,6 +266,8 @@ static bool carve_sort_ws(void *ws, size_t ws_bytes, int64_t n, SortWs &s)
 	s.hist = (uint32_t *)p;
 	s.nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
 	if (s.nblocks < 1) s.nblocks = 1;
+	s.cells = (uint32_t *)(p + align256(sizeof(uint32_t) * 256 * (size_t)s.nblocks));
+	s.cells_cap = (ws_bytes - (size_t)((char *)s.cells - (char *)ws)) / sizeof(uint32_t);
 	return true;
 }
 
@@ -404,8 +408,93 @@ static int launch_small_hash(const float *pts, int n, const Grid &g, int ncell, 
 	return GSR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Counting sort by cell for mid-size inputs whose cells are not crowded (n up to millions, the per-iteration hash of
+// N = 64 000 .. 10^6 Gaussians and of Q = N sample batches): histogram with global atomics -> one-CTA scan (= cell_start)
+// -> slot scatter -> canonical intra-cell order by rank counting (small_rank_kernel).  4 launches + 2 memsets instead of
+// the 3 launches per 8-bit digit of the radix path; the result is identical (stable sort by cell).
+// ------------------------------------------------------------------------------------------------
+template <int D, bool GAUSS>
+__global__ void __launch_bounds__(256) ch_keys_hist_kernel(const float *__restrict__ pts, int n, Grid g, uint32_t *__restrict__ keys, uint32_t *__restrict__ hist)
+{
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t key = GAUSS ? gauss_key<D>(pts, i, g) : sample_key<D, false>(pts, i, g);
+	keys[i] = key;
+	atomicAdd(hist + key, 1u);
+}
+
+// exclusive scan of hist[0..m) by one CTA -> out (int32); hist may alias out
+__global__ void __launch_bounds__(1024) ch_scan_kernel(const uint32_t *hist, int m, int32_t *out)
+{
+	__shared__ uint32_t warp_sums[32];
+	const int T = 1024, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int chunk = (m + T - 1) / T, b = threadIdx.x * chunk, e = min(b + chunk, m);
+	uint32_t s = 0;
+	for (int i = b; i < e; i++) s += hist[i];
+	uint32_t v = s;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+		if (lane >= o) v += t;
+	}
+	if (lane == 31) warp_sums[w] = v;
+	__syncthreads();
+	if (w == 0) {
+		const uint32_t ws = warp_sums[lane];
+		uint32_t t2 = ws;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, t2, o);
+			if (lane >= o) t2 += t;
+		}
+		warp_sums[lane] = t2 - ws;
+	}
+	__syncthreads();
+	uint32_t run = warp_sums[w] + (v - s);
+	for (int i = b; i < e; i++) {
+		const uint32_t t = hist[i];
+		out[i] = (int32_t)run;
+		run += t;
+	}
+}
+
+__global__ void __launch_bounds__(256) ch_scatter_kernel(const uint32_t *__restrict__ keys, int n, const int32_t *__restrict__ cell_start, uint32_t *__restrict__ fill,
+							 uint32_t *__restrict__ ids_tmp)
+{
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t key = keys[i];
+	ids_tmp[(uint32_t)cell_start[key] + atomicAdd(fill + key, 1u)] = (uint32_t)i;
+}
+
+int g_force_radix = 0;	// GSR_TUNE_FORCE_RADIX: tests compare the hash paths
+
+static bool count_hash_ok(int64_t n, int64_t ncell, const SortWs &s)
+{
+	return !g_force_radix && n > SH_MAX_N && ncell * 48 >= n && ncell <= (1 << 22) && s.cells_cap >= (size_t)(ncell + 2);
+}
+
+template <int D, bool GAUSS>
+static int launch_count_hash(const float *pts, int n, const Grid &g, int ncell, int32_t *cell_start, int32_t *ids_out, SortWs &s,
+			     const float *scal, const float *rot, const float *vals, float4 *packed, float *cull, cudaStream_t st)
+{
+	// cell_start doubles as the histogram (ncell + 1 counters: the last one collects the items outside the hash)
+	cudaError_t e = cudaMemsetAsync(cell_start, 0, sizeof(int32_t) * (size_t)(ncell + 1), st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(s.cells, 0, sizeof(uint32_t) * (size_t)(ncell + 1), st);
+	if (e != cudaSuccess) return (int)e;
+	g_launches += 4;
+	ch_keys_hist_kernel<D, GAUSS><<<(n + 255) / 256, 256, 0, st>>>(pts, n, g, s.kA, (uint32_t *)cell_start);
+	ch_scan_kernel<<<1, 1024, 0, st>>>((const uint32_t *)cell_start, ncell + 1, cell_start);
+	ch_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.kA, n, cell_start, s.cells, s.vTmp);
+	small_rank_kernel<D, GAUSS><<<(n + 127) / 128, 128, 0, st>>>(pts, n, ncell, cell_start, ids_out, s.kA, s.vTmp, scal, rot, vals, packed, cull);
+	GSR_CHECK_LAUNCH();
+	return GSR_OK;
+}
+
 static bool small_hash_ok(int64_t n, int64_t ncell)
 {
+	if (g_force_radix) return false;
 	// one CTA, shared-memory histogram, and an intra-cell ranking that is quadratic in the cell occupancy
 	return n > 0 && n <= SH_MAX_N && ncell <= SH_MAX_CELLS && ncell * 48 >= n;
 }
@@ -434,8 +523,16 @@ __global__ void min_kernel(const float *__restrict__ a, int64_t n, float *out)
 
 using namespace gsr;
 
-extern "C" size_t gsr_build_grid_ws_bytes(const gsr_grid_desc *, int64_t N) { return sort_ws_bytes(N); }
-extern "C" size_t gsr_bin_samples_ws_bytes(const gsr_grid_desc *, int64_t Q) { return sort_ws_bytes(Q); }
+extern "C" size_t gsr_build_grid_ws_bytes(const gsr_grid_desc *d, int64_t N)
+{
+	Grid g;
+	return sort_ws_bytes(N, make_grid(d, g) ? g.ncell : 0);
+}
+extern "C" size_t gsr_bin_samples_ws_bytes(const gsr_grid_desc *d, int64_t Q)
+{
+	Grid g;
+	return sort_ws_bytes(Q, make_grid(d, g) ? g.pcell : 0);
+}
 
 extern "C" int64_t gsr_padded_cells(const gsr_grid_desc *d)
 {
@@ -470,6 +567,10 @@ extern "C" int gsr_build_grid(const gsr_grid_desc *d, const float *positions, in
 		// one launch: keys, histogram, scan, scatter, canonical order and (optionally) the packed records
 		int rc = (g.D == 3) ? launch_small_hash<3, true>(positions, n, g, g.ncell, cell_start, sorted_id, s.kA, s.vTmp, scalings, rotations, values, (float4 *)packed, cull, st)
 				    : launch_small_hash<2, true>(positions, n, g, g.ncell, cell_start, sorted_id, s.kA, s.vTmp, scalings, rotations, values, (float4 *)packed, cull, st);
+		if (rc) return rc;
+	} else if (count_hash_ok(N, g.ncell, s)) {
+		int rc = (g.D == 3) ? launch_count_hash<3, true>(positions, n, g, g.ncell, cell_start, sorted_id, s, scalings, rotations, values, (float4 *)packed, cull, st)
+				    : launch_count_hash<2, true>(positions, n, g, g.ncell, cell_start, sorted_id, s, scalings, rotations, values, (float4 *)packed, cull, st);
 		if (rc) return rc;
 	} else {
 		const uint32_t *ks = s.keys0;
@@ -514,6 +615,13 @@ extern "C" int gsr_bin_samples(const gsr_grid_desc *d, const float *x, int64_t Q
 			return (g.D == 3) ? launch_small_hash<3, false>(x, n, g, g.pcell, scs, perm, s.kA, s.vTmp, nullptr, nullptr, nullptr, nullptr, nullptr, st)
 					  : launch_small_hash<2, false>(x, n, g, g.pcell, scs, perm, s.kA, s.vTmp, nullptr, nullptr, nullptr, nullptr, nullptr, st);
 		}
+	}
+	if (!shift && count_hash_ok(Q, g.pcell, s)) {
+		// the cell table is a by-product; without a caller buffer it lands in the radix histogram scratch when that is large enough
+		int32_t *scs = sample_cell_start ? sample_cell_start : ((size_t)(g.pcell + 1) <= 256 * (size_t)s.nblocks ? (int32_t *)s.hist : nullptr);
+		if (scs)
+			return (g.D == 3) ? launch_count_hash<3, false>(x, n, g, g.pcell, scs, perm, s, nullptr, nullptr, nullptr, nullptr, nullptr, st)
+					  : launch_count_hash<2, false>(x, n, g, g.pcell, scs, perm, s, nullptr, nullptr, nullptr, nullptr, nullptr, st);
 	}
 	const uint32_t *ks = s.keys0;
 	if (n > 0) {

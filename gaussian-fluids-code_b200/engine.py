@@ -172,7 +172,7 @@ class HashEngine:
 		alloc = (lambda name, shape: torch.empty(shape, dtype=torch.int32, device=self.device)) if key else (lambda name, shape: self.scratch.typed(name + tag, shape, torch.int32))
 		perm = alloc('perm_', (Q,))
 		scs = None
-		if need_cells or need_tiles or Q <= 16384:	# small batches: the single-launch hash produces the cell table anyway
+		if True:	# the single-launch and counting hash paths produce the cell table anyway, and it is small
 			pcell = self.lib.gsr_padded_cells(C.byref(self.desc))
 			scs = alloc('scs_', (pcell + 1,))
 		nbytes = self.lib.gsr_bin_samples_ws_bytes(C.byref(self.desc), C.c_int64(Q))

@@ -146,3 +146,34 @@ def test_against_oracle_seeded(n, Q):
 		for nm, b in zip(NAMES, grp):
 			a = acc[f'{tag}_{nm}_grad'].cpu().numpy()
 			assert rel_err(a, b) < 5e-4, (tag, nm, rel_err(a, b))
+
+
+@pytest.mark.parametrize('n,Q', [(10, 3000), (20, 12000), (30, 40000), (34, 70000)])
+def test_hash_paths_agree(n, Q):
+	"""the single-launch hash (n <= 16384), the counting sort (larger, uncrowded cells) and the stable radix sort must produce the
+	same cell tables, the same canonical Gaussian order and the same sample order; outputs downstream are then bit-identical"""
+	import ctypes as C
+	from gaussian_fluids_code_b200 import _lib
+	lib = _lib.lib()
+	P, S, R, V, mgs, gen = synthetic(n)
+	X = (torch.rand((Q, 3), generator=gen) * 1.3 - .15).cuda()	# some samples outside the domain / the padded grid
+	ref_vor = torch.randn((Q, 3), generator=gen).cuda() * .1
+	out = []
+	for force_radix in (1, 0):
+		assert lib.gsr_set_tuning(C.c_int(5), C.c_int(force_radix)) == 0
+		try:
+			o = make_fast3d(P, S, R, V, 5e-3, mgs)
+			e = o._engine
+			e.ensure_packed(o._params())
+			bins = e.bin_samples(X, True)
+			in_grid = int(bins.scs[-1].item())
+			val, grad = torch.empty((Q, 3), device='cuda'), torch.empty((Q, 3, 3), device='cuda')
+			e.forward(X, val, grad, False, perm=bins)
+			acc, mask = e.backward_gather(X, bins.perm, bins.scs, val, grad, (0., 0., 0., 1., 0., 1.), {'ref_vor': ref_vor}, None)
+			torch.cuda.synchronize()
+			out.append([e.cell_start.cpu().numpy().copy(), e.sorted_id.cpu().numpy().copy(), e.packed.cpu().numpy().copy(), bins.scs.cpu().numpy().copy(),
+						bins.perm[:in_grid].cpu().numpy().copy(), np.sort(bins.perm[in_grid:].cpu().numpy()), val.cpu().numpy().copy(), acc[1:].cpu().numpy().copy()])	# set 0 (direct) is not written by this call
+		finally:
+			lib.gsr_set_tuning(C.c_int(5), C.c_int(0))
+	for a, b in zip(*out):
+		np.testing.assert_array_equal(a, b)
