@@ -166,7 +166,9 @@ class HashEngine:
 			key = (x.data_ptr(), x._version, Q, tuple(self.dims))
 			gs_now = None if self.desc.grid_scale_dev else float(self.desc.grid_scale)
 			ent = self._bin_cache.get(key)
-			if ent is not None and ent['gs'] == gs_now and (gs_now is not None or ent['uses'] < self.BIN_CACHE_AGE):
+			# reuse while young; when both grid_scales are known on the host, also require them to be close (the ordering
+			# only matters for locality, see the docstring)
+			if ent is not None and ent['uses'] < self.BIN_CACHE_AGE and (gs_now is None or ent['gs'] is None or abs(ent['gs'] / gs_now - 1.) < .05):
 				ent['uses'] += 1
 				return ent['bins']
 		alloc = (lambda name, shape: torch.empty(shape, dtype=torch.int32, device=self.device)) if key else (lambda name, shape: self.scratch.typed(name + tag, shape, torch.int32))
