@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 		const int cx = cell_coord(p0.x, g.lo[0], gs), cy = cell_coord(p0.y, g.lo[1], gs), cz = cell_coord(p0.z, g.lo[2], gs);
 		const float tau = g.tau, q_thr = P.q_thr;
 		// one accepted-or-not visit of sorted sample k
-		auto visit = [&](int k) {
-			const float4 r0 = __ldg(rec + (size_t)STRIDE * k);
+		constexpr bool R1_EARLY = DIR_MODE == 1 && !HAS_VOR;	// tiny record: its second float4 is fetched with the first, not after the test
+		auto visit = [&](int k, const float4 r0, const float4 r1v) {
 			const float d[3] = {r0.x - p0.x, r0.y - p0.y, r0.z - p0.z};
 			const float w[3] = {Am[0] * d[0] + Am[1] * d[1] + Am[2] * d[2], Am[1] * d[0] + Am[3] * d[1] + Am[4] * d[2], Am[2] * d[0] + Am[4] * d[1] + Am[5] * d[2]};
 			const float q = d[0] * w[0] + d[1] * w[1] + d[2] * w[2];
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 					aX.G[5] += hk * (2.f * v[2] * d[2] - vw * dd[5]);
 				}
 				if (DIR_MODE == 1) {
-					const float4 r1 = __ldg(rec + (size_t)STRIDE * k + o);
+					const float4 r1 = HAS_VOR ? __ldg(rec + (size_t)STRIDE * k + o) : r1v;
 					const float a[3] = {r1.x, r1.y, r1.z};
 					pair_accum3_value(aD, a, v, w, dd, gg, gm);
 				}
@@ -359,18 +359,37 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 				s = __ldg(scs + base);
 				n = __ldg(scs + base + 3) - s;
 			}, pre, off, total);
-			for (int f = lane; f < total; f += LPG) {
-				int dlt = off[0];
+			// 4 visits per trip with all their record loads issued first: the kernel is bound by the latency of these loads
+			for (int f0 = lane; f0 < total; f0 += 4 * LPG) {
+				int kk[4];
+				bool ok[4];
+				float4 R0[4], R1[4];
 #pragma unroll
-				for (int r = 1; r < 9; r++) dlt = (f >= pre[r]) ? off[r] : dlt;
-				visit(f + dlt);
+				for (int b = 0; b < 4; b++) {
+					const int f = f0 + b * LPG;
+					ok[b] = f < total;
+					const int ff = ok[b] ? f : f0;	// a valid index to load from when this slot is past the end
+					int dlt = off[0];
+#pragma unroll
+					for (int r = 1; r < 9; r++) dlt = (ff >= pre[r]) ? off[r] : dlt;
+					kk[b] = ff + dlt;
+				}
+#pragma unroll
+				for (int b = 0; b < 4; b++) {
+					R0[b] = __ldg(rec + (size_t)STRIDE * kk[b]);
+					R1[b] = R1_EARLY ? __ldg(rec + (size_t)STRIDE * kk[b] + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+				}
+#pragma unroll
+				for (int b = 0; b < 4; b++)
+					if (ok[b]) visit(kk[b], R0[b], R1[b]);
 			}
 		} else {
 			for (int pi = cx; pi <= cx + 2; pi++) {
 				for (int pj = cy; pj <= cy + 2; pj++) {
 					const int base = (pi * g.pdims[1] + pj) * g.pdims[2] + cz;
 					const int s = __ldg(scs + base), e = __ldg(scs + base + 3);
-					for (int k = s + lane; k < e; k += LPG) visit(k);
+					for (int k = s + lane; k < e; k += LPG)
+						visit(k, __ldg(rec + (size_t)STRIDE * k), R1_EARLY ? __ldg(rec + (size_t)STRIDE * k + 1) : make_float4(0.f, 0.f, 0.f, 0.f));
 				}
 			}
 		}

@@ -101,28 +101,42 @@ __device__ __forceinline__ void eval_point3(const EvalParams &P, const int32_t *
 				n = __ldg(cell_start + base + zhi + 1) - s;
 			}
 		}, pre, off, total);
-		for (int f = lane; f < total; f += LANES) {
-			int d = off[0];
+		// two candidates per trip, all six record loads issued first (the shape is bound by the latency of these loads)
+		for (int f0 = lane; f0 < total; f0 += 2 * LANES) {
+			float4 Pa[2], Pb[2], Pc[2];
+			bool okc[2];
 #pragma unroll
-			for (int r = 1; r < 9; r++) d = (f >= pre[r]) ? off[r] : d;
-			const int t = f + d;
-			const float4 p0 = __ldg(packed + 3 * t), p1 = __ldg(packed + 3 * t + 1), p2 = __ldg(packed + 3 * t + 2);
-			const float dx = x - p0.x, dy = y - p0.y, dz = z - p0.z;
-			const float wx = p1.x * dx + p1.y * dy + p1.z * dz;
-			const float wy = p1.y * dx + p2.x * dy + p2.y * dz;
-			const float wz = p1.z * dx + p2.y * dy + p2.z * dz;
-			const float q = dx * wx + dy * wy + dz * wz;
-			if (q <= q_thr) {
-				const float gs_ = ex2_approx(q * kNegHalfLog2e);
-				const float gm = gs_ - tau;
-				u[0] = fmaf(p0.w, gm, u[0]);
-				u[1] = fmaf(p1.w, gm, u[1]);
-				u[2] = fmaf(p2.w, gm, u[2]);
-				if (NEED_GRAD) {
-					const float ax = -gs_ * wx, ay = -gs_ * wy, az = -gs_ * wz;
-					G[0] = fmaf(p0.w, ax, G[0]); G[1] = fmaf(p0.w, ay, G[1]); G[2] = fmaf(p0.w, az, G[2]);
-					G[3] = fmaf(p1.w, ax, G[3]); G[4] = fmaf(p1.w, ay, G[4]); G[5] = fmaf(p1.w, az, G[5]);
-					G[6] = fmaf(p2.w, ax, G[6]); G[7] = fmaf(p2.w, ay, G[7]); G[8] = fmaf(p2.w, az, G[8]);
+			for (int b = 0; b < 2; b++) {
+				const int f = f0 + b * LANES;
+				okc[b] = f < total;
+				const int ff = okc[b] ? f : f0;
+				int d = off[0];
+#pragma unroll
+				for (int r = 1; r < 9; r++) d = (ff >= pre[r]) ? off[r] : d;
+				const int t = ff + d;
+				Pa[b] = __ldg(packed + 3 * t); Pb[b] = __ldg(packed + 3 * t + 1); Pc[b] = __ldg(packed + 3 * t + 2);
+			}
+#pragma unroll
+			for (int b = 0; b < 2; b++) {
+				if (!okc[b]) continue;
+				const float4 p0 = Pa[b], p1 = Pb[b], p2 = Pc[b];
+				const float dx = x - p0.x, dy = y - p0.y, dz = z - p0.z;
+				const float wx = p1.x * dx + p1.y * dy + p1.z * dz;
+				const float wy = p1.y * dx + p2.x * dy + p2.y * dz;
+				const float wz = p1.z * dx + p2.y * dy + p2.z * dz;
+				const float q = dx * wx + dy * wy + dz * wz;
+				if (q <= q_thr) {
+					const float gs_ = ex2_approx(q * kNegHalfLog2e);
+					const float gm = gs_ - tau;
+					u[0] = fmaf(p0.w, gm, u[0]);
+					u[1] = fmaf(p1.w, gm, u[1]);
+					u[2] = fmaf(p2.w, gm, u[2]);
+					if (NEED_GRAD) {
+						const float ax = -gs_ * wx, ay = -gs_ * wy, az = -gs_ * wz;
+						G[0] = fmaf(p0.w, ax, G[0]); G[1] = fmaf(p0.w, ay, G[1]); G[2] = fmaf(p0.w, az, G[2]);
+						G[3] = fmaf(p1.w, ax, G[3]); G[4] = fmaf(p1.w, ay, G[4]); G[5] = fmaf(p1.w, az, G[5]);
+						G[6] = fmaf(p2.w, ax, G[6]); G[7] = fmaf(p2.w, ay, G[7]); G[8] = fmaf(p2.w, az, G[8]);
+					}
 				}
 			}
 		}
