@@ -57,43 +57,65 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t *__r
 	hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];	// digit-major
 }
 
-// exclusive scan of m entries by one block
-__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ a, int m)
+// Exclusive scan of the digit-major histogram hist[256][nblocks] (row-major order = the order of a stable counting sort):
+// CTA d scans row d in place and publishes the row total; the last CTA to finish turns the 256 totals into row bases.
+// The scatter kernel adds base[d] to its row-local offsets.  (A one-CTA scan of all 256 * nblocks entries took 0.44 ms at
+// 2 M keys — more than everything else in the pass.)
+__global__ void __launch_bounds__(256) rs_scan_kernel(uint32_t *__restrict__ hist, int nblocks, uint32_t *__restrict__ totals, uint32_t *__restrict__ base,
+						       unsigned int *__restrict__ done)
 {
-	__shared__ uint32_t warp_sums[32];
-	__shared__ uint32_t carry_s;
-	const int T = 1024;
-	int chunk = (m + T - 1) / T;
-	int b = threadIdx.x * chunk, e = min(b + chunk, m);
+	__shared__ uint32_t warp_sums[8];
+	__shared__ bool last;
+	const int d = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t *row = hist + (size_t)d * nblocks;
+	const int chunk = (nblocks + 255) / 256, b = threadIdx.x * chunk, e = min(b + chunk, nblocks);
 	uint32_t s = 0;
-	for (int i = b; i < e; i++) s += a[i];
-	// block exclusive scan of s
+	for (int i = b; i < e; i++) s += row[i];
 	uint32_t v = s;
-	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) {
-		uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+		const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
 		if (lane >= o) v += t;
 	}
 	if (lane == 31) warp_sums[w] = v;
-	if (threadIdx.x == 0) carry_s = 0;
 	__syncthreads();
-	if (w == 0) {
-		uint32_t ws = warp_sums[lane], t2 = ws;
+	uint32_t wbase = 0, total = 0;
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			uint32_t t = __shfl_up_sync(0xffffffffu, t2, o);
-			if (lane >= o) t2 += t;
-		}
-		warp_sums[lane] = t2 - ws;	// exclusive
+	for (int k = 0; k < 8; k++) {
+		if (k < w) wbase += warp_sums[k];
+		total += warp_sums[k];
 	}
-	__syncthreads();
-	uint32_t run = warp_sums[w] + (v - s);
+	uint32_t run = wbase + (v - s);
 	for (int i = b; i < e; i++) {
-		uint32_t t = a[i];
-		a[i] = run;
+		const uint32_t t = row[i];
+		row[i] = run;
 		run += t;
 	}
+	if (threadIdx.x == 0) {
+		totals[d] = total;
+		__threadfence();
+		last = atomicAdd(done, 1u) == 255u;
+	}
+	__syncthreads();
+	if (!last) return;
+	__threadfence();
+	// 256 totals -> exclusive bases, by this one CTA (thread t owns digit t)
+	const uint32_t mine = ((volatile uint32_t *)totals)[threadIdx.x];
+	uint32_t v2 = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, v2, o);
+		if (lane >= o) v2 += t;
+	}
+	__syncthreads();
+	if (lane == 31) warp_sums[w] = v2;
+	__syncthreads();
+	uint32_t wb = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++)
+		if (k < w) wb += warp_sums[k];
+	base[threadIdx.x] = wb + v2 - mine;
+	if (threadIdx.x == 0) *done = 0;	// re-arm for the next pass
 }
 
 // Stable in-warp ranking of one 32-key slice: lanes with equal digits get consecutive offsets in lane
@@ -115,13 +137,13 @@ __device__ __forceinline__ uint32_t warp_rank(uint32_t digit, bool valid, uint32
 
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
 								uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-								int n, int shift, const uint32_t *__restrict__ hist, int nblocks)
+								int n, int shift, const uint32_t *__restrict__ hist, int nblocks, const uint32_t *__restrict__ digit_base)
 {
 	__shared__ uint32_t cnt[RS_WARPS][256];
 	__shared__ uint32_t gbase[256];
 	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
-	gbase[threadIdx.x] = hist[threadIdx.x * nblocks + blockIdx.x];
+	gbase[threadIdx.x] = hist[(size_t)threadIdx.x * nblocks + blockIdx.x] + digit_base[threadIdx.x];
 	__syncthreads();
 	int base = blockIdx.x * RS_TILE + w * (32 * RS_ITEMS);
 	uint32_t key[RS_ITEMS], off[RS_ITEMS];
@@ -251,7 +273,7 @@ static size_t sort_ws_bytes(int64_t n, int64_t cells = 0)
 	int64_t nb = (n + RS_TILE - 1) / RS_TILE;
 	if (nb < 1) nb = 1;
 	// 4 arrays of n, the radix histograms, and one per-cell counter array (the counting-sort path)
-	return 4 * align256(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1)) + align256(sizeof(uint32_t) * 256 * (size_t)nb) + align256(sizeof(uint32_t) * (size_t)(cells + 2));
+	return 4 * align256(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1)) + align256(sizeof(uint32_t) * (256 * (size_t)nb + 1024)) + align256(sizeof(uint32_t) * (size_t)(cells + 2));
 }
 
 static bool carve_sort_ws(void *ws, size_t ws_bytes, int64_t n, SortWs &s)
@@ -266,7 +288,7 @@ static bool carve_sort_ws(void *ws, size_t ws_bytes, int64_t n, SortWs &s)
 	s.hist = (uint32_t *)p;
 	s.nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
 	if (s.nblocks < 1) s.nblocks = 1;
-	s.cells = (uint32_t *)(p + align256(sizeof(uint32_t) * 256 * (size_t)s.nblocks));
+	s.cells = (uint32_t *)(p + align256(sizeof(uint32_t) * (256 * (size_t)s.nblocks + 1024)));
 	s.cells_cap = (ws_bytes - (size_t)((char *)s.cells - (char *)ws)) / sizeof(uint32_t);
 	return true;
 }
@@ -287,9 +309,15 @@ static int radix_sort_index(SortWs &s, int n, uint32_t max_key, uint32_t *out_va
 		const uint32_t *kin = s.keys0, *vin = nullptr;
 		for (int p = 0; p < passes; p++) {
 			uint32_t *kout = (p & 1) ? s.kB : s.kA, *vout = (p & 1) ? vB : vA;
+			uint32_t *totals = s.hist + (size_t)256 * s.nblocks, *base = totals + 256;
+			unsigned int *done = base + 256;
+			if (p == 0) {
+				cudaError_t e = cudaMemsetAsync(done, 0, sizeof(unsigned int), st);
+				if (e != cudaSuccess) return (int)e;
+			}
 			rs_hist_kernel<<<s.nblocks, RS_THREADS, 0, st>>>(kin, n, 8 * p, s.hist, s.nblocks);
-			rs_scan_kernel<<<1, 1024, 0, st>>>(s.hist, 256 * s.nblocks);
-			rs_scatter_kernel<<<s.nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, 8 * p, s.hist, s.nblocks);
+			rs_scan_kernel<<<256, 256, 0, st>>>(s.hist, s.nblocks, totals, base, done);
+			rs_scatter_kernel<<<s.nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, 8 * p, s.hist, s.nblocks, base);
 			g_launches += 3;
 			GSR_CHECK_LAUNCH();
 			kin = kout;

@@ -177,3 +177,43 @@ def test_hash_paths_agree(n, Q):
 			lib.gsr_set_tuning(C.c_int(5), C.c_int(0))
 	for a, b in zip(*out):
 		np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize('n,Q', [(10, 600_000), (10, 2_097_152), (34, 2_097_152)])
+def test_radix_sort_full_size(n, Q):
+	"""the stable radix sort at the benchmark's batch sizes (more than 256 key blocks per digit row, which the small cases of
+	test_hash_paths_agree never reach): the sample order must equal a stable sort of keys recomputed here with the kernel's own
+	IEEE f32 formula (cell_coord of csrc/common.cuh, sample_key of csrc/hash_small.cuh), and the cell table the key histogram."""
+	import ctypes as C
+	from gaussian_fluids_code_b200 import _lib
+	lib = _lib.lib()
+	P, S, R, V, mgs, gen = synthetic(n)
+	X = (torch.rand((Q, 3), generator=gen) * 1.3 - .15).cuda()
+	assert lib.gsr_set_tuning(C.c_int(5), C.c_int(1)) == 0
+	try:
+		o = make_fast3d(P, S, R, V, 5e-3, mgs)
+		e = o._engine
+		e.ensure_packed(o._params())
+		bins = e.bin_samples(X, True)
+		torch.cuda.synchronize()
+	finally:
+		lib.gsr_set_tuning(C.c_int(5), C.c_int(0))
+	d = e.desc
+	dims = torch.tensor([d.dims[0], d.dims[1], d.dims[2]], device='cuda')
+	lo = torch.tensor([d.lo[0], d.lo[1], d.lo[2]], dtype=torch.float32, device='cuda')
+	gs = torch.tensor(d.grid_scale, dtype=torch.float32, device='cuda')
+	q = (X - lo) / gs
+	c = torch.floor(q).long()
+	ok = ((c >= -1) & (c <= dims)).all(dim=1)
+	pd = dims + 2
+	pcell = int(pd.prod().item())
+	key = torch.where(ok, ((c[:, 0] + 1) * pd[1] + (c[:, 1] + 1)) * pd[2] + (c[:, 2] + 1), torch.full_like(c[:, 0], pcell))
+	scs = bins.scs.long()
+	assert scs.numel() == pcell + 1
+	hist = torch.bincount(key, minlength=pcell + 1)
+	np.testing.assert_array_equal(scs.cpu().numpy(), (torch.cumsum(hist, 0) - hist)[:pcell + 1].cpu().numpy())
+	if bins.tiles is not None:	# fine keys: 2 more bits per axis order the samples inside a cell
+		sub = torch.clamp(((q - c.float()) * 4.).int(), 0, 3).long()
+		key = key * 64 + torch.where(ok, (sub[:, 0] * 4 + sub[:, 1]) * 4 + sub[:, 2], torch.zeros_like(key))
+	expect = torch.sort(key, stable=True).indices
+	np.testing.assert_array_equal(bins.perm.long().cpu().numpy(), expect.cpu().numpy())
