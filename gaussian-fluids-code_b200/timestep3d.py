@@ -129,6 +129,7 @@ class ShardedProjector(advance3d.FusedProjector):
 		self.acc, self.lp, self.lpb = self.views[0]	# set 0: boundary (direct), sets 1, 2: vorticity / divergence
 		self.nblk, self.nblkb = nblk, nblkb
 		self._streams = None
+		self._samplers = self._prep = None
 		if self.peer:
 			self.peer.new_phase()
 
@@ -142,21 +143,78 @@ class ShardedProjector(advance3d.FusedProjector):
 		cur._engine._packed_key = None
 		cur._engine.ensure_packed(cur._params())
 
-	def iterate(self, data, boundary=None, census=None, parity=0):
+	# ---- sample pipeline ------------------------------------------------------------------------------------------------
+	# Generating and binning the samples of iteration k+1 needs only the iteration counter and the grid_scale that step k
+	# leaves in the device state — not the updated Gaussians.  So it is forked right after the step kernels and runs beside
+	# the Gaussian hash + pack instead of in front of the next forward pass (the boundary batch's hash was 17 us of a 78 us
+	# critical path).  Same kernels on the same inputs as the unpipelined order: results are bitwise unchanged.
+	def set_samplers(self, data_fn, boundary_fn=None):
+		"""data_fn() -> (Q,3) samples, boundary_fn() -> ((Qb,3) points, (Qb,3) normals); both must write persistent tensors"""
+		self._samplers = (data_fn, boundary_fn)
+		self._prep = None
+
+	def _side_streams(self, census):
+		if self._streams is None:
+			self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+		main = torch.cuda.current_stream()
+		return (main,) + (self._streams if census is None else (main, main))	# the census pass shares one counter: keep it serial
+
+	def _prepare(self, census=None):
+		"""fork: samples + sample hash of the next iteration on the two side streams (not joined: see _join_prepared)"""
+		e = self.gv._engine
+		main, s_fwd, s_bnd = self._side_streams(census)
+		data_fn, boundary_fn = self._samplers
+		fork = torch.cuda.Event()
+		fork.record(main)
+		prep = {'boundary': None, 'ev': []}
+		if boundary_fn is not None:
+			s_bnd.wait_event(fork)
+			with torch.cuda.stream(s_bnd):
+				prep['boundary'] = boundary_fn()
+				prep['bins_b'] = e.bin_samples(prep['boundary'][0], True, tag='pb')
+				ev = torch.cuda.Event()
+				ev.record(s_bnd)
+				prep['ev'].append(ev)
+		s_fwd.wait_event(fork)
+		with torch.cuda.stream(s_fwd):
+			prep['data'] = data_fn()
+			prep['bins'] = e.bin_samples(prep['data'], True, tag='pt')
+			ev = torch.cuda.Event()
+			ev.record(s_fwd)
+			prep['ev'].append(ev)
+		self._prep = prep
+
+	def _join_prepared(self):
+		main = torch.cuda.current_stream()
+		for ev in self._prep['ev']:
+			main.wait_event(ev)
+		self._prep['ev'] = []
+
+	def prime(self, census=None):
+		"""prologue of a pipelined phase: prepare the samples of its first iteration"""
+		self._prepare(census)
+		self._join_prepared()
+
+	def iterate(self, data=None, boundary=None, census=None, parity=0):
 		"""
 		One optimiser iteration.  Three independent chains run on three streams (fork / join by events, so a captured graph
 		keeps the concurrency): the RK4 pull-back reference (previous field), the forward pass of the current field, and the
 		whole boundary pass; they meet at the adjoint kernel and at the all-reduce.
+		data=None: pipelined — use the samples prepared by prime() / the previous iteration and prepare the next ones.
 		"""
 		gv, e = self.gv, self.gv._engine
 		cur = self.ref.velocity_field
+		pipelined = data is None
+		prep = None
+		if pipelined:
+			prep = self._prep
+			if prep is None or prep['ev']:
+				raise _lib.GsrError('pipelined iterate() needs set_samplers() + prime() first')
+			data, boundary = prep['data'], prep['boundary']
 		Q, Qg = data.shape[0], data.shape[0] * self.world
 		acc_w, lp_w, lpb_w = self.views[parity if self.peer else 0]
 		acc_r, lp_r, lpb_r = self.reduced
-		main = torch.cuda.current_stream()
-		if self._streams is None:
-			self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
-		s_fwd, s_bnd = self._streams if census is None else (main, main)	# the census pass shares one counter: keep it serial
+		main, s_fwd, s_bnd = self._side_streams(census)
 		fork = torch.cuda.Event()
 		fork.record(main)
 		mask_b = 0
@@ -166,7 +224,7 @@ class ShardedProjector(advance3d.FusedProjector):
 			with torch.cuda.stream(s_bnd):
 				bdata, bnormal = boundary
 				Qb, Qbg = bdata.shape[0], bdata.shape[0] * self.world
-				bins_b = e.bin_samples(bdata, True, tag='b')
+				bins_b = prep['bins_b'] if pipelined else e.bin_samples(bdata, True, tag='b')
 				perm_b, scs_b = bins_b
 				valb = self._tmp('valb', (Qb, 3))
 				e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
@@ -177,7 +235,7 @@ class ShardedProjector(advance3d.FusedProjector):
 					e.count_pairs(bdata, census.c, 2, True)
 				done_b = torch.cuda.Event()
 				done_b.record(s_bnd)
-		bins = e.bin_samples(data, True)
+		bins = prep['bins'] if pipelined else e.bin_samples(data, True)
 		perm, scs = bins
 		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
 		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
@@ -204,7 +262,14 @@ class ShardedProjector(advance3d.FusedProjector):
 			self.peer.sum(parity, self.stepper.state[:1])	# one kernel: handshake + sum of all ranks' buffers over NVLink
 		elif self.world > 1:
 			torch.distributed.all_reduce(self.flat)
-		self.stepper.step([p.detach() for p in gv._params()], acc_r, mask, loss_srcs=srcs, rebuild=True)	# update + hash + packed records
+		params = [p.detach() for p in gv._params()]
+		if not pipelined:
+			self.stepper.step(params, acc_r, mask, loss_srcs=srcs, rebuild=True)	# update + hash + packed records
+			return
+		self.stepper.step(params, acc_r, mask, loss_srcs=srcs)	# update; leaves iteration counter and grid_scale of the next iteration
+		self._prepare(census)	# side streams: next samples + their hash ...
+		self._rebuild()	# ... beside the Gaussian hash + packed records on this one
+		self._join_prepared()
 
 
 class LeapfrogTimestep:
@@ -271,17 +336,23 @@ class LeapfrogTimestep:
 		# project, fixed iteration count; the iteration is captured once per orientation into a CUDA graph and replayed
 		ent = self._projector(new, cur)
 		fp = ent['fp']
-		one = lambda parity, cen=None: fp.iterate(self._samples(fp), self._boundary(fp) if self.boundary_lambda else None, cen, parity=parity)
-		unit = 2 if fp.peer else 1	# the peer-memory exchange alternates between two buffers: a graph holds one iteration of each parity
-		if self.iters % unit or self.check_iter % unit:
-			raise ValueError('iters and check_iter must be even with the peer-memory exchange')
-		body = lambda: [one(k) for k in range(unit)]
+		fp.set_samplers(lambda: self._samples(fp), (lambda: self._boundary(fp)) if self.boundary_lambda else None)
+		fp.prime(census)
+		one = lambda parity, cen=None: fp.iterate(None, None, cen, parity=parity)
+		# iterations per captured graph: a replay costs ~5 us of launch overhead (tools/graph_probe.py), so several iterations share
+		# one; the peer-memory exchange alternates between two buffers, so a graph then holds whole pairs of iterations
+		unit = int(os.environ.get('GSR_GRAPH_UNIT', '0'))
+		if unit <= 0:
+			unit = next(u for u in (10, 4, 2, 1) if self.iters % u == 0 and self.check_iter % u == 0 and not (fp.peer and u % 2))
+		if (fp.peer and unit % 2) or self.iters % unit or self.check_iter % unit:
+			raise ValueError('iters and check_iter must be multiples of the iterations per graph (even with the peer-memory exchange)')
+		body = lambda: [one(k & 1) for k in range(unit)]
 		done = 0
 		if self.use_graph and census is None and ent['graph'] is None:
 			side = torch.cuda.Stream()
 			side.wait_stream(torch.cuda.current_stream())
 			with torch.cuda.stream(side):
-				for _ in range(2 // unit):	# eager warm-up iterations (they count): sizes every scratch buffer
+				for _ in range(max(1, 2 // unit)):	# eager warm-up iterations (they count): sizes every scratch buffer
 					l0 = new._engine.lib.gsr_launch_count()
 					body()
 					ent['per_iter'] = new._engine.lib.gsr_launch_count() - l0
@@ -298,7 +369,7 @@ class LeapfrogTimestep:
 				self.graph_launches += ent['per_iter']	# kernels of this library inside one replay
 			else:
 				for k in range(unit):
-					one(k, census)
+					one(k & 1, census)
 			done += unit
 			if done % self.check_iter == 0:
 				self.last_test = fp.evaluate(self.lattice, probe=getattr(self, 'probe', None))

@@ -148,9 +148,10 @@ def test_against_oracle_seeded(n, Q):
 			assert rel_err(a, b) < 5e-4, (tag, nm, rel_err(a, b))
 
 
-@pytest.mark.parametrize('n,Q', [(10, 3000), (20, 12000), (30, 40000), (34, 70000)])
+@pytest.mark.parametrize('n,Q', [(10, 3000), (20, 12000), (30, 40000), (34, 70000), (10, 8192), (10, 16384), (12, 33), (10, 1025)])
 def test_hash_paths_agree(n, Q):
-	"""the single-launch hash (n <= 16384), the counting sort (larger, uncrowded cells) and the stable radix sort must produce the
+	"""the single-launch hash (n <= 16384), the single-CTA stable counting sort of small sample batches (Q <= 16384 on <= 3200
+	padded cells, crowded or not), the counting sort (larger, uncrowded cells) and the stable radix sort must produce the
 	same cell tables, the same canonical Gaussian order and the same sample order; outputs downstream are then bit-identical"""
 	import ctypes as C
 	from gaussian_fluids_code_b200 import _lib
