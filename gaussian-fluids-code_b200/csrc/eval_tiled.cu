@@ -282,6 +282,7 @@ static int64_t tile_slots(const Grid &g, int64_t Q)
 }
 
 extern int g_force_radix;	// grid.cu
+extern int g_step_small_n;	// step.cu
 
 // tunables (gsr_set_tuning)
 int g_tiled_min_q = 1 << 17;
@@ -332,6 +333,7 @@ extern "C" int gsr_set_tuning(int key, int value)
 	case GSR_TUNE_TILED_MIN_Q: g_tiled_min_q = value; return GSR_OK;
 	case GSR_TUNE_RK4_SMEM_STATE: g_rk4_smem_state = value; return GSR_OK;
 	case GSR_TUNE_FORCE_RADIX: g_force_radix = value; return GSR_OK;
+	case GSR_TUNE_STEP_SMALL_N: g_step_small_n = value; return GSR_OK;
 	case GSR_TUNE_FW_P4_MIN_SPC: g_fw_p4_min_spc = value; return GSR_OK;
 	case GSR_TUNE_TILED_CAP:
 		if (value < 0 || tiled_smem(value) > 200 * 1024) return GSR_EINVAL;

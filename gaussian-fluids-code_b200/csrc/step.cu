@@ -8,8 +8,11 @@
 // 48 B/set (twice: kernels A and B), writes params 52 B + m,v 104 B.
 #include "chain.cuh"
 #include <math.h>
+#include <cooperative_groups.h>
 
 namespace gsr {
+
+int g_step_small_n = 2048;	// GSR_TUNE_STEP_SMALL_N: up to this many Gaussians gsr_step is ONE cluster launch (else four launches)
 
 template <int D> struct Dim {
 	static constexpr int P = (D == 3) ? 13 : 7;	// parameter floats per Gaussian
@@ -330,6 +333,247 @@ __global__ void stepS_kernel(gsr_step_cfg cfg, float *st, float *min_out)
 	step_grid_scale(cfg, st, min_s);
 }
 
+// ---- small N (the reference's own sizes): the whole step as ONE launch of ONE 8-CTA cluster ---------------------------------
+// The four-launch form is a chain of dependent memory round trips at these sizes (ncu: long-scoreboard stalls, 18 us inside the
+// captured iteration for 1000 Gaussians): kernel boundaries, the re-read of parameters and accumulators by kernel B, Adam
+// moments loaded one by one between stores through the same pointer.  Here every Gaussian's record is loaded once, up front;
+// the parameter-space gradients of both loss sets are formed once and stay in registers; the two grid-wide steps (PCGrad dots /
+// regulariser moments, and min(s)) are cluster barriers with the per-CTA partials read through distributed shared memory; the
+// reduction tail (PCGrad coefficients, scheduler, bias corrections) runs redundantly in every CTA on a shared-memory copy of
+// the state scalars, which CTA 0 writes back.
+constexpr int SC_CTAS = 8;
+constexpr int SC_MAX_THREADS = 256;
+constexpr int SC_MAX_N = SC_CTAS * SC_MAX_THREADS;
+
+template <int D>
+__global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_MAX_THREADS, 1)
+step_cluster_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__restrict__ scal, float *__restrict__ rot, float *__restrict__ vals,
+		    const float *__restrict__ acc, int sets_mask, const float *__restrict__ ex0, const float *__restrict__ ex1,
+		    const float *__restrict__ pos_org, LossSrcs ls, float *st)
+{
+	namespace cg = cooperative_groups;
+	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR, P = Dim<D>::P;
+	cg::cluster_group cluster = cg::this_cluster();
+	__shared__ float cst[GSR_STATE_SCALARS];	// the state scalars: read once, advanced by the tail, written back by CTA 0
+	__shared__ float wpart[SC_MAX_THREADS / 32][S_COUNT];
+	__shared__ float part[S_COUNT];	// this CTA's partial sums (read by every CTA of the cluster)
+	__shared__ double Tsm[S_COUNT + 8];
+	__shared__ float wmin[SC_MAX_THREADS / 32];
+	__shared__ float bmin;	// this CTA's min over the new scalings (read by CTA 0)
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+	const int rank = (int)cluster.block_rank();
+	const int i = rank * blockDim.x + tid;
+	const bool on = i < N;
+	// ---- every load of the step, issued together --------------------------------------------------------------------------
+	for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x) cst[k] = st[k];
+	float sc[D], r[NR], p[D], v[D], po[D], mo[P], vo[P], a0[AF], a1[AF], a2[AF], b0[AF], b1[AF];
+	float *m = st + GSR_STATE_SCALARS + (size_t)i * P, *vv = st + GSR_STATE_SCALARS + (size_t)N * P + (size_t)i * P;
+	if (on) {
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			sc[k] = scal[(size_t)D * i + k]; p[k] = pos[(size_t)D * i + k]; v[k] = vals[(size_t)D * i + k];
+			po[k] = pos_org ? pos_org[(size_t)D * i + k] : 0.f;
+		}
+#pragma unroll
+		for (int k = 0; k < NR; k++) r[k] = rot[(size_t)NR * i + k];
+#pragma unroll
+		for (int k = 0; k < P; k++) { mo[k] = m[k]; vo[k] = vv[k]; }
+#pragma unroll
+		for (int k = 0; k < AF; k++) {
+			a0[k] = (sets_mask & 1) ? acc[(size_t)i * AF + k] : 0.f;
+			a1[k] = (sets_mask & 2) ? acc[((size_t)1 * N + i) * AF + k] : 0.f;
+			a2[k] = (sets_mask & 4) ? acc[((size_t)2 * N + i) * AF + k] : 0.f;
+			b0[k] = ex0 ? ex0[(size_t)i * AF + k] : 0.f;
+			b1[k] = ex1 ? ex1[(size_t)i * AF + k] : 0.f;
+		}
+	}
+	if (tid >= S_COUNT && tid < S_COUNT + 8) {	// weighted sums of the sample-loss partials (blocks in order, double)
+		const int k = tid - S_COUNT;
+		double s = 0.;
+		for (int src = 0; src < ls.n; src++) {
+			double t = 0.;
+			for (int b = 0; b < ls.nblocks[src]; b++) t += (double)ls.partials[src][(size_t)b * 8 + k];
+			s += (double)ls.w[src][k] * t;
+		}
+		Tsm[tid] = s;
+	}
+	// ---- parameter-space gradients [pos D][scal D][rot NR][val D] of the sets, once -------------------------------------------
+	float g1[P], g2[P], gd[P];	// vorticity set, divergence set, direct sets (boundary / value / gradient losses)
+	float S[S_COUNT];
+#pragma unroll
+	for (int k = 0; k < S_COUNT; k++) S[k] = 0.f;
+	float ssum = 0.f;
+	int kmin = 0, kmax = 0;
+	if (on) {
+		auto to_param = [&](const float *a, float *g) {
+			float gp[D], gs[D], gr[NR], gv[D];
+			param_grad<D>(a, sc, r, gp, gs, gr, gv);
+#pragma unroll
+			for (int k = 0; k < D; k++) { g[k] = gp[k]; g[D + k] = gs[k]; g[2 * D + NR + k] = gv[k]; }
+#pragma unroll
+			for (int k = 0; k < NR; k++) g[2 * D + k] = gr[k];
+		};
+#pragma unroll
+		for (int k = 0; k < P; k++) g1[k] = g2[k] = gd[k] = 0.f;
+		if (sets_mask & 2) to_param(a1, g1);
+		if (sets_mask & 4) to_param(a2, g2);
+		float t[P];
+		if (sets_mask & 1) {
+			to_param(a0, t);
+#pragma unroll
+			for (int k = 0; k < P; k++) gd[k] += t[k];
+		}
+		if (ex0) {
+			to_param(b0, t);
+#pragma unroll
+			for (int k = 0; k < P; k++) gd[k] += t[k];
+		}
+		if (ex1) {
+			to_param(b1, t);
+#pragma unroll
+			for (int k = 0; k < P; k++) gd[k] += t[k];
+		}
+		if ((sets_mask & 6) == 6) {
+#pragma unroll
+			for (int k = 0; k < P; k++) {
+				const int grp = k < D ? 0 : (k < 2 * D ? 1 : (k < 2 * D + NR ? 2 : 3));
+				S[S_DOT + grp] += g1[k] * g2[k]; S[S_N1 + grp] += g1[k] * g1[k]; S[S_N2 + grp] += g2[k] * g2[k];
+			}
+		}
+		// regulariser moments (3D/advance.py:237-242): V = exp(-sum s), rho = exp(max s - min s)
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			ssum += sc[k];
+			if (sc[k] < sc[kmin]) kmin = k;	// first index on ties, like torch.min / torch.max
+			if (sc[k] > sc[kmax]) kmax = k;
+		}
+	}
+	float smin_k = 0.f, smax_k = 0.f;
+#pragma unroll
+	for (int k = 0; k < D; k++) { if (k == kmin) smin_k = on ? sc[k] : 0.f; if (k == kmax) smax_k = on ? sc[k] : 0.f; }
+	const float V = expf(-ssum), rho = expf(smax_k - smin_k);
+	if (on) {
+		S[S_V] += V;
+		S[S_V2] += V * V;
+		S[S_ANISO] += (rho >= cfg.aniso_ratio ? rho : cfg.aniso_ratio) - cfg.aniso_ratio;
+#pragma unroll
+		for (int k = 0; k < D; k++) S[S_ABSV] += fabsf(v[k]);
+		if (pos_org) {
+#pragma unroll
+			for (int k = 0; k < D; k++) { const float dlt = p[k] - po[k]; S[S_DPOS] += dlt * dlt; }
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < S_COUNT; k++) {
+#pragma unroll
+		for (int o = 16; o; o >>= 1) S[k] += __shfl_xor_sync(0xffffffffu, S[k], o);
+	}
+	if (lane == 0) {
+#pragma unroll
+		for (int k = 0; k < S_COUNT; k++) wpart[w][k] = S[k];
+	}
+	__syncthreads();
+	if (tid < S_COUNT) {
+		float s = 0.f;
+		for (int ww = 0; ww < nw; ww++) s += wpart[ww][tid];
+		part[tid] = s;
+	}
+	cluster.sync();
+	if (tid < S_COUNT) {	// CTAs in order, double: the same T in every CTA
+		double s = 0.;
+#pragma unroll
+		for (int q = 0; q < SC_CTAS; q++) s += (double)*cluster.map_shared_rank(&part[tid], q);
+		Tsm[tid] = s;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		double T[S_COUNT + 8];
+#pragma unroll
+		for (int k = 0; k < S_COUNT + 8; k++) T[k] = Tsm[k];
+		step_reduce_tail<D>(cfg, N, T, cst);
+	}
+	__syncthreads();
+	// ---- projected gradient + regulariser gradients + Adam (step_update_one, on the registers loaded above) -------------------
+	float smin = __int_as_float(0x7f800000);
+	if (on) {
+		float g[P];
+#pragma unroll
+		for (int k = 0; k < P; k++) {
+			const int grp = k < D ? 0 : (k < 2 * D ? 1 : (k < 2 * D + NR ? 2 : 3));
+			float t = 0.f;
+			if (sets_mask & 2) t += cst[C_A1 + grp] * g1[k];
+			if (sets_mask & 4) t += cst[C_A2 + grp] * g2[k];
+			g[k] = t + gd[k];
+		}
+		if (rho >= cfg.aniso_ratio && kmin != kmax) {
+			const float c = cfg.w_aniso * rho / (float)N;
+#pragma unroll
+			for (int k = 0; k < D; k++) g[D + k] += (k == kmax ? c : 0.f) - (k == kmin ? c : 0.f);
+		}
+		const float rV = V / cst[C_MEANV];
+		const float cv = -cfg.w_vol * 2.f / (float)N * rV * (rV - cst[C_MEANR2]);
+#pragma unroll
+		for (int k = 0; k < D; k++) g[D + k] += cv;
+		if (cfg.w_valreg != 0.f) {
+			const float c = cfg.w_valreg / (float)(N * D);
+#pragma unroll
+			for (int k = 0; k < D; k++) g[2 * D + NR + k] += c * (float)((v[k] > 0.f) - (v[k] < 0.f));
+		}
+		if (pos_org && cfg.w_dpos != 0.f) {
+			const float c = cfg.w_dpos * 2.f / (float)(N * D);
+#pragma unroll
+			for (int k = 0; k < D; k++) g[k] += c * (p[k] - po[k]);
+		}
+		float prm[P];
+#pragma unroll
+		for (int k = 0; k < D; k++) { prm[k] = p[k]; prm[D + k] = sc[k]; prm[2 * D + NR + k] = v[k]; }
+#pragma unroll
+		for (int k = 0; k < NR; k++) prm[2 * D + k] = r[k];
+		const float bc2 = cst[C_BC2];
+#pragma unroll
+		for (int k = 0; k < P; k++) {
+			const int grp = k < D ? 0 : (k < 2 * D ? 1 : (k < 2 * D + NR ? 2 : 3));
+			const float mk = mo[k] + (g[k] - mo[k]) * (1.f - cfg.beta1);
+			const float vk = vo[k] * cfg.beta2 + (1.f - cfg.beta2) * g[k] * g[k];
+			mo[k] = mk;
+			vo[k] = vk;
+			prm[k] -= cst[C_STEP + grp] * (mk / (sqrtf(vk) * bc2 + cfg.eps));
+		}
+#pragma unroll
+		for (int k = 0; k < P; k++) { m[k] = mo[k]; vv[k] = vo[k]; }
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			pos[(size_t)D * i + k] = prm[k];
+			scal[(size_t)D * i + k] = prm[D + k];
+			vals[(size_t)D * i + k] = prm[2 * D + NR + k];
+			smin = fminf(smin, prm[D + k]);
+		}
+#pragma unroll
+		for (int k = 0; k < NR; k++) rot[(size_t)NR * i + k] = prm[2 * D + k];
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+	if (lane == 0) wmin[w] = smin;
+	__syncthreads();
+	if (tid == 0) {
+		float mn = wmin[0];
+		for (int ww = 1; ww < nw; ww++) mn = fminf(mn, wmin[ww]);
+		bmin = mn;
+	}
+	cluster.sync();
+	if (rank == 0) {
+		for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x)
+			if (k != GSR_ST_GRID_SCALE && k != GSR_ST_MIN_S) st[k] = cst[k];
+		if (tid == 0) {
+			float mn = fminf(bmin, cst[GSR_ST_MIN_S]);
+#pragma unroll
+			for (int q = 1; q < SC_CTAS; q++) mn = fminf(mn, *cluster.map_shared_rank(&bmin, q));
+			step_grid_scale(cfg, st, mn);
+		}
+	}
+	cluster.sync();	// no CTA leaves while CTA 0 may still read its shared memory
+}
+
 __global__ void init_state_kernel(float *st, size_t n_moments, gsr_step_cfg cfg)
 {
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,17 +650,24 @@ static int step_impl(const gsr_step_cfg *cfg, int64_t N, float *positions, float
 		for (int k = 0; k < 8; k++) ls.w[s][k] = (s < n_loss_src) ? loss_src[s].w[k] : 0.f;
 	}
 	const float *ex0 = extra_direct ? extra_direct[0] : nullptr, *ex1 = extra_direct ? extra_direct[1] : nullptr;
-	if (cfg->D == 3) {
-		stepA_kernel<3><<<nblk, ST_THREADS, 0, st>>>(n, positions, scalings, rotations, values, acc, sets_mask, positions_org, cfg->aniso_ratio, partials);
-		stepR_kernel<3><<<1, 256, 0, st>>>(*cfg, n, nblk, partials, ls, state);
-		stepB_kernel<3><<<nblk, ST_THREADS, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, state);
+	if (N <= g_step_small_n && N <= SC_MAX_N) {
+		const int bt = (((n + SC_CTAS - 1) / SC_CTAS) + 31) & ~31;
+		if (cfg->D == 3) step_cluster_kernel<3><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state);
+		else step_cluster_kernel<2><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state);
+		g_launches += 1;
 	} else {
-		stepA_kernel<2><<<nblk, ST_THREADS, 0, st>>>(n, positions, scalings, rotations, values, acc, sets_mask, positions_org, cfg->aniso_ratio, partials);
-		stepR_kernel<2><<<1, 256, 0, st>>>(*cfg, n, nblk, partials, ls, state);
-		stepB_kernel<2><<<nblk, ST_THREADS, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, state);
+		if (cfg->D == 3) {
+			stepA_kernel<3><<<nblk, ST_THREADS, 0, st>>>(n, positions, scalings, rotations, values, acc, sets_mask, positions_org, cfg->aniso_ratio, partials);
+			stepR_kernel<3><<<1, 256, 0, st>>>(*cfg, n, nblk, partials, ls, state);
+			stepB_kernel<3><<<nblk, ST_THREADS, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, state);
+		} else {
+			stepA_kernel<2><<<nblk, ST_THREADS, 0, st>>>(n, positions, scalings, rotations, values, acc, sets_mask, positions_org, cfg->aniso_ratio, partials);
+			stepR_kernel<2><<<1, 256, 0, st>>>(*cfg, n, nblk, partials, ls, state);
+			stepB_kernel<2><<<nblk, ST_THREADS, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, state);
+		}
+		stepS_kernel<<<1, 1, 0, st>>>(*cfg, state, nullptr);
+		g_launches += 4;
 	}
-	stepS_kernel<<<1, 1, 0, st>>>(*cfg, state, nullptr);
-	g_launches += 4;
 	GSR_CHECK_LAUNCH();
 	if (gd) return gsr_build_grid(gd, positions, N, cell_start, sorted_id, nullptr, nullptr, scalings, rotations, values, packed, cull, hash_ws, hash_ws_bytes, stream);
 	return GSR_OK;

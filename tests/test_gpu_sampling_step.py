@@ -105,6 +105,44 @@ def test_step_rebuild_equals_step_then_build():
 		np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize('n', [4, 8, 12])
+def test_step_cluster_launch_equals_four_launch(n):
+	"""gsr_step for small N (one launch of one 8-CTA cluster: partial sums and min(s) through distributed shared memory) against
+	the four-launch form used for large N: same formulas, only the grouping of the float block sums differs.  Three consecutive
+	steps, so that the Adam moments, the scheduler state and the re-armed min accumulator carry over."""
+	import ctypes as C
+	from gaussian_fluids_code_b200 import _lib
+	from gaussian_fluids_code_b200.engine import FusedStepper
+	lib = _lib.lib()
+	res = []
+	for small_n in (2048, 0):
+		assert lib.gsr_set_tuning(C.c_int(6), C.c_int(small_n)) == 0
+		try:
+			o, gen = engine_field(n)
+			e = o._engine
+			x = torch.rand((o.N, 3), generator=torch.Generator().manual_seed(3)).cuda()
+			ref_vor = torch.randn((o.N, 3), generator=torch.Generator().manual_seed(4)).cuda() * .1
+			st = FusedStepper(e, [3e-4, 1e-5, 3e-4, 1e-5], 50, 10., 10., tau=o.clamp_threshold, min_grid_scale=o.min_grid_scale, ext_bounds=o._ext())
+			st.init(o.scalings)
+			params = [p.detach() for p in o._params()]
+			for _ in range(3):
+				e.build(o.positions.detach(), params=params)
+				bins = e.bin_samples(x, True)
+				val, grad = torch.empty((o.N, 3), device='cuda'), torch.empty((o.N, 3, 3), device='cuda')
+				e.forward(x, val, grad, False, perm=bins)
+				acc, mask = e.backward_gather(x, bins.perm, bins.scs, val, grad, (0., 0., 0., 1., 0., 1.), {'ref_vor': ref_vor}, None, want_losses=True)
+				lp, nblk = e.last_loss_partials
+				st.step(params, acc, mask, loss_srcs=[(lp, nblk, [1. / o.N, 0., 1. / o.N, 0., 0., 0., 0., 0.])])
+			torch.cuda.synchronize()
+			res.append([p.cpu().numpy().copy() for p in params] + [np.array(st.scalars()[:14])])
+		finally:
+			lib.gsr_set_tuning(C.c_int(6), C.c_int(2048))
+	for a, b in zip(res[0][:-1], res[1][:-1]):	# block partials are float sums over 32 or 128 Gaussians: ~1e-7 relative in the coefficients
+		np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-8)
+	np.testing.assert_allclose(res[0][-1], res[1][-1], rtol=1e-4, atol=1e-7)
+	assert res[0][-1][0] == 3.	# three Adam steps counted
+
+
 def test_xrank_sum_single_rank():
 	"""gsr_xrank_sum with world = 1 (a single GPU cannot host kernels that wait for one another): the handshake with itself, the
 	epoch arithmetic over two parities, and the copy-out.  The 2-rank behaviour is checked by tools/exchange_check.py under torchrun
