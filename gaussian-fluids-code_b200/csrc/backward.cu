@@ -249,6 +249,7 @@ __device__ __forceinline__ void pair_accum3(Acc12 &acc, const float a[3], const 
 }
 
 constexpr int GA_THREADS = 128;
+int g_gather_cta_max_n = 4096;	// GSR_TUNE_GATHER_CTA_MAX_N
 
 template <int LPG>
 __device__ __forceinline__ void acc12_reduce(Acc12 &a)
@@ -350,11 +351,11 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 				}
 			}
 		};
-		if (LPG == 32) {
-			// a warp (or 8 lanes) on one Gaussian: the 9 sample runs are looked up by the lanes at once, concatenated by a scan
+		if (LPG >= 32) {
+			// a warp (or a whole CTA of 4 warps, each doing the lookup for itself) on one Gaussian: the 9 sample runs are looked up by the lanes at once, concatenated by a scan
 			// inside the lane group, and the lanes stride through the flat list (one round trip instead of nine dependent ones)
 			int pre[9], off[9], total;
-			flat_runs3<(LPG >= 8 ? LPG : 8)>(lane, true, [&](int r, int &s, int &n) {
+			flat_runs3<(LPG >= 32 ? 32 : 8)>(lane & 31, true, [&](int r, int &s, int &n) {
 				const int base = ((cx + r / 3) * g.pdims[1] + (cy + r % 3)) * g.pdims[2] + cz;
 				s = __ldg(scs + base);
 				n = __ldg(scs + base + 3) - s;
@@ -394,6 +395,34 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 			}
 		}
 	}
+	const Acc12 *sets[3] = {&aD, &aV, &aX};
+	const bool has[3] = {HAS_DIR, HAS_VOR, HAS_DIV};
+	if (LPG == 128) {	// one CTA per Gaussian (many samples per Gaussian, few Gaussians): warp sums, then the 4 warps in order
+		__shared__ float red[3][GA_THREADS / 32][12];
+		if (HAS_DIR) acc12_reduce<32>(aD);
+		if (HAS_VOR) acc12_reduce<32>(aV);
+		if (HAS_DIV) acc12_reduce<32>(aX);
+		if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+			for (int s = 0; s < 3; s++) {
+				if (!has[s]) continue;
+				float *o = red[s][threadIdx.x >> 5];
+#pragma unroll
+				for (int k = 0; k < 3; k++) { o[k] = sets[s]->dv[k]; o[3 + k] = sets[s]->dm[k]; }
+#pragma unroll
+				for (int k = 0; k < 6; k++) o[6 + k] = sets[s]->G[k];
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x < 36 && has[threadIdx.x / 12]) {
+			const int s = threadIdx.x / 12, k = threadIdx.x % 12;
+			float t = 0.f;
+#pragma unroll
+			for (int ww = 0; ww < GA_THREADS / 32; ww++) t += red[s][ww][k];
+			acc_out[((size_t)s * N + id) * 12 + k] = t;
+		}
+		return;
+	}
 	if (LPG > 1) {
 		if (HAS_DIR) acc12_reduce<LPG>(aD);
 		if (HAS_VOR) acc12_reduce<LPG>(aV);
@@ -401,8 +430,6 @@ __global__ void __launch_bounds__(GA_THREADS) gather3d_kernel(EvalParams P, cons
 		if (!valid || lane != 0) return;
 	}
 	// original-id order, set-major
-	const Acc12 *sets[3] = {&aD, &aV, &aX};
-	const bool has[3] = {HAS_DIR, HAS_VOR, HAS_DIV};
 #pragma unroll
 	for (int s = 0; s < 3; s++) {
 		if (!has[s]) continue;
@@ -681,6 +708,7 @@ extern "C" int gsr_backward_gather(const gsr_grid_desc *d, const int32_t *cell_s
 	// lanes per Gaussian: by the amount of parallelism N offers, and more when there are many samples per Gaussian
 	int lpg = pick_lanes(N);
 	if (lpg == 1 && Q >= 8 * N) lpg = 8;
+	if (D == 3 && N <= g_gather_cta_max_n && Q >= 4 * N) lpg = 128;	// few Gaussians, many samples each (the boundary batch): a CTA per Gaussian
 	int blocks = (int)((N * lpg + GA_THREADS - 1) / GA_THREADS);
 	g_launches += Q > 0 ? 2 : 1;
 	const int dirmode = !dir ? 0 : (cfg->w_grad != 0.f ? 2 : 1);	// no gradient loss: A = 0 in the direct set
@@ -689,7 +717,9 @@ extern "C" int gsr_backward_gather(const gsr_grid_desc *d, const int32_t *cell_s
 				  : launch_adjoint<2>(dirmode, vor, in, (int)Q, perm, w, rec, lin, cfg->loss_partials, st);
 		if (rc) return rc;
 	}
-	if (D == 3)
+	if (D == 3 && lpg == 128)
+		GATHER_DISPATCH_L(gather3d_kernel, 128, P, cell_start, sorted_id, (const float4 *)packed, (int)N, sample_cell_start, rec, cfg->stop_gradient, tscale, acc);
+	else if (D == 3)
 		GATHER_DISPATCH(gather3d_kernel, P, cell_start, sorted_id, (const float4 *)packed, (int)N, sample_cell_start, rec, cfg->stop_gradient, tscale, acc);
 	else
 		GATHER_DISPATCH(gather2d_kernel, P, cell_start, sorted_id, (const float4 *)packed, (int)N, sample_cell_start, rec, cfg->stop_gradient, acc);

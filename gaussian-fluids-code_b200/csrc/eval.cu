@@ -281,6 +281,8 @@ __global__ void __launch_bounds__(EV_THREADS) count_kernel(EvalParams P_, const 
 	}
 }
 
+int g_lanes8_min_n = 1 << 14;	// items (points or Gaussians) from which 8 lanes share one item instead of a warp
+
 static inline int blocks_for(int64_t Q, int lanes) { return (int)((Q * lanes + EV_THREADS - 1) / EV_THREADS); }
 
 // eval_tiled.cu

@@ -250,6 +250,7 @@ inline EvalParams make_params(const Grid &g)
 }
 
 // lanes per point (or per Gaussian) for a problem of n items: keep >= ~250k threads in flight when n is small
-inline int pick_lanes(int64_t n) { return n >= (1 << 18) ? 1 : (n >= (1 << 14) ? 8 : 32); }
+extern int g_lanes8_min_n;	// eval.cu, GSR_TUNE_LANES8_MIN_N
+inline int pick_lanes(int64_t n) { return n >= (1 << 18) ? 1 : (n >= g_lanes8_min_n ? 8 : 32); }
 
 }  // namespace gsr

@@ -21,7 +21,7 @@ import os
 
 import torch
 
-from . import _lib, advance3d, gsr3d
+from . import _lib, advance3d, engine, gsr3d
 from .init_cond3d import sample_on_box
 from .synth import make_fast3d, synthetic_field
 
@@ -129,7 +129,7 @@ class ShardedProjector(advance3d.FusedProjector):
 		self.acc, self.lp, self.lpb = self.views[0]	# set 0: boundary (direct), sets 1, 2: vorticity / divergence
 		self.nblk, self.nblkb = nblk, nblkb
 		self._streams = None
-		self._samplers = self._prep = None
+		self._samplers = self._prep = self._ident = None
 		if self.peer:
 			self.peer.new_phase()
 
@@ -155,14 +155,14 @@ class ShardedProjector(advance3d.FusedProjector):
 
 	def _side_streams(self, census):
 		if self._streams is None:
-			self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+			self._streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
 		main = torch.cuda.current_stream()
-		return (main,) + (self._streams if census is None else (main, main))	# the census pass shares one counter: keep it serial
+		return (main,) + (self._streams if census is None else (main, main, main))	# the census pass shares one counter: keep it serial
 
 	def _prepare(self, census=None):
 		"""fork: samples + sample hash of the next iteration on the two side streams (not joined: see _join_prepared)"""
 		e = self.gv._engine
-		main, s_fwd, s_bnd = self._side_streams(census)
+		main, s_fwd, s_bnd, s_ref = self._side_streams(census)
 		data_fn, boundary_fn = self._samplers
 		fork = torch.cuda.Event()
 		fork.record(main)
@@ -177,30 +177,50 @@ class ShardedProjector(advance3d.FusedProjector):
 				prep['ev'].append(ev)
 		s_fwd.wait_event(fork)
 		with torch.cuda.stream(s_fwd):
-			prep['data'] = data_fn()
-			prep['bins'] = e.bin_samples(prep['data'], True, tag='pt')
+			data = prep['data'] = data_fn()
+			made = torch.cuda.Event()
+			made.record(s_fwd)
+			prep['bins'] = e.bin_samples(data, True, tag='pt')
 			ev = torch.cuda.Event()
 			ev.record(s_fwd)
 			prep['ev'].append(ev)
+		# the RK4 pull-back reference reads only the samples and the PREVIOUS field, which does not change during the phase: it
+		# starts as soon as the samples exist and has until the adjoint kernel of the next iteration to finish — beside the hash
+		# builds and the forward passes, off the critical path (it was 14 us of the longer of the two chains)
+		s_ref.wait_event(made)
+		with torch.cuda.stream(s_ref):
+			Q = data.shape[0]
+			if self._ident is None or self._ident.perm.shape[0] != Q:
+				self._ident = engine.Bins(torch.arange(Q, dtype=torch.int32, device=data.device))
+			ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
+			self.ref.velocity_field._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=self._ident)
+			prep['ev_ref'] = torch.cuda.Event()
+			prep['ev_ref'].record(s_ref)
 		self._prep = prep
 
-	def _join_prepared(self):
+	def _join_prepared(self, join_ref=True):
+		"""join the prepared samples and their hashes; the pull-back reference only when asked (it is needed at the adjoint kernel
+		of the next iteration, which waits for it itself — but a captured graph must end with every stream joined)"""
 		main = torch.cuda.current_stream()
 		for ev in self._prep['ev']:
 			main.wait_event(ev)
 		self._prep['ev'] = []
+		if join_ref and self._prep.get('ev_ref') is not None:
+			main.wait_event(self._prep['ev_ref'])
+			self._prep['ev_ref'] = None
 
 	def prime(self, census=None):
 		"""prologue of a pipelined phase: prepare the samples of its first iteration"""
 		self._prepare(census)
 		self._join_prepared()
 
-	def iterate(self, data=None, boundary=None, census=None, parity=0):
+	def iterate(self, data=None, boundary=None, census=None, parity=0, join_all=True):
 		"""
 		One optimiser iteration.  Three independent chains run on three streams (fork / join by events, so a captured graph
 		keeps the concurrency): the RK4 pull-back reference (previous field), the forward pass of the current field, and the
 		whole boundary pass; they meet at the adjoint kernel and at the all-reduce.
-		data=None: pipelined — use the samples prepared by prime() / the previous iteration and prepare the next ones.
+		data=None: pipelined — use the samples prepared by prime() / the previous iteration and prepare the next ones;
+		join_all=False leaves the next pull-back reference running into the next call (not for the last call of a captured graph).
 		"""
 		gv, e = self.gv, self.gv._engine
 		cur = self.ref.velocity_field
@@ -214,7 +234,7 @@ class ShardedProjector(advance3d.FusedProjector):
 		Q, Qg = data.shape[0], data.shape[0] * self.world
 		acc_w, lp_w, lpb_w = self.views[parity if self.peer else 0]
 		acc_r, lp_r, lpb_r = self.reduced
-		main, s_fwd, s_bnd = self._side_streams(census)
+		main, s_fwd, s_bnd, _ = self._side_streams(census)
 		fork = torch.cuda.Event()
 		fork.record(main)
 		mask_b = 0
@@ -246,7 +266,11 @@ class ShardedProjector(advance3d.FusedProjector):
 			e.forward(data, val, grad, accumulate=False, perm=bins)
 			done_f = torch.cuda.Event()
 			done_f.record(s_fwd)
-		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
+		if not pipelined:
+			cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
+		elif prep.get('ev_ref') is not None:	# the pull-back of these samples was launched when they were generated
+			main.wait_event(prep['ev_ref'])
+			prep['ev_ref'] = None
 		main.wait_event(done_f)
 		_, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
 									{'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, Q_norm=Qg, acc=acc_w, loss_partials=lp_w)
@@ -269,7 +293,7 @@ class ShardedProjector(advance3d.FusedProjector):
 		self.stepper.step(params, acc_r, mask, loss_srcs=srcs)	# update; leaves iteration counter and grid_scale of the next iteration
 		self._prepare(census)	# side streams: next samples + their hash ...
 		self._rebuild()	# ... beside the Gaussian hash + packed records on this one
-		self._join_prepared()
+		self._join_prepared(join_ref=join_all)
 
 
 class LeapfrogTimestep:
@@ -338,7 +362,7 @@ class LeapfrogTimestep:
 		fp = ent['fp']
 		fp.set_samplers(lambda: self._samples(fp), (lambda: self._boundary(fp)) if self.boundary_lambda else None)
 		fp.prime(census)
-		one = lambda parity, cen=None: fp.iterate(None, None, cen, parity=parity)
+		one = lambda parity, cen=None, last=True: fp.iterate(None, None, cen, parity=parity, join_all=last)
 		# iterations per captured graph: a replay costs ~5 us of launch overhead (tools/graph_probe.py), so several iterations share
 		# one; the peer-memory exchange alternates between two buffers, so a graph then holds whole pairs of iterations
 		unit = int(os.environ.get('GSR_GRAPH_UNIT', '0'))
@@ -346,7 +370,7 @@ class LeapfrogTimestep:
 			unit = next(u for u in (10, 4, 2, 1) if self.iters % u == 0 and self.check_iter % u == 0 and not (fp.peer and u % 2))
 		if (fp.peer and unit % 2) or self.iters % unit or self.check_iter % unit:
 			raise ValueError('iters and check_iter must be multiples of the iterations per graph (even with the peer-memory exchange)')
-		body = lambda: [one(k & 1) for k in range(unit)]
+		body = lambda: [one(k & 1, last=(k == unit - 1)) for k in range(unit)]
 		done = 0
 		if self.use_graph and census is None and ent['graph'] is None:
 			side = torch.cuda.Stream()

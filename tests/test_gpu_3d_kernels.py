@@ -218,3 +218,40 @@ def test_radix_sort_full_size(n, Q):
 		key = key * 64 + torch.where(ok, (sub[:, 0] * 4 + sub[:, 1]) * 4 + sub[:, 2], torch.zeros_like(key))
 	expect = torch.sort(key, stable=True).indices
 	np.testing.assert_array_equal(bins.perm.long().cpu().numpy(), expect.cpu().numpy())
+
+
+@pytest.mark.parametrize('weights,refs', [((0., 1., 0., 0., 0., 0.), 'normals'), ((0., 0., 0., 1., 0., 1.), 'ref_vor'), ((1., 0., 1., 0., 0., 0.), 'val_grad')])
+def test_gather_cta_per_gaussian_equals_warp_per_gaussian(weights, refs):
+	"""few Gaussians, many samples each (the 8192 boundary samples on 1000 Gaussians): the backward gather gives a whole CTA to a
+	Gaussian.  Same visits as the warp-per-Gaussian kernel, summed in a different grouping: 1e-5 of the largest entry per set."""
+	import ctypes as C
+	from gaussian_fluids_code_b200 import _lib
+	lib = _lib.lib()
+	P, S, R, V, mgs, gen = synthetic(10)
+	Q = 8192
+	X = torch.rand((Q, 3), generator=gen).cuda()
+	X[: Q // 2, 0] = 0.	# half of them on a face, like the boundary batch
+	aux = {'normals': {'normals': torch.nn.functional.normalize(torch.randn((Q, 3), generator=gen), dim=1).cuda()},
+		   'ref_vor': {'ref_vor': torch.randn((Q, 3), generator=gen).cuda() * .1},
+		   'val_grad': {'ref_val': torch.randn((Q, 3), generator=gen).cuda() * .1, 'ref_grad': torch.randn((Q, 3, 3), generator=gen).cuda() * .1}}[refs]
+	out = []
+	for max_n in (4096, 0):
+		assert lib.gsr_set_tuning(C.c_int(7), C.c_int(max_n)) == 0
+		try:
+			o = make_fast3d(P, S, R, V, 5e-3, mgs)
+			e = o._engine
+			e.ensure_packed(o._params())
+			bins = e.bin_samples(X, True)
+			val, grad = torch.empty((Q, 3), device='cuda'), torch.empty((Q, 3, 3), device='cuda')
+			e.forward(X, val, grad, False, perm=bins)
+			acc, mask = e.backward_gather(X, bins.perm, bins.scs, val, grad, weights, aux, None)
+			torch.cuda.synchronize()
+			out.append((acc.cpu().numpy().copy(), mask))
+		finally:
+			lib.gsr_set_tuning(C.c_int(7), C.c_int(4096))
+	assert out[0][1] == out[1][1]
+	for s in range(3):
+		if out[0][1] & (1 << s):
+			a, b = out[0][0][s], out[1][0][s]
+			assert np.abs(b).max() > 0.
+			assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), s

@@ -6,6 +6,11 @@ import torch
 from gaussian_fluids_code_b200 import timestep3d, gsr3d
 gsr3d.device = torch.device('cuda', 0)
 UNIT, REPS = 10, 30
+for kv in filter(None, os.environ.get('GSR_TUNE', '').split(',')):	# e.g. GSR_TUNE=7=0,8=8192
+	import ctypes
+	from gaussian_fluids_code_b200 import _lib
+	k, v = kv.split('=')
+	assert _lib.lib().gsr_set_tuning(ctypes.c_int(int(k)), ctypes.c_int(int(v))) == 0
 ts = timestep3d.LeapfrogTimestep(n=int(sys.argv[1]) if len(sys.argv) > 1 else 10, iters=20, test_res=32, check_iter=10)
 ts.step(); ts.step()
 torch.cuda.synchronize()
@@ -51,8 +56,8 @@ def variant(off, boundary=True):
 	torch.cuda.synchronize()
 	g = torch.cuda.CUDAGraph()
 	with torch.cuda.graph(g):
-		for _ in range(UNIT):
-			fp.iterate(None)
+		for k in range(UNIT):
+			fp.iterate(None, join_all=(k == UNIT - 1))
 	for _ in range(3):
 		g.replay()
 	torch.cuda.synchronize()
@@ -87,8 +92,4 @@ def loop_us(fn, reps=300):
 		fn()
 	e1.record(); torch.cuda.synchronize()
 	return e0.elapsed_time(e1) * 1e3 / reps
-out['eager_bin_boundary'] = loop_us(lambda: e.bin_samples(ts._xb, True, tag='pb'))
-out['eager_bin_samples'] = loop_us(lambda: e.bin_samples(ts._x, True, tag='pt'))
-out['eager_gen_boundary'] = loop_us(sample_fns[1])
-out['eager_rebuild'] = loop_us(fp._rebuild)
 print(json.dumps({k: round(v, 2) for k, v in out.items()}))
