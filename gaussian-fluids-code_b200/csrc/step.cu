@@ -345,6 +345,66 @@ constexpr int SC_CTAS = 8;
 constexpr int SC_MAX_THREADS = 256;
 constexpr int SC_MAX_N = SC_CTAS * SC_MAX_THREADS;
 
+// step_reduce_tail with its three independent strands on three warps (in one thread they are ~4 us of dependent double
+// divisions and two pow() while every other thread of the cluster waits at the barrier — ncu: barrier stalls dominated):
+// PCGrad coefficients (4 lanes), losses + scheduler decision (1 lane), Adam bias corrections (2 lanes); then the per-group
+// step sizes and learning rates.  Same formulas, same results.  All threads of the CTA must call it (needs >= 3 warps).
+template <int D>
+__device__ __forceinline__ void step_reduce_tail_split(const gsr_step_cfg &cfg, int N, const double *T, float *st, double *bc_sm, int *decay_sm)
+{
+	const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+	if (w == 0 && lane < 4) {
+		const int g = lane;
+		float a1 = 1.f, a2 = 1.f;
+		if (cfg.pcgrad && T[S_DOT + g] < 0.) {
+			a1 = (float)(1. - T[S_DOT + g] / T[S_N1 + g]);
+			a2 = (float)(1. - T[S_DOT + g] / T[S_N2 + g]);
+		}
+		st[C_A1 + g] = a1;
+		st[C_A2 + g] = a2;
+	} else if (w == 1 && lane == 0) {
+		const double n = (double)N;
+		const double meanV = T[S_V] / n, meanR2 = T[S_V2] / n / (meanV * meanV);
+		st[C_MEANV] = (float)meanV;
+		st[C_MEANR2] = (float)meanR2;
+		const double L_aniso = T[S_ANISO] / n, L_vol = meanR2 - 1., L_valreg = T[S_ABSV] / (n * D), L_dpos = T[S_DPOS] / (n * D);
+		double loss_src = 0.;
+		for (int k = 0; k < 8; k++) loss_src += T[S_COUNT + k];
+		const double loss_tot = loss_src + cfg.w_aniso * L_aniso + cfg.w_vol * L_vol + cfg.w_valreg * L_valreg + cfg.w_dpos * L_dpos;
+		st[GSR_ST_LOSS_TOT] = (float)loss_tot;
+		st[GSR_ST_L_ANISO] = (float)L_aniso;
+		st[GSR_ST_L_VOL] = (float)L_vol;
+		st[GSR_ST_L_VALREG] = (float)L_valreg;
+		st[GSR_ST_L_DPOS] = (float)L_dpos;
+		const float cur = (float)loss_tot;
+		float best = st[GSR_ST_BEST], bad = st[GSR_ST_BAD];
+		if (cur < best * (1.f - cfg.sched_threshold)) { best = cur; bad = 0.f; } else bad += 1.f;
+		const int decay = bad > (float)cfg.sched_patience;
+		if (decay) bad = 0.f;
+		st[GSR_ST_BEST] = best;
+		st[GSR_ST_BAD] = bad;
+		*decay_sm = decay;
+	} else if (w == 2 && lane < 2) {
+		const double t = (double)st[GSR_ST_T] + 1.;
+		bc_sm[lane] = 1. - pow((double)(lane ? cfg.beta2 : cfg.beta1), t);
+	}
+	__syncthreads();
+	if (tid < 4) {
+		const int g = tid;
+		const float lr = st[GSR_ST_LR + g];
+		st[C_LRUSED + g] = lr;
+		st[C_STEP + g] = (float)((double)lr / bc_sm[0]);
+		if (*decay_sm) {
+			const float new_lr = fmaxf(lr * cfg.sched_factor, cfg.sched_min_lr);
+			if (lr - new_lr > cfg.sched_eps) st[GSR_ST_LR + g] = new_lr;
+		}
+	} else if (tid == 4) {
+		st[C_BC2] = (float)(1. / sqrt(bc_sm[1]));
+	} else if (tid == 5) {
+		st[GSR_ST_T] = (float)((double)st[GSR_ST_T] + 1.);
+	}
+}
+
 template <int D>
 __global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC_MAX_THREADS, 1)
 step_cluster_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__restrict__ scal, float *__restrict__ rot, float *__restrict__ vals,
@@ -358,6 +418,8 @@ step_cluster_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__r
 	__shared__ float wpart[SC_MAX_THREADS / 32][S_COUNT];
 	__shared__ float part[S_COUNT];	// this CTA's partial sums (read by every CTA of the cluster)
 	__shared__ double Tsm[S_COUNT + 8];
+	__shared__ double bc_sm[2];
+	__shared__ int decay_sm;
 	__shared__ float wmin[SC_MAX_THREADS / 32];
 	__shared__ float bmin;	// this CTA's min over the new scalings (read by CTA 0)
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
@@ -486,7 +548,9 @@ step_cluster_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__r
 		Tsm[tid] = s;
 	}
 	__syncthreads();
-	if (tid == 0) {
+	if (nw >= 3) {
+		step_reduce_tail_split<D>(cfg, N, Tsm, cst, bc_sm, &decay_sm);
+	} else if (tid == 0) {
 		double T[S_COUNT + 8];
 #pragma unroll
 		for (int k = 0; k < S_COUNT + 8; k++) T[k] = Tsm[k];
