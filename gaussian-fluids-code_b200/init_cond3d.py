@@ -1,7 +1,7 @@
 """
 Scenario tables and boundary samplers of the reference's 3D/init_cond.py (domains :13-32, ring parameters :39-108,
-box sampler :227-249).  The analytic Biot-Savart fields (:115-216) are evaluated with plain torch here (they run once
-per initial fit, not per time step — SURVEY 8f row N2); the OBJ mesh sampler (:223-226) is SURVEY row N3.
+box sampler :227-249) and the analytic Biot-Savart fields (:115-216) on the CUDA kernel of csrc/fields.cu;
+the OBJ mesh sampler (:223-226) is SURVEY row N3.
 """
 import torch
 
@@ -53,47 +53,49 @@ def _ring_particles(ring):
 	return x0, w, ring['radius'] / (2 * ring['n']), ring['thickness']
 
 
-def _chunks(x, size=16384):
-	for b in range(0, x.shape[0], size):
-		yield slice(b, min(b + size, x.shape[0]))
+def _biot_savart(x, ring, val, grad):
+	"""gsr_vortex_particles: val (Q,3) += velocity, grad (Q,3,3) += Jacobian of one ring's regularised Biot-Savart field"""
+	import ctypes as C
+	from . import _lib
+	from ._lib import check, ptr, stream
+	if not x.is_cuda:
+		raise _lib.GsrError('the analytic initial fields run on the GPU (gsr_vortex_particles); got a CPU tensor')
+	x0, w, U, a = _ring_particles(ring)
+	x = x.detach().contiguous().float()
+	check(_lib.lib().gsr_vortex_particles(ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(x0.contiguous()), ptr(w.contiguous()), C.c_int64(x0.shape[0]),
+										  C.c_float(U), C.c_float(a), ptr(val, allow_none=True), ptr(grad, allow_none=True), stream()), 'gsr_vortex_particles')
 
 
 def vortex_ring(x, ring):
-	"""regularised Biot-Savart velocity of one ring: sum_j U f(r) (w_j x d),  f = (1 - exp(-(r/a)^3)) / r^3 (3D/init_cond.py:122-131)"""
-	x0, w, U, a = _ring_particles(ring)
-	res = torch.zeros_like(x)
-	for sl in _chunks(x):
-		d = x[sl, None, :] - x0[None, :, :]
-		r = d.norm(dim=-1)
-		fr = (1. - torch.exp(-(r / a) ** 3)) / r ** 3
-		res[sl] = (U * fr[..., None] * torch.linalg.cross(w[None].expand_as(d), d)).sum(dim=1)
+	"""regularised Biot-Savart velocity of one ring: sum_j U f(r) (w_j x d),  f = (1 - exp(-(r/a)^3)) / r^3 (3D/init_cond.py:122-131, :147-158)"""
+	res = torch.zeros((x.shape[0], 3), dtype=torch.float32, device=x.device)
+	_biot_savart(x, ring, res, None)
 	return res
 
 
 def vortex_ring_gradient(x, ring):
-	"""Jacobian of vortex_ring (3D/init_cond.py:132-145): U (f'/r) [w]x d d^T + U f [w]x"""
-	x0, w, U, a = _ring_particles(ring)
-	W = torch.zeros((w.shape[0], 3, 3), device=x.device)
-	W[:, 0, 1], W[:, 0, 2], W[:, 1, 0], W[:, 1, 2], W[:, 2, 0], W[:, 2, 1] = -w[:, 2], w[:, 1], w[:, 2], -w[:, 0], -w[:, 1], w[:, 0]
-	res = torch.zeros((x.shape[0], 3, 3), device=x.device)
-	for sl in _chunks(x, 4096):
-		d = x[sl, None, :] - x0[None, :, :]
-		r = d.norm(dim=-1)
-		ex = torch.exp(-(r / a) ** 3)
-		fr = (1. - ex) / r ** 3
-		frp = -3. / r ** 4 * (1. - ex) + 3. / (a ** 3 * r) * ex
-		Wd = torch.einsum('jkl,qjl->qjk', W, d)
-		res[sl] = (U * (frp / r)[..., None, None] * Wd[..., :, None] * d[..., None, :] + U * fr[..., None, None] * W[None]).sum(dim=1)
+	"""Jacobian of vortex_ring (3D/init_cond.py:132-145, :159-170): U (f'/r) [w]x d d^T + U f [w]x"""
+	res = torch.zeros((x.shape[0], 3, 3), dtype=torch.float32, device=x.device)
+	_biot_savart(x, ring, None, res)
 	return res
 
 
 def make_field(init_cond):
-	"""velocity field callable with a .gradient attribute, like `eval(cmd_args.init_cond)` in 3D/initialize.py:53"""
+	"""velocity field callable with a .gradient attribute, like `eval(cmd_args.init_cond)` in 3D/initialize.py:53; `.both(x)` returns
+	(velocity, Jacobian) from one pass over the particles (the fit needs both for every batch)"""
 	rings = rings_of(init_cond)
 
+	def run(x, need_val, need_grad):
+		val = torch.zeros((x.shape[0], 3), dtype=torch.float32, device=x.device) if need_val else None
+		grad = torch.zeros((x.shape[0], 3, 3), dtype=torch.float32, device=x.device) if need_grad else None
+		for r in rings:	# the kernel accumulates, like the reference's `res +=`
+			_biot_savart(x, r, val, grad)
+		return val, grad
+
 	def field(x):
-		return sum(vortex_ring(x, r) for r in rings)
-	field.gradient = lambda x: sum(vortex_ring_gradient(x, r) for r in rings)
+		return run(x, True, False)[0]
+	field.gradient = lambda x: run(x, False, True)[1]
+	field.both = lambda x: run(x, True, True)
 	return field
 
 

@@ -42,7 +42,10 @@ def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gra
 	for epoch in range(max_epoch):
 		data = data_generator(batch_size).detach()
 		Q = data.shape[0]
-		ref_val, ref_grad = reference_field(data).contiguous(), reference_gradient(data).contiguous()
+		if hasattr(reference_field, 'both'):	# the analytic ring fields give velocity and Jacobian from one pass over the particles
+			ref_val, ref_grad = reference_field.both(data)
+		else:
+			ref_val, ref_grad = reference_field(data).contiguous(), reference_gradient(data).contiguous()
 		bins = e.bin_samples(data, True)
 		val, grad = torch.empty((Q, 3), device=dev), torch.empty((Q, 3, 3), device=dev)
 		e.forward(data, val, grad, accumulate=False, perm=bins)

@@ -100,6 +100,13 @@ int gsr_build_tiles(const gsr_grid_desc *g, const int32_t *sample_cell_start, in
 #define GSR_TUNE_GATHER_CTA_MAX_N 7	/* 3D backward gather: up to this many Gaussians, with >= 4 samples per Gaussian, one CTA per Gaussian (default 4096; 0: never) */
 #define GSR_TUNE_LANES8_MIN_N 8	/* items (points / Gaussians) from which the latency-shape kernels give 8 lanes to an item instead of a warp (default 16384) */
 #define GSR_TUNE_RK4_SMEM_STATE 3	/* 1 (default): tiled RK4 keeps the integrator state in shared memory, 4 points per thread; 0: registers, 2 per thread */
+/* ---- N2: analytic initial fields (3D/init_cond.py:122-145, Taichi kernels vortex_particle / vortex_particle_gradient) ----
+ * Regularised Biot-Savart sum over M vortex particles (x0 (M,3), w (M,3) strength-scaled tangents, U = radius / (2 n),
+ * a = thickness): val (Q,3) += U f(r) (w x d), grad (Q,3,3) += its Jacobian; either output may be NULL.  Accumulates, like
+ * the reference's kernels (callers zero the outputs, 3D/init_cond.py:156, :169).  One launch. */
+int gsr_vortex_particles(const float *x, int64_t Q, const float *x0, const float *w, int64_t M, float U, float a,
+			 float *val, float *grad, void *stream);
+
 int gsr_set_tuning(int key, int value);
 
 /* ---- a2: forward  (loop 1 of get_losses_ti 3D/GSR.py:270-298; 2D/GSR.py:266-281, :378-395) ------ */

@@ -358,6 +358,34 @@ void FN(o3_rk4)(const gsr_grid3 *g, const float *pos, const float *scal, const f
 	}
 }
 
+/* ---- analytic initial field: regularised Biot-Savart sum over vortex particles (3D/init_cond.py:122-145) -------------
+ * res[i] += U f(r) (w_j x d),  f = (1 - exp(-(r/a)^3)) / r^3,  d = x_i - x0_j, r = |d|          (vortex_particle, :122-131)
+ * jac[i] += U (f'/r) [w_j]x d d^T + U f [w_j]x,  f' = -3/r^4 (1 - e) + 3/(a^3 r) e,  e = exp(-(r/a)^3)  (vortex_particle_gradient, :132-145)
+ * U and a are f32 kernel arguments in the reference; accumulation into res/jac (+=), as there. */
+void FN(o3_vortex_particles)(const float *x, long Q, const REAL *x0, const REAL *w, long M, float U_, float a_, REAL *res, REAL *jac, int nthreads)
+{
+	const REAL U = (REAL)U_, a = (REAL)a_;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+	for (long i = 0; i < Q; i++) {
+		for (long j = 0; j < M; j++) {
+			const REAL d[3] = {(REAL)x[3 * i] - x0[3 * j], (REAL)x[3 * i + 1] - x0[3 * j + 1], (REAL)x[3 * i + 2] - x0[3 * j + 2]};
+			const REAL r = FN(r_sqrt)(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+			const REAL q = r / a, e = FN(r_exp)(-(q * q * q));
+			const REAL fr = (REAL)1 / (r * r * r) * ((REAL)1 - e);
+			const REAL wj[3] = {w[3 * j], w[3 * j + 1], w[3 * j + 2]};
+			const REAL c[3] = {wj[1] * d[2] - wj[2] * d[1], wj[2] * d[0] - wj[0] * d[2], wj[0] * d[1] - wj[1] * d[0]};	/* w x d */
+			if (res)
+				for (int k = 0; k < 3; k++) res[3 * i + k] += U * fr * c[k];
+			if (jac) {
+				const REAL frp = (REAL)-3 / (r * r * r * r) * ((REAL)1 - e) + (REAL)3 / (a * a * a * r) * e;
+				const REAL W[3][3] = {{0, -wj[2], wj[1]}, {wj[2], 0, -wj[0]}, {-wj[1], wj[0], 0}};
+				for (int k = 0; k < 3; k++)
+					for (int l = 0; l < 3; l++) jac[9 * i + 3 * k + l] += U * (frp / r) * (c[k] * d[l]) + U * fr * W[k][l];
+			}
+		}
+	}
+}
+
 #undef ACC
 #undef M3T
 #undef V3T

@@ -277,3 +277,16 @@ class OracleGSR:
 		fn(C.byref(self._G), _p(self.positions), _p(self.scalings), _p(self.rotations), C.c_double(self.tau), C.c_double(rel_band),
 		   _p(x), C.c_long(Q), _p(n_acc), _p(n_band))
 		return n_acc, n_band
+
+
+def vortex_particles(x, x0, w, U, a, real=np.float64, need_val=True, need_grad=True, nthreads=0):
+	"""regularised Biot-Savart sum of 3D/init_cond.py:122-145 over the particles (x0, w): returns (res (Q,3) | None, jac (Q,3,3) | None)"""
+	x = _f32(x)
+	x0, w = np.ascontiguousarray(x0, real), np.ascontiguousarray(w, real)
+	Q, M = x.shape[0], x0.shape[0]
+	res = np.zeros((Q, 3), real) if need_val else None
+	jac = np.zeros((Q, 3, 3), real) if need_grad else None
+	f = getattr(lib(), 'o3_vortex_particles' + ('_f32' if real == np.float32 else '_f64'))
+	f.restype = None
+	f(_p(x), C.c_long(Q), _p(x0), _p(w), C.c_long(M), C.c_float(np.float32(U)), C.c_float(np.float32(a)), _p(res), _p(jac), C.c_int(nthreads or os.cpu_count() or 1))
+	return res, jac

@@ -118,3 +118,28 @@ def test_dense_reference_class(D):
 	val, grad = o.forward(g[p + 'x'])
 	assert rel_err(val, g[f'd{D}_val']) < 1e-11
 	assert rel_err(grad, g[f'd{D}_grad']) < 1e-11
+
+
+def test_init_fields_oracle_matches_reference_golden():
+	"""N2: the oracle's regularised Biot-Savart sum against the reference's own vortex_particle / vortex_particle_gradient
+	kernels run through the shim on the four 3D scenes (tests/golden/make_golden_init3d.py)"""
+	import importlib
+	import os
+	import sys
+	sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+	from helpers import ring_particles_np
+	init_cond3d = importlib.import_module('gaussian_fluids_code_b200.init_cond3d')
+	import oracle.oracle as orc
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref3d_init_fields.npz'))
+	x = g['x']
+	for name in ('leapfrog', 'single_vortex_ring', 'ring_collide', 'ring_with_obstacle'):
+		for real, tag, tol in ((np.float64, 'f64', 1e-9), (np.float32, 'f32', 1e-4)):
+			val, jac = np.zeros((x.shape[0], 3), real), np.zeros((x.shape[0], 3, 3), real)
+			for ring in init_cond3d.rings_of(name):
+				x0, w, U, a = ring_particles_np(ring, real)
+				v, j = orc.vortex_particles(x, x0, w, U, a, real=real)
+				val += v
+				jac += j
+			for got, key in ((val, 'val'), (jac, 'grad')):
+				ref = g[f'{name}_{key}_{tag}']
+				assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), (name, key, tag, np.abs(got - ref).max() / np.abs(ref).max())
