@@ -120,8 +120,21 @@ def sample_on_box(n, x_min, x_max, y_min, y_max, z_min, z_max):
 	return data.contiguous(), normal.contiguous()
 
 
-def make_boundary_sampler(init_cond):
+def make_boundary_sampler(init_cond, obj_file=None):
+	"""`boundary_sampler[init_cond]` of 3D/init_cond.py:251-265; ring_with_obstacle adds n points on the obstacle mesh to the n
+	points on the domain box (sample_for_ring_with_obstacle).  obj_file overrides the scene's asset path (the reference's
+	assets/bunny.obj is not shipped with it)."""
 	x_min, x_max, y_min, y_max, z_min, z_max = domain[init_cond]
-	if init_cond == 'ring_with_obstacle':
-		raise NotImplementedError('mesh boundary sampler (assets/bunny.obj is not shipped with the reference): SURVEY 8f row N3')
-	return lambda n: sample_on_box(n, x_min, x_max, y_min, y_max, z_min, z_max)
+	box = lambda n: sample_on_box(n, x_min, x_max, y_min, y_max, z_min, z_max)
+	info = other_info[init_cond]
+	if 'obj_file' not in info:
+		return box
+	from .mesh_sampler import MeshSampler
+	mesh = MeshSampler(obj_file or info['obj_file'], info['scale'], info.get('rotate', torch.eye(3)), info['translate'])
+
+	def both(n):
+		d1, n1 = box(n)
+		d2, n2 = mesh.sample(n)
+		return torch.cat([d1, d2], dim=0), torch.cat([n1, n2], dim=0)
+	both.mesh = mesh
+	return both

@@ -107,6 +107,17 @@ int gsr_build_tiles(const gsr_grid_desc *g, const int32_t *sample_cell_start, in
 int gsr_vortex_particles(const float *x, int64_t Q, const float *x0, const float *w, int64_t M, float U, float a,
 			 float *val, float *grad, void *stream);
 
+/* ---- N3: mesh boundary sampler (3D/mesh_sampler.py:12-21, :60-88) --------------------------------------------------------
+ * gsr_mesh_tri_areas: area (F) of every triangle (faces (F,3) int32 into vertices (V,3)); the caller forms the inclusive
+ * prefix sums (ti_get_tri_area's second loop).
+ * gsr_sample_mesh: n points on the mesh, triangles weighted by area (binary search in area_presum), uniform on the triangle,
+ * vertex normals (facenormals (F,3) into normals) interpolated and normalised.  Uniforms: Philox keyed like gsr_sample_box, or,
+ * when `uniforms` (n,3) is given, exactly those three draws per sample in the reference's order (face, u, v).  One launch. */
+int gsr_mesh_tri_areas(const float *vertices, const int32_t *faces, int64_t F, float *area, void *stream);
+int gsr_sample_mesh(int64_t n, const float *vertices, const float *normals, const int32_t *faces, const int32_t *facenormals,
+		    const float *area_presum, int64_t F, uint64_t seed, uint32_t stream_id, const float *iteration_dev,
+		    const float *uniforms, float *data, float *normal, void *stream);
+
 int gsr_set_tuning(int key, int value);
 
 /* ---- a2: forward  (loop 1 of get_losses_ti 3D/GSR.py:270-298; 2D/GSR.py:266-281, :378-395) ------ */

@@ -227,3 +227,41 @@ void o2_classify_pairs(const gsr_grid2 *g, const float *pos, const float *scal, 
 		n_acc[j] = na; n_band[j] = nb;
 	}
 }
+
+/* ---- N3: mesh boundary sampler (3D/mesh_sampler.py:12-21, :60-88), float32 as in the reference --------------------------
+ * o3_mesh_area_presum: per-face area, then the SERIAL inclusive prefix sum of ti_get_tri_area.
+ * o3_mesh_sample: the map (three uniforms per sample) -> (point, normal) of ti_lower_bound + ti_sample. */
+void o3_mesh_area_presum(const float *vertices, const int *faces, long F, float *presum)
+{
+	for (long i = 0; i < F; i++) {
+		const float *a = vertices + 3 * faces[3 * i], *b = vertices + 3 * faces[3 * i + 1], *c = vertices + 3 * faces[3 * i + 2];
+		const float e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+		const float x = e1[1] * e2[2] - e1[2] * e2[1], y = e1[2] * e2[0] - e1[0] * e2[2], z = e1[0] * e2[1] - e1[1] * e2[0];
+		presum[i] = sqrtf(x * x + y * y + z * z) * .5f;
+	}
+	for (long i = 1; i < F; i++) presum[i] += presum[i - 1];
+}
+
+void o3_mesh_sample(long n, const float *uniforms, const float *vertices, const float *normals, const int *faces, const int *facenormals,
+		    const float *presum, long F, float *data, float *normal)
+{
+	const float total = presum[F - 1];
+	for (long i = 0; i < n; i++) {
+		const float t = uniforms[3 * i] * total;
+		long l = 0, r = F;
+		while (l < r) {
+			const long m = (l + r) / 2;
+			if (presum[m] < t) l = m + 1;
+			else r = m;
+		}
+		const long f = l < F - 1 ? l : F - 1;
+		const float u = 1.f - sqrtf(uniforms[3 * i + 1]), v = uniforms[3 * i + 2] * (1.f - u), w = 1.f - u - v;
+		float nn[3];
+		for (int k = 0; k < 3; k++) {
+			data[3 * i + k] = u * vertices[3 * faces[3 * f] + k] + v * vertices[3 * faces[3 * f + 1] + k] + w * vertices[3 * faces[3 * f + 2] + k];
+			nn[k] = u * normals[3 * facenormals[3 * f] + k] + v * normals[3 * facenormals[3 * f + 1] + k] + w * normals[3 * facenormals[3 * f + 2] + k];
+		}
+		const float len = sqrtf(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+		for (int k = 0; k < 3; k++) normal[3 * i + k] = nn[k] / len;
+	}
+}

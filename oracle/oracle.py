@@ -290,3 +290,23 @@ def vortex_particles(x, x0, w, U, a, real=np.float64, need_val=True, need_grad=T
 	f.restype = None
 	f(_p(x), C.c_long(Q), _p(x0), _p(w), C.c_long(M), C.c_float(np.float32(U)), C.c_float(np.float32(a)), _p(res), _p(jac), C.c_int(nthreads or os.cpu_count() or 1))
 	return res, jac
+
+
+def mesh_area_presum(vertices, faces):
+	"""ti_get_tri_area (3D/mesh_sampler.py:12-21): inclusive prefix sums of the triangle areas, float32, serial order"""
+	v, f = _f32(vertices), np.ascontiguousarray(faces, np.int32)
+	out = np.zeros(f.shape[0], np.float32)
+	lib().o3_mesh_area_presum.restype = None
+	lib().o3_mesh_area_presum(_p(v), _p(f), C.c_long(f.shape[0]), _p(out))
+	return out
+
+
+def mesh_sample(uniforms, vertices, normals, faces, facenormals, presum):
+	"""ti_sample (3D/mesh_sampler.py:60-88) for given uniforms (n,3): returns (data (n,3), normal (n,3)), float32"""
+	u, v, nr = _f32(uniforms), _f32(vertices), _f32(normals)
+	f, fn, ps = np.ascontiguousarray(faces, np.int32), np.ascontiguousarray(facenormals, np.int32), _f32(presum)
+	n = u.shape[0]
+	data, normal = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+	lib().o3_mesh_sample.restype = None
+	lib().o3_mesh_sample(C.c_long(n), _p(u), _p(v), _p(nr), _p(f), _p(fn), _p(ps), C.c_long(f.shape[0]), _p(data), _p(normal))
+	return data, normal

@@ -219,6 +219,25 @@ def _kernel(fn):
 	return wrapped
 
 
+_RANDOM = []
+
+
+def set_random_sequence(seq):
+	"""the values successive ti.random() calls return (a replayable stand-in for Taichi's generator)"""
+	global _RANDOM
+	_RANDOM = [float(v) for v in seq][::-1]
+
+
+def _random():
+	if not _RANDOM:
+		raise RuntimeError('ti.random(): sequence exhausted (set_random_sequence)')
+	return _DT(_RANDOM.pop())
+
+
+def _cross(a, b):
+	return Vec([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]])
+
+
 def install():
 	"""Put stub `taichi`, `taichi.math`, `vtk`, `matplotlib` modules into sys.modules."""
 	ti = types.ModuleType('taichi')
@@ -232,6 +251,8 @@ def install():
 	ti.types = types.SimpleNamespace(ndarray=lambda: None)
 	ti.field = Field
 	ti.atomic_add = _atomic_add
+	ti.random = _random
+	ti.min = min
 	ti.math = tm
 	tm.vec2, tm.vec3, tm.vec4 = _vecn(2), _vecn(3), _vecn(4)
 	tm.mat2, tm.mat3 = _matn(2), _matn(3)
@@ -239,6 +260,7 @@ def install():
 	tm.exp, tm.sin, tm.cos, tm.sqrt = _map(np.exp), _map(np.sin), _map(np.cos), _map(np.sqrt)
 	tm.sign = _map(_sign)
 	tm.length = lambda v: np.sqrt(v.dot(v))
+	tm.cross = _cross
 	tm.normalize = lambda v: v / np.sqrt(v.dot(v))
 	sys.modules['taichi'] = ti
 	sys.modules['taichi.math'] = tm

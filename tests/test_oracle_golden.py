@@ -143,3 +143,16 @@ def test_init_fields_oracle_matches_reference_golden():
 			for got, key in ((val, 'val'), (jac, 'grad')):
 				ref = g[f'{name}_{key}_{tag}']
 				assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), (name, key, tag, np.abs(got - ref).max() / np.abs(ref).max())
+
+
+def test_mesh_sampler_oracle_matches_reference_golden():
+	"""N3: the oracle's mesh sampler against the reference's own ti_get_tri_area / ti_lower_bound / ti_sample bodies run through
+	the shim with a recorded sequence of uniforms (tests/golden/make_golden_mesh.py)"""
+	import os
+	import oracle.oracle as orc
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref3d_mesh_sampler.npz'))
+	ps = orc.mesh_area_presum(g['vertices'], g['faces'])
+	np.testing.assert_allclose(ps, g['area_presum'], rtol=2e-6)	# same serial order; the shim's cross product rounds each product separately too
+	data, normal = orc.mesh_sample(g['uniforms'], g['vertices'], g['normals'], g['faces'], g['facenormals'], g['area_presum'])
+	np.testing.assert_allclose(data, g['data'], rtol=0., atol=2e-7)
+	np.testing.assert_allclose(normal, g['normal'], rtol=0., atol=5e-7)
