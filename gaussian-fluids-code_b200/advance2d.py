@@ -405,7 +405,7 @@ def advance(scene, gaussian_velocity, new_gaussian_velocity, dt, max_epoch=20000
 	gen = lambda n, gs, restrict=None: scene.data_generator(gs)
 	test = lambda gs: scene.test_generator()
 	clone_velocity_field(new_gaussian_velocity, gaussian_velocity, gen, test, max_epoch=max_epoch, verbose=verbose)
-	advect_covector_field(new_gaussian_velocity, gaussian_velocity, dt)
+	advect_covector_field(new_gaussian_velocity, gaussian_velocity, dt, extra_advector=scene.extra_advector)	# karman: the inlet moves with the flow
 	ref = AdvectedCovectorField(gaussian_velocity, gaussian_velocity, dt, domain=scene.scaled(scene.advance_domain))
 	b1, b2 = scene.boundary_samplers
 	project(new_gaussian_velocity, ref, gen, test, boundary_generator_1=b1, boundary_generator_2=b2, boundary_lambda=boundary_lambda, max_epoch=max_epoch,

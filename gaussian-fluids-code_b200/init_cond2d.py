@@ -1,9 +1,12 @@
 """
-2D scenarios — the data tables, analytic fields, boundary samplers and scale converters of the reference's
+2D scenarios — the data tables, analytic fields, boundary samplers, scale converters and the moving inlet of the reference's
 2D/init_cond.py, as an object (`Scene2D(init_cond)`) instead of module globals keyed by the command line.
 
-Covered: taylor_green, taylor_vortex, leapfrog (closed-form fields, box boundary).  The obstacle scenes
-(vortices_pass*, karman) need the circle / moving-inlet samplers of 2D/init_cond.py:267-428 and are not built yet.
+All eight scenes of the reference: taylor_green, taylor_vortex, leapfrog (closed-form fields, box boundary); vortices_pass,
+vortices_pass_narrow (two discs, free-slip), vortices_pass_noslip (two discs, no-slip: value samples on the discs), karman
+(disc in a channel whose inlet moves with the flow: `extra_advector` / `extra_loader`), vortices_pass_particles (field from
+an OBJ list of vortex particles — the asset is not shipped with the reference; pass `particles_obj=`).
+Pinned by tests/golden/ref2d_scenes.npz, produced by the reference module itself (tests/golden/make_golden_scenes2d.py).
 """
 import numpy as np
 import torch
@@ -11,16 +14,24 @@ import torch
 from . import gsr2d
 
 # 2D/init_cond.py:12-69
-initialize_domain = {'taylor_green': (0., 2. * np.pi, 0., 2. * np.pi), 'taylor_vortex': (-5., 5., -5., 5.), 'leapfrog': (-5., 5., -5., 5.)}
+initialize_domain = {'taylor_green': (0., 2. * np.pi, 0., 2. * np.pi), 'taylor_vortex': (-5., 5., -5., 5.), 'leapfrog': (-5., 5., -5., 5.),
+					 'vortices_pass': (0., 1., 0., 1.), 'vortices_pass_narrow': (0., 1., 0., 1.), 'vortices_pass_noslip': (0., 1., 0., 1.),
+					 'vortices_pass_particles': (-5., 5., -5., 5.), 'karman': (-6.10321, 1.906778, -0.598466, 0.60349)}
 advance_domain = dict(initialize_domain)
-visualize_domain = dict(initialize_domain)
-initial_particle_count = {'taylor_green': (24, 24), 'taylor_vortex': (71, 71), 'leapfrog': (71, 71)}
-visualize_res = {'taylor_green': (200, 200), 'taylor_vortex': (200, 200), 'leapfrog': (200, 200)}
+visualize_domain = dict(initialize_domain, vortices_pass_particles=(-2.5, 2.5, -2.5, 2.5), karman=(-1.10321, 1.906778, -0.598466, 0.60349))
+initial_particle_count = dict({k: (71, 71) for k in initialize_domain}, taylor_green=(24, 24), karman=(400, 60))
+visualize_res = dict({k: (200, 200) for k in initialize_domain}, karman=(501, 200))
 # 2D/init_cond.py:76-131
+_PASS = {'U': 5e-3, 'a': 3e-2, 'vortex_pos1': (.1, .525), 'vortex_pos2': (.1, .475), 'obstacle_radius': 60. / 511.}
 other_info = {
 	'taylor_green': {},
 	'taylor_vortex': {'U': 3., 'a': .5, 'vortex_pos1': (-.8, 0.), 'vortex_pos2': (.8, 0.)},
 	'leapfrog': {'U': .5, 'a': .3, 'vortex_pos1': (-3., -3.), 'vortex_pos2': (-1., -3.), 'vortex_pos3': (1., -3.), 'vortex_pos4': (3., -3.)},
+	'vortices_pass': dict(_PASS, obstacle_pos1=(.5, .27), obstacle_pos2=(.5, .73)),
+	'vortices_pass_narrow': dict(_PASS, obstacle_pos1=(.5, .285), obstacle_pos2=(.5, .715)),
+	'vortices_pass_noslip': dict(_PASS, obstacle_pos1=(.5, .27), obstacle_pos2=(.5, .73)),
+	'vortices_pass_particles': {'particles_obj': '../assets/vortices_pass_particles.obj', 'obstacle_pos1': (0., 1.), 'obstacle_pos2': (0., -1.), 'obstacle_radius': .25},
+	'karman': {'v_magnitude': .5, 'obstacle_pos': (-0.80356845, -0.00502235), 'obstacle_radius': 0.04553178393357534, 'd0': np.pi / 15.},
 }
 
 
@@ -78,24 +89,78 @@ def leapfrog(x, grad):
 	return res
 
 
-FIELDS = {'taylor_green': taylor_green, 'taylor_vortex': taylor_vortex, 'leapfrog': leapfrog}
+def vortices_pass_of(name):
+	"""2D/init_cond.py:204-211: a counter-rotating pair of regularised point vortices"""
+	info = other_info[name]
+
+	def field(x, grad):
+		return vortex_particle(x, torch.tensor(info['vortex_pos1'], device=x.device), info['a'], info['U'], grad) \
+			+ vortex_particle(x, torch.tensor(info['vortex_pos2'], device=x.device), info['a'], -info['U'], grad)
+	return field
+
+
+def karman(x, grad):
+	"""2D/init_cond.py:251-260: uniform inflow (v_magnitude, 0); its Jacobian is zero"""
+	if grad:
+		return torch.zeros((x.shape[0], 2, 2), device=x.device)
+	res = torch.zeros_like(x)
+	res[:, 0] += other_info['karman']['v_magnitude']
+	return res
+
+
+def load_vortex_particles(path):
+	"""`v x _ y w` records of the particle list (2D/init_cond.py:213-224): positions (M,2) and strengths (M)"""
+	X, Y, W = [], [], []
+	with open(path, 'r') as fd:
+		for line in fd.readlines():
+			if line.startswith('v '):
+				t = line.split(' ')
+				X.append(float(t[1])); Y.append(float(t[3])); W.append(float(t[4]))
+	return torch.tensor([X, Y]).transpose(0, 1).contiguous(), torch.tensor(W)
+
+
+def vortices_pass_particles_of(pos, strength):
+	"""2D/init_cond.py:226-238: u(x) = rot90( sum_j w_j (p_j - x) / (|p_j - x|^2 + eps) ), eps = .1; the Jacobian in closed form
+	(the reference differentiates with torch.func.jacfwd)"""
+	eps = .1
+
+	def field(x, grad):
+		p, w = pos.to(x.device), strength.to(x.device)
+		d = p[None] - x[:, None]	# (Q, M, 2)
+		q = (d ** 2).sum(dim=-1) + eps
+		if not grad:
+			s = (w[None, :, None] * d / q[..., None]).sum(dim=1)
+			return torch.stack([-s[:, 1], s[:, 0]], dim=1).contiguous()
+		# ds_k/dx_l = sum_j w_j ( -delta_kl / q + 2 d_k d_l / q^2 )
+		ds = (w[None, :, None, None] * (-torch.eye(2, device=x.device)[None, None] / q[..., None, None] + 2. * d[..., :, None] * d[..., None, :] / (q ** 2)[..., None, None])).sum(dim=1)
+		return torch.stack([-ds[:, 1, :], ds[:, 0, :]], dim=1).contiguous()
+	return field
+
+
+FIELDS = {'taylor_green': taylor_green, 'taylor_vortex': taylor_vortex, 'leapfrog': leapfrog, 'karman': karman,
+		  'vortices_pass': vortices_pass_of('vortices_pass'), 'vortices_pass_narrow': vortices_pass_of('vortices_pass_narrow'),
+		  'vortices_pass_noslip': vortices_pass_of('vortices_pass_noslip')}
 
 
 class Scene2D:
 	"""everything 2D/init_cond.py derives from `--init_cond`"""
 
-	def __init__(self, init_cond):
-		if init_cond not in FIELDS:
-			raise NotImplementedError(f'2D scene {init_cond!r} (obstacle scenes need the circle / inlet samplers of 2D/init_cond.py:267-428)')
+	def __init__(self, init_cond, particles_obj=None):
+		if init_cond not in initialize_domain:
+			raise KeyError(f'unknown 2D scene {init_cond!r}')
 		self.name = init_cond
+		self.info = other_info[init_cond]
 		self.initialize_domain = initialize_domain[init_cond]
-		self.advance_domain = advance_domain[init_cond]
+		self.advance_domain = list(advance_domain[init_cond])	# karman moves its left edge (extra_advector)
 		self.visualize_domain = visualize_domain[init_cond]
 		self.particle_count = initial_particle_count[init_cond]
 		self.visualize_res = visualize_res[init_cond]
 		x_min, x_max, y_min, y_max = self.initialize_domain
 		self.scaling_factor = 10. / min(x_max - x_min, y_max - y_min)	# 2D/init_cond.py:22-25
-		self._field = FIELDS[init_cond]
+		if init_cond == 'vortices_pass_particles':
+			self._field = vortices_pass_particles_of(*load_vortex_particles(particles_obj or self.info['particles_obj']))
+		else:
+			self._field = FIELDS[init_cond]
 
 	# ---- fields in "original" coordinates and their GSR-space ("target") versions (2D/init_cond.py:435-453) ----
 	def velocity(self, x):
@@ -113,6 +178,15 @@ class Scene2D:
 	def scaled(self, dom):
 		return tuple(v * self.scaling_factor for v in dom)
 
+	# ---- the moving inlet of karman (2D/init_cond.py:267-300) ------------------------------------------------------
+	def extra_advector(self, dt, advection_scheme='rk4'):
+		if self.name == 'karman':
+			self.advance_domain[0] = min(self.advance_domain[0] + dt * self.info['v_magnitude'], self.visualize_domain[0])
+
+	def extra_loader(self, start_frame, dt):
+		if self.name == 'karman':
+			self.advance_domain[0] = min(self.initialize_domain[0] + (start_frame * dt) * self.info['v_magnitude'], self.visualize_domain[0])
+
 	# ---- samplers -------------------------------------------------------------------------------------------------
 	def data_generator(self, gaussian_splatting):
 		"""default_data_generator of 2D/advance.py:314-316 / initialize.py: Q = N uniform samples of the advance domain, GSR space"""
@@ -125,9 +199,9 @@ class Scene2D:
 		x_min, x_max, y_min, y_max = self.advance_domain
 		return gsr2d.get_grid_points(x_min, x_max, y_min, y_max, *self.visualize_res) * self.scaling_factor
 
-	def boundary_sampler_2(self, n):
-		"""sample_on_domain_boundary_2 (2D/init_cond.py:306-325) in GSR space: points on the four edges (perimeter-weighted), OUTWARD
-		normals, target normal velocity 0.  Written without boolean-mask indexing (no host sync)."""
+	def _on_domain_boundary_2(self, n):
+		"""sample_on_domain_boundary_2 (2D/init_cond.py:306-325): points on the four edges (perimeter-weighted), OUTWARD normals,
+		target normal velocity 0.  Written without boolean-mask indexing (no host sync)."""
 		x_min, x_max, y_min, y_max = self.advance_domain
 		xs, ys = x_max - x_min, y_max - y_min
 		dev = _dev()
@@ -137,9 +211,69 @@ class Scene2D:
 		py = torch.stack([torch.full_like(t, y_min), y_min + t - xs, torch.full_like(t, y_max), y_max - t + 2. * xs + ys], dim=1)
 		data = torch.stack([px.gather(1, edge[:, None])[:, 0], py.gather(1, edge[:, None])[:, 0]], dim=1)
 		normals = torch.tensor([[0., -1.], [1., 0.], [0., 1.], [-1., 0.]], device=dev)[edge]
-		return (data * self.scaling_factor).contiguous(), normals.contiguous(), torch.zeros(n, device=dev)
+		return data.contiguous(), normals.contiguous(), torch.zeros(n, device=dev)
+
+	@staticmethod
+	def _on_circle(n, x, y, r):
+		"""the points of sample_on_sphere_1 / _2 (2D/init_cond.py:327-343): returns (data, unit outward normal)"""
+		dev = _dev()
+		theta = torch.rand(n, device=dev) * 2. * np.pi
+		nrm = torch.stack([torch.cos(theta), torch.sin(theta)], dim=1)
+		return r * nrm + torch.tensor([x, y], device=dev), nrm
+
+	def _discs(self):
+		return [self.info[k] for k in ('obstacle_pos1', 'obstacle_pos2') if k in self.info] or [self.info['obstacle_pos']]
+
+	def _discs_1(self, n):
+		"""value samples on the discs: u = 0 there (sample_for_vortices_pass_1 / sample_for_karman_1, :345-352, :391-392)"""
+		data = torch.cat([self._on_circle(n, x, y, self.info['obstacle_radius'])[0] for (x, y) in self._discs()], dim=0)
+		return data, torch.zeros_like(data)
+
+	def _discs_2(self, n):
+		"""normal samples on the discs: u.n = 0 (the disc parts of sample_for_vortices_pass_2 / _particles_2, :354-372)"""
+		parts = [self._on_circle(n, x, y, self.info['obstacle_radius']) for (x, y) in self._discs()]
+		return torch.cat([p[0] for p in parts], dim=0), torch.cat([p[1] for p in parts], dim=0), torch.zeros(n * len(parts), device=_dev())
+
+	def _karman_2(self, n):
+		"""sample_for_karman_2 (2D/init_cond.py:394-425): channel walls (u.n = 0), inlet and outlet of the advance domain and the
+		left edge of the visualised window (u.n = +-v_magnitude)"""
+		x_min, x_max, y_min, y_max = self.advance_domain
+		x_min_v, vm = self.visualize_domain[0], self.info['v_magnitude']
+		dev = _dev()
+		t = torch.rand(n, device=dev) * (x_max - x_min) + x_min
+		t2 = torch.rand(n, device=dev) * (y_max - y_min) + y_min
+		col = lambda v: torch.full((n,), v, device=dev)
+		data = torch.cat([torch.stack([t, col(y_min)], 1), torch.stack([t, col(y_max)], 1), torch.stack([col(x_min), t2], 1),
+						  torch.stack([col(x_max), t2], 1), torch.stack([col(x_min_v), t2], 1)], dim=0)
+		nrm = torch.tensor([[0., 1.], [0., -1.], [1., 0.], [-1., 0.], [1., 0.]], device=dev).repeat_interleave(n, dim=0)
+		val = torch.tensor([0., 0., vm, -vm, vm], device=dev).repeat_interleave(n)
+		return data, nrm, val
+
+	def _raw_samplers(self):
+		"""[boundary_generator_1, boundary_generator_2] in original coordinates (the `boundary_sampler` table, :440-449)"""
+		def pass_2(n):	# discs first, then the domain box: the reference's order of draws (:354-362)
+			d, nr, v = self._discs_2(n)
+			d3, n3, v3 = self._on_domain_boundary_2(n)
+			return torch.cat([d, d3], dim=0), torch.cat([nr, n3], dim=0), torch.cat([v, v3], dim=0)
+		return {'vortices_pass': [None, pass_2], 'vortices_pass_narrow': [None, pass_2],
+				'vortices_pass_noslip': [self._discs_1, self._on_domain_boundary_2],
+				'vortices_pass_particles': [None, self._discs_2],
+				'karman': [self._discs_1, self._karman_2]}.get(self.name, [None, self._on_domain_boundary_2])
+
+	def boundary_sampler_2(self, n):
+		"""the scene's normal-velocity sampler in GSR space (target_boundary_sampler_2, :433-438): (points, normals, target u.n)"""
+		data, normal, val = self._raw_samplers()[1](n)
+		return (data * self.scaling_factor).contiguous(), normal.contiguous(), val * self.scaling_factor
+
+	def boundary_sampler_1(self, n):
+		"""the scene's value sampler in GSR space (target_boundary_sampler_1, :427-432): (points, target u), or None for free-slip scenes"""
+		raw = self._raw_samplers()[0]
+		if raw is None:
+			return None
+		data, value = raw(n)
+		return (data * self.scaling_factor).contiguous(), (value * self.scaling_factor).contiguous()
 
 	@property
 	def boundary_samplers(self):
-		"""[boundary_generator_1, boundary_generator_2] as in 2D/init_cond.py:419-428"""
-		return [None, self.boundary_sampler_2]
+		"""[boundary_generator_1, boundary_generator_2] as in 2D/init_cond.py:440-449"""
+		return [self.boundary_sampler_1 if self._raw_samplers()[0] is not None else None, self.boundary_sampler_2]
