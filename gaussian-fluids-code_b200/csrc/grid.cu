@@ -9,6 +9,7 @@
 // then a gather that writes the 48 B (3D) / 32 B (2D) packed Gaussian record in cell order.
 #include "common.cuh"
 #include "hash_small.cuh"
+#include "sampling.cuh"
 #include <math.h>
 #include <cooperative_groups.h>
 
@@ -539,9 +540,18 @@ constexpr int CB_MAX_ROUNDS = 8;
 constexpr int CB_MAX_N = CB_CTAS * CB_THREADS * CB_MAX_ROUNDS;
 constexpr int CB_MAX_SLOTS = 8192;	// cells + the out-of-grid bucket: 26 B of shared memory each, keys fit 13 bits
 
-template <int D>
+// what cell_bin_kernel<D, true> needs to draw the samples itself (the boundary batch of project(): gsr_sample_box_surface)
+struct SurfaceGen {
+	Box box;
+	uint64_t seed;
+	uint32_t stream_id;
+	const float *iteration;
+	float *data, *normal;
+};
+
+template <int D, bool GEN>
 __global__ void __cluster_dims__(CB_CTAS, 1, 1) __launch_bounds__(CB_THREADS, 1)
-cell_bin_kernel(const float *__restrict__ x, int n, Grid g, int rounds, int kbits, int32_t *__restrict__ scs, int32_t *__restrict__ perm)
+cell_bin_kernel(const float *__restrict__ x, int n, Grid g, int rounds, int kbits, int32_t *__restrict__ scs, int32_t *__restrict__ perm, SurfaceGen gen)
 {
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster();
@@ -561,7 +571,22 @@ cell_bin_kernel(const float *__restrict__ x, int n, Grid g, int rounds, int kbit
 #pragma unroll
 	for (int j = 0; j < CB_MAX_ROUNDS; j++) {
 		kr[j] = 0xffffffffu;
-		if (j < rounds && base + 32 * j < n) kr[j] = sample_key<D, false>(x, base + 32 * j, g);
+		if (j < rounds && base + 32 * j < n) {
+			if (GEN) {	// draw sample base + 32 j exactly as sample_box_surface_kernel does, store it, and key it from registers
+				const int i = base + 32 * j;
+				const Philox r(gen.seed, gen.stream_id, (uint32_t)i, gen.iteration ? (uint32_t)__ldg(gen.iteration) : 0u);
+				float pt[3], nm[3];
+				box_surface_point(gen.box, r, pt, nm);
+#pragma unroll
+				for (int k = 0; k < 3; k++) {
+					gen.data[3 * (size_t)i + k] = pt[k];
+					gen.normal[3 * (size_t)i + k] = nm[k];
+				}
+				kr[j] = sample_key_of<D, false>(pt, g);
+			} else {
+				kr[j] = sample_key<D, false>(x, base + 32 * j, g);
+			}
+		}
 	}
 	__syncthreads();
 	uint16_t *mine = hist + w * mp;
@@ -653,20 +678,20 @@ static bool cell_bin_ok(int64_t n, int64_t slots)
 	return !g_force_radix && n > 0 && n <= CB_MAX_N && slots <= CB_MAX_SLOTS;
 }
 
-template <int D>
-static int launch_cell_bin(const float *x, int n, const Grid &g, int32_t *scs, int32_t *perm, cudaStream_t st)
+template <int D, bool GEN>
+static int launch_cell_bin(const float *x, int n, const Grid &g, int32_t *scs, int32_t *perm, cudaStream_t st, const SurfaceGen &gen = SurfaceGen())
 {
 	const int m = g.pcell + 1, mp = (m + 1) & ~1;
 	const size_t sm = sizeof(uint32_t) * 2 * (size_t)mp + sizeof(uint16_t) * (CB_WARPS + 1) * (size_t)mp;
 	if (sm > 48 * 1024) {
-		cudaError_t e = cudaFuncSetAttribute(cell_bin_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+		cudaError_t e = cudaFuncSetAttribute(cell_bin_kernel<D, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
 		if (e != cudaSuccess) return (int)e;
 	}
 	g_launches += 1;
 	int kbits = 1;
 	while ((g.pcell >> kbits) != 0) kbits++;	// keys are 0 .. pcell
 	const int per_warp = (n + CB_CTAS * CB_WARPS - 1) / (CB_CTAS * CB_WARPS);
-	cell_bin_kernel<D><<<CB_CTAS, CB_THREADS, sm, st>>>(x, n, g, (per_warp + 31) / 32, kbits, scs, perm);
+	cell_bin_kernel<D, GEN><<<CB_CTAS, CB_THREADS, sm, st>>>(x, n, g, (per_warp + 31) / 32, kbits, scs, perm, gen);
 	GSR_CHECK_LAUNCH();
 	return GSR_OK;
 }
@@ -788,7 +813,7 @@ extern "C" int gsr_bin_samples(const gsr_grid_desc *d, const float *x, int64_t Q
 	int n = (int)Q;
 	if (!shift && cell_bin_ok(Q, (int64_t)g.pcell + 1)) {
 		int32_t *scs = sample_cell_start ? sample_cell_start : ((size_t)(g.pcell + 1) <= 256 * (size_t)s.nblocks + 1024 ? (int32_t *)s.hist : nullptr);
-		if (scs) return (g.D == 3) ? launch_cell_bin<3>(x, n, g, scs, perm, st) : launch_cell_bin<2>(x, n, g, scs, perm, st);
+		if (scs) return (g.D == 3) ? launch_cell_bin<3, false>(x, n, g, scs, perm, st) : launch_cell_bin<2, false>(x, n, g, scs, perm, st);
 	}
 	if (!shift && small_hash_ok(Q, g.pcell)) {
 		// sample_cell_start is produced as a by-product; when the caller does not want it, it lands in scratch
@@ -825,6 +850,24 @@ extern "C" int gsr_bin_samples(const gsr_grid_desc *d, const float *x, int64_t Q
 		GSR_CHECK_LAUNCH();
 	}
 	return GSR_OK;
+}
+
+extern "C" int gsr_sample_box_surface(const float *box, int64_t n, uint64_t seed, uint32_t stream_id, const float *iteration_dev, float *data, float *normal,
+				      void *stream);
+
+extern "C" int gsr_sample_box_surface_binned(const float *box, int64_t n, uint64_t seed, uint32_t stream_id, const float *iteration_dev,
+					     float *data, float *normal, const gsr_grid_desc *d, int32_t *perm, int32_t *sample_cell_start,
+					     void *ws, size_t ws_bytes, void *stream)
+{
+	Grid g;
+	if (!box || !data || !normal || !perm || !sample_cell_start || !make_grid(d, g) || g.D != 3 || n < 0 || n >= ((int64_t)1 << 30)) return GSR_EINVAL;
+	if (n > 0 && cell_bin_ok(n, (int64_t)g.pcell + 1)) {	// one launch draws the samples and sorts them by cell
+		SurfaceGen gen = {make_box(box), seed, stream_id, iteration_dev, data, normal};
+		return launch_cell_bin<3, true>(nullptr, (int)n, g, sample_cell_start, perm, (cudaStream_t)stream, gen);
+	}
+	int rc = gsr_sample_box_surface(box, n, seed, stream_id, iteration_dev, data, normal, stream);
+	if (rc) return rc;
+	return gsr_bin_samples(d, data, n, perm, sample_cell_start, 0, ws, ws_bytes, stream);
 }
 
 extern "C" int gsr_pack_gaussians(const gsr_grid_desc *d, const float *positions, const float *scalings, const float *rotations,

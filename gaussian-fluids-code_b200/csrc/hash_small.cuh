@@ -35,7 +35,7 @@ __device__ __forceinline__ uint32_t gauss_key(const float *__restrict__ pos, int
 // FINE: the key is extended by 2 bits per axis of sub-cell position (a 4^D raster inside the cell), so that consecutive
 // sorted samples are spatially compact — the warps of the tiled evaluation kernels then reject most candidates as a whole.
 template <int D, bool FINE>
-__device__ __forceinline__ uint32_t sample_key(const float *__restrict__ x, int i, const Grid &g)
+__device__ __forceinline__ uint32_t sample_key_of(const float (&pt)[3], const Grid &g)
 {
 	bool ok = true;
 	int c[3] = {-1, -1, -1};
@@ -43,7 +43,7 @@ __device__ __forceinline__ uint32_t sample_key(const float *__restrict__ x, int 
 	const float gs = grid_gs(g);
 #pragma unroll
 	for (int k = 0; k < D; k++) {
-		const float xv = x[(size_t)D * i + k];
+		const float xv = pt[k];
 		c[k] = cell_coord(xv, g.lo[k], gs);
 		ok = ok && c[k] >= -1 && c[k] <= g.dims[k];
 		if (FINE) {
@@ -55,6 +55,15 @@ __device__ __forceinline__ uint32_t sample_key(const float *__restrict__ x, int 
 	if (ok) key = (uint32_t)(((c[0] + 1) * g.pdims[1] + (c[1] + 1)) * g.pdims[2] + (c[2] + 1));
 	if (FINE) key = (key << (2 * D)) | (ok ? sub : 0u);
 	return key;
+}
+
+template <int D, bool FINE>
+__device__ __forceinline__ uint32_t sample_key(const float *__restrict__ x, int i, const Grid &g)
+{
+	float pt[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+	for (int k = 0; k < D; k++) pt[k] = x[(size_t)D * i + k];
+	return sample_key_of<D, FINE>(pt, g);
 }
 
 

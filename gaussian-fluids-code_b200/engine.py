@@ -294,6 +294,19 @@ class HashEngine:
 		check(self.lib.gsr_sample_box(b, C.c_int64(out.shape[0]), C.c_uint64(seed), C.c_uint32(stream_id), ptr(iteration, allow_none=True), ptr(out), stream()), 'gsr_sample_box')
 		return out
 
+	def sample_box_surface_binned(self, box, data, normal, seed, stream_id, iteration=None, tag='pb'):
+		"""gsr_sample_box_surface_binned: draw the boundary samples AND order them for the kernels (one launch for the per-iteration
+		batch sizes); returns Bins — exactly what sample_box_surface + bin_samples(data, True, tag) give"""
+		b = (C.c_float * 6)(*[float(v) for v in box])
+		Q = data.shape[0]
+		perm = self.scratch.typed('perm_' + tag, (Q,), torch.int32)
+		scs = self.scratch.typed('scs_' + tag, (self.lib.gsr_padded_cells(C.byref(self.desc)) + 1,), torch.int32)
+		ws = self.scratch.get('sort_' + tag, self.lib.gsr_bin_samples_ws_bytes(C.byref(self.desc), C.c_int64(Q)))
+		check(self.lib.gsr_sample_box_surface_binned(b, C.c_int64(Q), C.c_uint64(seed), C.c_uint32(stream_id), ptr(iteration, allow_none=True), ptr(data), ptr(normal),
+													 C.byref(self.desc), ptr(perm, torch.int32), ptr(scs, torch.int32), ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()),
+			  'gsr_sample_box_surface_binned')
+		return Bins(perm, scs, None)
+
 	def sample_box_surface(self, box, data, normal, seed, stream_id, iteration=None):
 		b = (C.c_float * 6)(*[float(v) for v in box])
 		check(self.lib.gsr_sample_box_surface(b, C.c_int64(data.shape[0]), C.c_uint64(seed), C.c_uint32(stream_id), ptr(iteration, allow_none=True),

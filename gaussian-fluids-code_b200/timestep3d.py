@@ -151,7 +151,8 @@ class ShardedProjector(advance3d.FusedProjector):
 	ORDERED_REF_MIN_Q = 8192	# from this batch size the pull-back reference walks its samples in cell order
 
 	def set_samplers(self, data_fn, boundary_fn=None):
-		"""data_fn() -> (Q,3) samples, boundary_fn() -> ((Qb,3) points, (Qb,3) normals); both must write persistent tensors"""
+		"""data_fn() -> (Q,3) samples; boundary_fn() -> ((Qb,3) points, (Qb,3) normals), or (that pair, engine.Bins) when the sampler
+		already ordered the batch (sample_box_surface_binned); both must write persistent tensors"""
 		self._samplers = (data_fn, boundary_fn)
 		self._prep = None
 
@@ -172,8 +173,12 @@ class ShardedProjector(advance3d.FusedProjector):
 		if boundary_fn is not None:
 			s_bnd.wait_event(fork)
 			with torch.cuda.stream(s_bnd):
-				prep['boundary'] = boundary_fn()
-				prep['bins_b'] = e.bin_samples(prep['boundary'][0], True, tag='pb')
+				res = boundary_fn()
+				if isinstance(res[1], engine.Bins):	# the sampler drew and ordered the batch in one launch
+					prep['boundary'], prep['bins_b'] = res
+				else:
+					prep['boundary'] = res
+					prep['bins_b'] = e.bin_samples(res[0], True, tag='pb')
 				ev = torch.cuda.Event()
 				ev.record(s_bnd)
 				prep['ev'].append(ev)
@@ -337,6 +342,11 @@ class LeapfrogTimestep:
 		"""sample_on_box(Qb) on the unit cube (3D/init_cond.py:227-249), one kernel"""
 		return fp.gv._engine.sample_box_surface((0., 1.) * 3, self._xb, self._nb, 42, 2 * self.rank + 1, fp.stepper.state[:1])
 
+	def _boundary_binned(self, fp):
+		"""_boundary + the engine's ordering of the batch, one launch: ((points, normals), Bins)"""
+		bins = fp.gv._engine.sample_box_surface_binned((0., 1.) * 3, self._xb, self._nb, 42, 2 * self.rank + 1, fp.stepper.state[:1], tag='pb')
+		return (self._xb, self._nb), bins
+
 	def _projector(self, new, cur):
 		"""the persistent projector (buffers, optimiser state, captured iteration graph) of one (new, cur) orientation"""
 		key = id(new)
@@ -365,7 +375,7 @@ class LeapfrogTimestep:
 		# project, fixed iteration count; the iteration is captured once per orientation into a CUDA graph and replayed
 		ent = self._projector(new, cur)
 		fp = ent['fp']
-		fp.set_samplers(lambda: self._samples(fp), (lambda: self._boundary(fp)) if self.boundary_lambda else None)
+		fp.set_samplers(lambda: self._samples(fp), (lambda: self._boundary_binned(fp)) if self.boundary_lambda else None)
 		fp.prime(census)
 		one = lambda parity, cen=None, last=True: fp.iterate(None, None, cen, parity=parity, join_all=last)
 		# iterations per captured graph: a replay costs ~5 us of launch overhead (tools/graph_probe.py), so several iterations share

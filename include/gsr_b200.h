@@ -100,6 +100,13 @@ int gsr_build_tiles(const gsr_grid_desc *g, const int32_t *sample_cell_start, in
 #define GSR_TUNE_GATHER_CTA_MAX_N 7	/* 3D backward gather: up to this many Gaussians, with >= 4 samples per Gaussian, one CTA per Gaussian (default 4096; 0: never) */
 #define GSR_TUNE_LANES8_MIN_N 8	/* items (points / Gaussians) from which the latency-shape kernels give 8 lanes to an item instead of a warp (default 16384) */
 #define GSR_TUNE_RK4_SMEM_STATE 3	/* 1 (default): tiled RK4 keeps the integrator state in shared memory, 4 points per thread; 0: registers, 2 per thread */
+/* gsr_sample_box_surface followed by gsr_bin_samples(fine = 0) on the drawn points, as ONE launch when the batch fits the
+ * cluster sort (n <= 16384 on <= 8191 padded cells; otherwise the two calls are made internally): data, normal (n,3), perm (n),
+ * sample_cell_start (padded cells + 1); ws as for gsr_bin_samples.  Same draws, same order as the two separate calls. */
+int gsr_sample_box_surface_binned(const float *box, int64_t n, uint64_t seed, uint32_t stream_id, const float *iteration_dev,
+				  float *data, float *normal, const gsr_grid_desc *g, int32_t *perm, int32_t *sample_cell_start,
+				  void *ws, size_t ws_bytes, void *stream);
+
 /* ---- N2: analytic initial fields (3D/init_cond.py:122-145, Taichi kernels vortex_particle / vortex_particle_gradient) ----
  * Regularised Biot-Savart sum over M vortex particles (x0 (M,3), w (M,3) strength-scaled tangents, U = radius / (2 n),
  * a = thickness): val (Q,3) += U f(r) (w x d), grad (Q,3,3) += its Jacobian; either output may be NULL.  Accumulates, like

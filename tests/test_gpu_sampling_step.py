@@ -166,3 +166,24 @@ def test_xrank_sum_single_rank():
 		torch.cuda.synchronize()
 		assert torch.equal(out, bufs[k % 2]) and int(err.item()) == 0 and int(pad[0].item()) == 1000 + k + 1
 	assert lib.gsr_xrank_sum(ptrs, sig, C.c_int(0), C.c_int(1), C.c_int64(n + 1), _lib.ptr(it), _lib.ptr(base, torch.int32), _lib.ptr(out), _lib.ptr(err, torch.int32), _lib.stream()) == -1
+
+
+@pytest.mark.parametrize('n,Qb', [(10, 8192), (10, 1000), (30, 8192), (10, 20000)])
+def test_surface_samples_drawn_and_binned_in_one_launch(n, Qb):
+	"""gsr_sample_box_surface_binned == gsr_sample_box_surface followed by gsr_bin_samples: the same draws, the same order, the
+	same cell table (one cluster launch when the batch fits it; n = 30 has too many cells and Qb = 20000 too many samples, which
+	exercises the internal two-call form)"""
+	o, gen = engine_field(n)
+	e = o._engine
+	it = torch.full((1,), 5., device='cuda')
+	box = (0., 1.) * 3
+	d1, n1 = torch.empty((Qb, 3), device='cuda'), torch.empty((Qb, 3), device='cuda')
+	e.sample_box_surface(box, d1, n1, 42, 3, it)
+	b1 = e.bin_samples(d1, True, tag='sep')
+	d2, n2 = torch.empty((Qb, 3), device='cuda'), torch.empty((Qb, 3), device='cuda')
+	b2 = e.sample_box_surface_binned(box, d2, n2, 42, 3, it, tag='fused')
+	torch.cuda.synchronize()
+	np.testing.assert_array_equal(d1.cpu().numpy(), d2.cpu().numpy())
+	np.testing.assert_array_equal(n1.cpu().numpy(), n2.cpu().numpy())
+	np.testing.assert_array_equal(b1.scs.cpu().numpy(), b2.scs.cpu().numpy())
+	np.testing.assert_array_equal(b1.perm.cpu().numpy(), b2.perm.cpu().numpy())

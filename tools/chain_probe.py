@@ -24,7 +24,7 @@ def gather_spy(*a, **k):
 	masks[k.get('tag', 'main')] = r[1]
 	return r
 e.backward_gather = gather_spy
-sample_fns = [lambda: ts._samples(fp), lambda: ts._boundary(fp)]
+sample_fns = [lambda: ts._samples(fp), (lambda: ts._boundary(fp)) if os.environ.get('SEPARATE_BOUNDARY_GEN') else (lambda: ts._boundary_binned(fp))]
 fp.set_samplers(*sample_fns); fp.prime(); fp.iterate(None)
 torch.cuda.synchronize()
 bins_cache = {}
@@ -34,6 +34,8 @@ def bin_spy(x, need_cells, tag='x'):
 	return b
 e.bin_samples = bin_spy
 fp.iterate(None); torch.cuda.synchronize()
+if not os.environ.get('SEPARATE_BOUNDARY_GEN'):
+	bins_cache['pb'] = ts._boundary_binned(fp)[1]
 tick = torch.zeros(8, device='cuda')
 
 def variant(off, boundary=True):
@@ -44,7 +46,7 @@ def variant(off, boundary=True):
 	fp._rebuild = (lambda: None) if 'rebuild' in off else real['rebuild']
 	if 'prep' in off:
 		e.bin_samples = lambda x, need_cells, tag='x': bins_cache[tag]
-		fns = [lambda: ts._x, lambda: (ts._xb, ts._nb)]
+		fns = [lambda: ts._x, (lambda: (ts._xb, ts._nb)) if os.environ.get('SEPARATE_BOUNDARY_GEN') else (lambda: ((ts._xb, ts._nb), bins_cache['pb']))]
 	else:
 		e.bin_samples = real['bin']
 		fns = sample_fns
