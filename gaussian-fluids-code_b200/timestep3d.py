@@ -12,9 +12,14 @@ count pinned to the reference's minimum, because the reference's own count is da
 Multi-GPU (one process per GPU): sample points are sharded — every rank draws its own N training and 8192 boundary
 samples (global Q = world * N, the loss normalisers use the global counts) and its own test_res^3 share of a lattice that
 is world times finer along z (fixed work per rank: weak scaling);
-Gaussian parameters, hash and optimiser state are replicated; ONE NCCL all-reduce per iteration sums the compact
-gradient accumulators and the loss partial sums, after which every rank runs the identical fused step, so the
-replicas stay bit-identical without a broadcast.
+Gaussian parameters, hash and optimiser state are replicated; ONE exchange per iteration sums the compact gradient
+accumulators and the loss partial sums (a single kernel over NVLink peer memory, csrc/xrank.cu; NCCL all-reduce as the
+fallback), after which every rank runs the identical fused step, so the replicas stay bit-identical without a broadcast.
+
+Schedule of an iteration (ShardedProjector): the iteration is a strict cycle — forward needs the rebuilt hash, the step needs
+every gather — so everything that does not depend on the updated Gaussians is moved off it: the next iteration's samples and
+their hashes are prepared right after the step (beside the Gaussian hash), and the RK4 pull-back reference of those samples
+runs on its own stream until the next adjoint kernel needs it.  Ten iterations form one captured CUDA graph.
 """
 import ctypes as C
 import os

@@ -82,3 +82,17 @@ def test_no_cpu_fallback():
 		engine.HashEngine(3, 'cpu')
 	with pytest.raises(_lib.GsrError):
 		_lib.ptr(torch.zeros(3))
+
+
+def test_obj_parser_of_the_mesh_sampler():
+	"""host side of mesh_sampler.MeshSampler (3D/mesh_sampler.py:23-36): v / vn / f records, `a/b/c` and `a//c` face items, 1-based"""
+	from gaussian_fluids_code_b200 import _lib
+	from gaussian_fluids_code_b200.mesh_sampler import parse_obj
+	text = '# comment\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvn 0 0 1\nvn 1 0 0\nvt 0.5 0.5\nf 1//1 2//1 3//1\nf 1/7/2 3/8/2 4/9/2\n'
+	v, n, f, fn = parse_obj(text)
+	assert v == [[0., 0., 0.], [1., 0., 0.], [0., 1., 0.], [0., 0., 1.]] and n == [[0., 0., 1.], [1., 0., 0.]]
+	assert f == [[0, 1, 2], [0, 2, 3]] and fn == [[0, 0, 0], [1, 1, 1]]
+	with pytest.raises(_lib.GsrError):
+		parse_obj('v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvn 0 0 1\nf 1//1 2//1 3//1 4//1\n')	# quads: not supported, as in the reference
+	with pytest.raises(_lib.GsrError):
+		parse_obj('v 0 0 0\nf 1 1 1\n')	# no normals
