@@ -386,6 +386,36 @@ void FN(o3_vortex_particles)(const float *x, long Q, const REAL *x0, const REAL 
 	}
 }
 
+/* ---- N1: trilinear resampling of a lattice field at given positions (ti_get_interp_val, 3D/advance_density.py:24-50) ----
+ * field (nx,ny,nz), positions (Q,3) inside the domain, result (Q).  The domain bounds are f32 kernel arguments in the reference. */
+void FN(o3_interp_val)(const REAL *field, const int *dims, const REAL *positions, long Q, const float *domain, REAL *result, int nthreads)
+{
+	const int nx = dims[0], ny = dims[1], nz = dims[2];
+	const REAL lo[3] = {(REAL)domain[0], (REAL)domain[2], (REAL)domain[4]}, hi[3] = {(REAL)domain[1], (REAL)domain[3], (REAL)domain[5]};
+	const REAL d[3] = {(hi[0] - lo[0]) / (REAL)(nx - 1), (hi[1] - lo[1]) / (REAL)(ny - 1), (hi[2] - lo[2]) / (REAL)(nz - 1)};
+	const int n[3] = {nx, ny, nz};
+#define FLD(i, j, k) field[((size_t)(i) * ny + (j)) * nz + (k)]
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+	for (long q = 0; q < Q; q++) {
+		int i0[3], i1[3];
+		REAL w[3];
+		for (int a = 0; a < 3; a++) {
+			const REAL p = positions[3 * q + a] - lo[a];
+			i0[a] = (int)(sizeof(REAL) == 4 ? floorf((float)(p / d[a])) : floor((double)(p / d[a])));
+			i1[a] = i0[a] + 1 < n[a] - 1 ? i0[a] + 1 : n[a] - 1;
+			/* corner_min = ti_get_coord(pi, ...) - zero_p = (lo + (hi - lo) / (n - 1) * pi) - lo */
+			const REAL corner = (lo[a] + (hi[a] - lo[a]) / (REAL)(n[a] - 1) * (REAL)i0[a]) - lo[a];
+			w[a] = (p - corner) / d[a];
+		}
+		const REAL one = (REAL)1;
+		result[q] = FLD(i0[0], i0[1], i0[2]) * (one - w[0]) * (one - w[1]) * (one - w[2]) + FLD(i1[0], i0[1], i0[2]) * w[0] * (one - w[1]) * (one - w[2])
+			  + FLD(i0[0], i1[1], i0[2]) * (one - w[0]) * w[1] * (one - w[2]) + FLD(i1[0], i1[1], i0[2]) * w[0] * w[1] * (one - w[2])
+			  + FLD(i0[0], i0[1], i1[2]) * (one - w[0]) * (one - w[1]) * w[2] + FLD(i1[0], i0[1], i1[2]) * w[0] * (one - w[1]) * w[2]
+			  + FLD(i0[0], i1[1], i1[2]) * (one - w[0]) * w[1] * w[2] + FLD(i1[0], i1[1], i1[2]) * w[0] * w[1] * w[2];
+	}
+#undef FLD
+}
+
 #undef ACC
 #undef M3T
 #undef V3T

@@ -310,3 +310,16 @@ def mesh_sample(uniforms, vertices, normals, faces, facenormals, presum):
 	lib().o3_mesh_sample.restype = None
 	lib().o3_mesh_sample(C.c_long(n), _p(u), _p(v), _p(nr), _p(f), _p(fn), _p(ps), C.c_long(f.shape[0]), _p(data), _p(normal))
 	return data, normal
+
+
+def interp_val(field, positions, domain, real=np.float64, nthreads=0):
+	"""ti_get_interp_val (3D/advance_density.py:24-50): trilinear samples of field (nx,ny,nz) at positions (...,3) -> (...)"""
+	f = np.ascontiguousarray(field, real)
+	p = np.ascontiguousarray(positions, real)
+	out = np.zeros(p.shape[:-1], real)
+	dims = np.array(f.shape, np.int32)
+	dom = np.array(domain, np.float32)
+	fn = getattr(lib(), 'o3_interp_val' + ('_f32' if real == np.float32 else '_f64'))
+	fn.restype = None
+	fn(_p(f), _p(dims), _p(p), C.c_long(out.size), _p(dom), _p(out), C.c_int(nthreads or os.cpu_count() or 1))
+	return out

@@ -261,6 +261,8 @@ def install():
 	tm.sign = _map(_sign)
 	tm.length = lambda v: np.sqrt(v.dot(v))
 	tm.cross = _cross
+	tm.dot = lambda a, b: a.dot(b)
+	tm.floor = lambda x, dtype=None: int(np.floor(x)) if dtype is I32 else _DT(np.floor(x))
 	tm.normalize = lambda v: v / np.sqrt(v.dot(v))
 	sys.modules['taichi'] = ti
 	sys.modules['taichi.math'] = tm
@@ -286,3 +288,12 @@ class GArr(np.ndarray):
 	def __getitem__(self, idx):
 		r = super().__getitem__(idx)
 		return r if not isinstance(r, np.ndarray) else r
+
+
+class IdxArr(np.ndarray):
+	"""ndarray whose iteration yields index tuples, like a Taichi struct-for over an ndarray argument (`for i, j, k in field:`)"""
+	def __new__(cls, a, dtype=None):
+		return np.array(a, dtype=dtype).view(cls)
+
+	def __iter__(self):
+		return iter(np.ndindex(*self.shape))

@@ -156,3 +156,28 @@ def test_mesh_sampler_oracle_matches_reference_golden():
 	data, normal = orc.mesh_sample(g['uniforms'], g['vertices'], g['normals'], g['faces'], g['facenormals'], g['area_presum'])
 	np.testing.assert_allclose(data, g['data'], rtol=0., atol=2e-7)
 	np.testing.assert_allclose(normal, g['normal'], rtol=0., atol=5e-7)
+
+
+def test_density_resampling_oracle_matches_reference_golden():
+	"""N1: the oracle's trilinear resampling against the reference's own ti_get_interp_val body, at the back-traced lattice the
+	reference's advection_rk4_ti produced (tests/golden/make_golden_density.py), and the whole composition of advected_density
+	(RK4 back-trace by -dt, clamp, resample) through the oracle's RK4"""
+	import os
+	import oracle.oracle as orc
+	from helpers import oracle_from_golden
+	g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref3d_density.npz')))
+	for real, tag, tol in ((np.float64, 'f64', 1e-12), (np.float32, 'f32', 2e-6)):
+		for name in ('ring', 'smooth'):
+			got = orc.interp_val(g[f'{name}_density_{tag}'], g[f'backtraced_{tag}'], g['domain'], real=real)
+			assert np.abs(got - g[f'{name}_next_{tag}']).max() <= tol, (name, tag)
+	# the composition, float64: lattice -> oracle RK4 by -dt -> clamp -> resample
+	o = oracle_from_golden(g, 3, 'f64')
+	o.build_grid()
+	res, dom = g['res'], g['domain']
+	axes = [np.linspace(dom[2 * a], dom[2 * a + 1], res[a], dtype=np.float32) for a in range(3)]	# get_grid_points: torch.linspace in float32
+	x = np.stack(np.meshgrid(*axes, indexing='ij'), -1).reshape(-1, 3)
+	bk = o.rk4(x, -float(g['dt']))
+	bk = np.clip(bk, dom[0::2], dom[1::2]).reshape(*res, 3)
+	assert np.abs(bk - g['backtraced_f64']).max() < 1e-6	# lattice coordinates: float32 linspace here, float64 in the f64 golden run
+	got = orc.interp_val(g['smooth_density_f64'], bk, dom, real=np.float64)
+	assert np.abs(got - g['smooth_next_f64']).max() < 2e-5
