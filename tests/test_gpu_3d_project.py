@@ -109,3 +109,40 @@ def test_simulation_initialize_fits_the_leapfrog_rings():
 	gv = initialize3d.simulation_initialize('leapfrog', max_epoch=150, verbose=0)
 	err = float((gv(x) - ref).abs().mean() / ref.abs().mean())
 	assert np.isfinite(err) and err < .8, err	# from 1.0 (zero field) after 150 of the reference's 500 epochs
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('epochs', [1, 3])
+def test_project_matches_reference_golden(fused, epochs):
+	"""the per-timestep optimisation against the reference's OWN project() (3D/advance.py:183-334: PCGrad, autograd regularisers,
+	4 x Adam, 4 x ReduceLROnPlateau, grid rebuild) run on its own GaussianSplatting3DFast through the Taichi shim with recorded sample
+	batches (tests/golden/make_golden_project3d.py): the parameter updates after 1 and 3 iterations, the next grid_scale, the lrs"""
+	from helpers import load_golden
+	from gaussian_fluids_code_b200 import advance3d, gsr3d
+	gsr3d.device = torch.device('cuda', 0)
+	g = load_golden('ref3d_project.npz')
+
+	def field(P):
+		gv = gsr3d.GaussianSplatting3DFast(0., 1., 0., 1., 0., 1., P, dim=3)	# the reference's defaults: min_grid_scale and clamp_threshold
+		assert gv.min_grid_scale == pytest.approx(float(g['min_grid_scale']), rel=1e-12) and gv.clamp_threshold == float(g['tau'])
+		with torch.no_grad():
+			gv.scalings.copy_(torch.tensor(g['scalings'])); gv.rotations.copy_(torch.tensor(g['rotations'])); gv.values.copy_(torch.tensor(g['values']))
+		gv.reinitialize_grid()
+		gv.zero_grad()
+		return gv
+	cur, new = field(g['cur_positions']), field(g['new_positions'])
+	ref = advance3d.AdvectedCovectorField(cur, cur, float(g['dt']), 0., 1., 0., 1., 0., 1.)
+	datas = iter([torch.tensor(x, device='cuda') for x in g['samples']])
+	bnds = iter([(torch.tensor(d, device='cuda'), torch.tensor(n, device='cuda')) for d, n in zip(g['boundary_data'], g['boundary_normal'])])
+	advance3d.project(new, ref, 0., 1., 0., 1., 0., 1., lambda n, gv: next(datas), lambda gv: None, boundary_generator=lambda n: next(bnds),
+					  boundary_lambda=float(g['boundary_lambda']), batch_size=g['boundary_data'].shape[1], max_epoch=epochs, patience=500, verbose=0,
+					  fused=fused, check_iter=1000)
+	before = dict(positions=g['new_positions'], scalings=g['scalings'], rotations=g['rotations'], values=g['values'])
+	for nm in NAMES:
+		got = getattr(new, nm).detach().cpu().numpy()
+		want = g[f'after{epochs}_{nm}']
+		d_ref, d_got = want - before[nm], got - before[nm]
+		assert np.abs(d_ref).max() > 0
+		assert rel_err(got, want) < 1e-5, nm	# trajectory
+		assert rel_err(d_got, d_ref) < 2e-2, (nm, rel_err(d_got, d_ref))	# the updates themselves (same bound as fused vs unfused)
+	assert new.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
