@@ -102,3 +102,42 @@ def test_taylor_green_is_steady():
 	div = (g[:, 0, 0] + g[:, 1, 1]).abs().mean()
 	vor = (g[:, 1, 0] - g[:, 0, 1]).abs().mean()
 	assert float(div / vor) < .1
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('epochs', [1, 3])
+def test_project_matches_reference_golden(fused, epochs):
+	"""the 2D per-timestep optimisation against the reference's OWN project() (2D/advance.py:186-291: value samples on obstacles,
+	normal samples, PCGrad, autograd regularisers with the position-drift term, 4 x Adam, 4 x ReduceLROnPlateau, grid rebuild) run on
+	its own GaussianSplattingFast through the Taichi shim with recorded batches (tests/golden/make_golden_project2d.py)"""
+	from helpers import load_golden, rel_err
+	from gaussian_fluids_code_b200 import advance2d, gsr2d
+	gsr2d.device = torch.device('cuda', 0)
+	g = load_golden('ref2d_project.npz')
+	dom = tuple(float(v) for v in g['domain'])
+
+	def field(P):
+		gv = gsr2d.GaussianSplattingFast(*dom, P, dim=2)
+		assert gv.min_grid_scale == pytest.approx(float(g['min_grid_scale']), rel=1e-12) and gv.clamp_threshold == float(g['tau'])
+		with torch.no_grad():
+			gv.scalings.copy_(torch.tensor(g['scalings'])); gv.rotations.copy_(torch.tensor(g['rotations'])); gv.values.copy_(torch.tensor(g['values']))
+		gv.reinitialize_grid()
+		gv.zero_grad()
+		return gv
+	cur, new = field(g['cur_positions']), field(g['new_positions'])
+	ref = advance2d.AdvectedCovectorField(cur, cur, float(g['dt']), domain=dom)	# taylor_vortex: scale factor 1
+	T = lambda a: torch.tensor(a, device='cuda')
+	datas = iter([T(x) for x in g['samples']])
+	g1 = iter([(T(d), T(v)) for d, v in zip(g['b1_data'], g['b1_val'])])
+	g2 = iter([(T(d), T(n), T(r)) for d, n, r in zip(g['b2_data'], g['b2_normal'], g['b2_ref'])])
+	advance2d.project(new, ref, lambda n, gv: next(datas), lambda gv: None, boundary_generator_1=lambda n: next(g1), boundary_generator_2=lambda n: next(g2),
+					  boundary_lambda=float(g['boundary_lambda']), batch_size=g['b1_data'].shape[1], max_epoch=epochs, patience=500, verbose=0, fused=fused)
+	before = dict(positions=g['new_positions'], scalings=g['scalings'], rotations=g['rotations'], values=g['values'])
+	for nm in ('positions', 'scalings', 'rotations', 'values'):
+		got = getattr(new, nm).detach().cpu().numpy().reshape(before[nm].shape)
+		want = g[f'after{epochs}_{nm}']
+		d_ref, d_got = want - before[nm], got - before[nm]
+		assert np.abs(d_ref).max() > 0
+		assert rel_err(got, want) < 1e-5, nm
+		assert rel_err(d_got, d_ref) < 2e-2, (nm, rel_err(d_got, d_ref))
+	assert new.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
