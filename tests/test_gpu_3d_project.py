@@ -146,3 +146,31 @@ def test_project_matches_reference_golden(fused, epochs):
 		assert rel_err(got, want) < 1e-5, nm	# trajectory
 		assert rel_err(d_got, d_ref) < 2e-2, (nm, rel_err(d_got, d_ref))	# the updates themselves (same bound as fused vs unfused)
 	assert new.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('epochs', [1, 3])
+def test_fit_matches_reference_golden(fused, epochs):
+	"""the initial fit against the reference's OWN fit_velocity_with_gradient (3D/initialize.py:9-46) run on its own
+	GaussianSplatting3DFast through the Taichi shim with recorded batches and targets (tests/golden/make_golden_fit3d.py)"""
+	from helpers import load_golden
+	from gaussian_fluids_code_b200 import gsr3d, initialize3d
+	gsr3d.device = torch.device('cuda', 0)
+	g = load_golden('ref3d_fit.npz')
+	gv = gsr3d.GaussianSplatting3DFast(0., 1., 0., 1., 0., 1., g['positions'], dim=3)
+	np.testing.assert_allclose([gv.positions_lr, gv.scalings_lr, gv.rotations_lr, gv.values_lr], g['lrs'])	# the class's default learning rates
+	with torch.no_grad():
+		gv.scalings.copy_(torch.tensor(g['scalings'])); gv.rotations.copy_(torch.tensor(g['rotations'])); gv.values.copy_(torch.tensor(g['values']))
+	gv.reinitialize_grid()
+	gv.zero_grad()
+	T = lambda a: torch.tensor(a, device='cuda')
+	datas, vals, grads = iter([T(x) for x in g['samples']]), iter([T(x) for x in g['ref_val']]), iter([T(x) for x in g['ref_grad']])
+	initialize3d.fit_velocity_with_gradient(gv, lambda x: next(vals), lambda x: next(grads), lambda n: next(datas), batch_size=g['samples'].shape[1],
+											max_epoch=epochs, verbose=0, fused=fused)
+	for nm in NAMES:
+		got, want = getattr(gv, nm).detach().cpu().numpy(), g[f'after{epochs}_{nm}']
+		d_ref, d_got = want - g[nm], got - g[nm]
+		assert np.abs(d_ref).max() > 0
+		assert rel_err(got, want) < 1e-5, nm
+		assert rel_err(d_got, d_ref) < 2e-2, (nm, rel_err(d_got, d_ref))
+	assert gv.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
