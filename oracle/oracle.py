@@ -323,3 +323,121 @@ def interp_val(field, positions, domain, real=np.float64, nthreads=0):
 	fn.restype = None
 	fn(_p(f), _p(dims), _p(p), C.c_long(out.size), _p(dom), _p(out), C.c_int(nthreads or os.cpu_count() or 1))
 	return out
+
+
+# ---------------------------------------------------------------------------------------------
+# per-timestep optimisation: project() of 3D/advance.py:183-287 and step() of 3D/GSR.py:144-152, :704-716
+# ---------------------------------------------------------------------------------------------
+
+class _Adam:
+	"""torch.optim.Adam (defaults: betas .9/.999, eps 1e-8, no weight decay) + ReduceLROnPlateau(mode='min', threshold 1e-4 rel,
+	cooldown 0, eps 1e-8) for one parameter tensor, in float64 (torch works in the tensor's float32)"""
+
+	def __init__(self, lr, patience=50, factor=.9):
+		self.lr, self.patience, self.factor = float(lr), patience, factor
+		self.t, self.m, self.v = 0, None, None
+		self.best, self.bad = np.inf, 0
+
+	def step(self, p, g):
+		if self.m is None:
+			self.m, self.v = np.zeros_like(p, np.float64), np.zeros_like(p, np.float64)
+		self.t += 1
+		self.m += (g - self.m) * (1. - .9)
+		self.v = self.v * .999 + (1. - .999) * g * g
+		bc1, bc2 = 1. - .9 ** self.t, 1. - .999 ** self.t
+		return p - (self.lr / bc1) * (self.m / (np.sqrt(self.v) / np.sqrt(bc2) + 1e-8))
+
+	def schedule(self, metric):
+		if metric < self.best * (1. - 1e-4):
+			self.best, self.bad = metric, 0
+		else:
+			self.bad += 1
+		if self.bad > self.patience:
+			new_lr = max(self.lr * self.factor, 0.)
+			if self.lr - new_lr > 1e-8:
+				self.lr = new_lr
+			self.bad = 0
+
+
+def _curl3(J):
+	return np.stack([J[:, 2, 1] - J[:, 1, 2], J[:, 0, 2] - J[:, 2, 0], J[:, 1, 0] - J[:, 0, 1]], axis=1)
+
+
+class OracleProjector3D:
+	"""
+	One `project` phase of 3D/advance.py:183-287 on oracle fields: the advected-covector reference (:24-49) of the previous field,
+	the vorticity / helicity / divergence losses with separate gradient sets and their PCGrad projection (:202-225), the anisotropy
+	and volume regularisers (closed-form gradients; the reference uses autograd, :237-244), the boundary loss (:246-254), the
+	scheduler metric (:256, without the helicity loss), 4 x Adam + 4 x ReduceLROnPlateau (3D/GSR.py:50-71, :144-152) and the grid
+	rebuild with the new grid_scale (:704-716).  Parameters evolve in float64.
+	"""
+	LRS = (3e-4, 1e-5, 3e-4, 1e-5)	# positions, scalings, rotations, values (3D/advance.py:258-261)
+
+	def __init__(self, bounds, params, previous, dt, boundary_lambda, tau, min_grid_scale, precision='f64', nthreads=1):
+		self.bounds, self.dt, self.lam, self.tau, self.mgs = tuple(bounds), float(dt), float(boundary_lambda), float(tau), float(min_grid_scale)
+		self.ext = extended_bounds(3, self.bounds, self.mgs)
+		self.params = [np.array(p, np.float64) for p in params]
+		self.previous = previous	# OracleGSR of the field that advects (static during the phase)
+		self.prec, self.nthreads = precision, nthreads
+		self.opt = [_Adam(lr, patience=50, factor=.9) for lr in self.LRS]
+		self.grid_scale = None
+
+	def _field(self):
+		p = self.params
+		return OracleGSR(3, self.ext, p[0], p[1], p[2], p[3], self.tau, self.mgs, precision=self.prec, nthreads=self.nthreads)
+
+	def iterate(self, data, boundary=None):
+		f = self._field()
+		N = f.N
+		x = np.asarray(data, np.float32)
+		# reference: advected covector field (3D/advance.py:35-47)
+		psi, dpsi, pb_v, pb_dv = self.previous.rk4(x, -self.dt, pos_only=False)
+		pb_vor = _curl3(np.asarray(pb_dv, np.float64))
+		ref_hel = (np.asarray(pb_v, np.float64) * pb_vor).sum(axis=1)
+		ref_vor = np.einsum('qij,qj->qi', np.linalg.inv(np.asarray(dpsi, np.float64)), pb_vor)
+		# losses with separate gradient sets (weights 1, 1, 1)
+		val, grad = f.forward(x)
+		direct, vor, div = f.zero_grads(), f.zero_grads(), f.zero_grads()
+		f.backward3d(x, val, grad, ref_vor=ref_vor, weight_vor=1., ref_hel=ref_hel, weight_hel=1., weight_div=1., direct=direct, vor=vor, div=div)
+		total = [np.asarray(d, np.float64) for d in direct]
+		for k in range(4):	# PCGrad (:202-225)
+			g1, g2 = np.asarray(vor[k], np.float64).copy(), np.asarray(div[k], np.float64).copy()
+			if (g1 * g2).sum() < 0.:
+				n1, n2 = g1 / np.sqrt((g1 ** 2).sum()), g2 / np.sqrt((g2 ** 2).sum())
+				g1, g2 = g1 - (g1 * n2).sum() * n2, g2 - (g2 * n1).sum() * n1
+			total[k] = total[k] + g1 + g2
+		om = _curl3(np.asarray(grad, np.float64))
+		loss_vor = np.abs(om - ref_vor).mean(axis=1).mean()
+		loss_div = ((np.asarray(grad, np.float64)[:, 0, 0] + grad[:, 1, 1] + grad[:, 2, 2]) ** 2).mean()
+		# regularisers (:237-244): 10 * aniso + 10 * vol (+ 0 * |values|)
+		s = self.params[1]
+		ratio = np.exp(s.max(axis=1) - s.min(axis=1))
+		loss_aniso = (np.where(ratio >= 1.5, ratio, 1.5) - 1.5).mean()
+		vol = np.exp(-s.sum(axis=1))
+		r = vol / vol.mean()
+		loss_vol = ((r - 1.) ** 2).mean()
+		gs = np.zeros_like(s)
+		kmax, kmin = s.argmax(axis=1), s.argmin(axis=1)	# first index on ties, like torch
+		on = (ratio >= 1.5) & (kmax != kmin)
+		idx = np.arange(N)
+		gs[idx[on], kmax[on]] += 10. * ratio[on] / N
+		gs[idx[on], kmin[on]] -= 10. * ratio[on] / N
+		gs += (-10. * 2. / N * r * (r - (r ** 2).mean()))[:, None]	# d/ds_k of mean((V/mean V - 1)^2)
+		total[1] = total[1] + gs
+		# boundary loss (:246-254)
+		boundary_constraint = 0.
+		if self.lam and boundary is not None:
+			bx, bn = np.asarray(boundary[0], np.float32), np.asarray(boundary[1], np.float32)
+			bval, _ = f.forward(bx, need_grad=False)
+			bd = f.zero_grads()
+			f.backward3d(bx, bval, np.zeros((bx.shape[0], 3, 3), f.real), normals=bn, weight_boundary=self.lam, direct=bd)
+			for k in range(4):
+				total[k] = total[k] + np.asarray(bd[k], np.float64)
+			boundary_constraint = np.abs((np.asarray(bval, np.float64) * bn).sum(axis=1)).mean()
+		loss_tot = loss_vor + loss_div + 10. * loss_aniso + 10. * loss_vol + self.lam * boundary_constraint	# (:256: no helicity term)
+		# step (3D/GSR.py:144-152, :714-716): Adam x4, schedulers x4 on the same metric, new grid
+		for k in range(4):
+			self.params[k] = self.opt[k].step(self.params[k], total[k])
+			self.opt[k].schedule(float(np.float32(loss_tot)))
+		self.grid_scale = grid_scale_of(self.tau, np.asarray(self.params[1], np.float32), self.mgs, self.ext)
+		return loss_tot

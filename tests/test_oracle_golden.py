@@ -181,3 +181,26 @@ def test_density_resampling_oracle_matches_reference_golden():
 	assert np.abs(bk - g['backtraced_f64']).max() < 1e-6	# lattice coordinates: float32 linspace here, float64 in the f64 golden run
 	got = orc.interp_val(g['smooth_density_f64'], bk, dom, real=np.float64)
 	assert np.abs(got - g['smooth_next_f64']).max() < 2e-5
+
+
+@pytest.mark.parametrize('epochs', [1, 3])
+def test_optimisation_oracle_matches_reference_project(epochs):
+	"""the oracle's restatement of project() + step() (OracleProjector3D: PCGrad, closed-form regulariser gradients, Adam,
+	ReduceLROnPlateau, grid_scale) against the reference's OWN project() run through the shim (tests/golden/make_golden_project3d.py)"""
+	import os
+	import oracle.oracle as orc
+	g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref3d_project.npz')))
+	tau, mgs = float(g['tau']), float(g['min_grid_scale'])
+	bounds = (0., 1.) * 3
+	ext = orc.extended_bounds(3, bounds, mgs)
+	prev = orc.OracleGSR(3, ext, g['cur_positions'], g['scalings'], g['rotations'], g['values'], tau, mgs, precision='f64')
+	pr = orc.OracleProjector3D(bounds, [g['new_positions'], g['scalings'], g['rotations'], g['values']], prev, float(g['dt']), float(g['boundary_lambda']), tau, mgs)
+	for k in range(epochs):
+		pr.iterate(g['samples'][k], (g['boundary_data'][k], g['boundary_normal'][k]))
+	before = dict(positions=g['new_positions'], scalings=g['scalings'], rotations=g['rotations'], values=g['values'])
+	for nm, got in zip(('positions', 'scalings', 'rotations', 'values'), pr.params):
+		want = g[f'after{epochs}_{nm}']
+		d_ref, d_got = want.astype(np.float64) - before[nm], got - before[nm]
+		assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
+		assert np.abs(d_got - d_ref).max() <= 2e-2 * np.abs(d_ref).max(), (nm, np.abs(d_got - d_ref).max() / np.abs(d_ref).max())
+	assert pr.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
