@@ -441,3 +441,90 @@ class OracleProjector3D:
 			self.opt[k].schedule(float(np.float32(loss_tot)))
 		self.grid_scale = grid_scale_of(self.tau, np.asarray(self.params[1], np.float32), self.mgs, self.ext)
 		return loss_tot
+
+
+class OracleProjector2D:
+	"""
+	One `project` phase of 2D/advance.py:186-291 on oracle fields: the advected vorticity of the previous field, zero outside the
+	advance domain (:21-56), vorticity / divergence losses with separate gradient sets (get_grad_losses) and their PCGrad projection
+	(:187-193, :226-233), value samples (boundary_generator_1 through get_losses, :221-224), normal samples (boundary_generator_2,
+	:235-239), the anisotropy / volume / position-drift regularisers (:252-260; closed-form gradients), the scheduler metric (:262),
+	4 x Adam + 4 x ReduceLROnPlateau at lr 1e-4 (:264-269) and the grid rebuild.  Parameters evolve in float64.
+	"""
+
+	def __init__(self, bounds, params, previous, dt, boundary_lambda, tau, min_grid_scale, domain, precision='f64', nthreads=1):
+		self.bounds, self.dt, self.lam, self.tau, self.mgs = tuple(bounds), float(dt), float(boundary_lambda), float(tau), float(min_grid_scale)
+		self.domain = tuple(domain)	# the advance domain in GSR space: back-traced points outside it carry no vorticity
+		self.ext = extended_bounds(2, self.bounds, self.mgs)
+		self.params = [np.array(p, np.float64) for p in params]
+		self.positions_org = self.params[0].copy()
+		self.previous = previous
+		self.prec, self.nthreads = precision, nthreads
+		self.opt = [_Adam(1e-4, patience=50, factor=.9) for _ in range(4)]
+		self.grid_scale = None
+
+	def _field(self):
+		p = self.params
+		return OracleGSR(2, self.ext, p[0], p[1], p[2], p[3], self.tau, self.mgs, precision=self.prec, nthreads=self.nthreads)
+
+	def iterate(self, data, boundary_1=None, boundary_2=None):
+		f = self._field()
+		N = f.N
+		x = np.asarray(data, np.float32)
+		bk, _, _, dv = self.previous.rk4(x, -self.dt, pos_only=False)
+		dv = np.asarray(dv, np.float64)
+		ref_vor = dv[:, 1, 0] - dv[:, 0, 1]
+		x0, x1, y0, y1 = self.domain
+		bk = np.asarray(bk, np.float64)
+		ref_vor[(bk[:, 0] < x0) | (bk[:, 0] > x1) | (bk[:, 1] < y0) | (bk[:, 1] > y1)] = 0.
+		val, grad = f.forward(x)
+		direct, vor, div = f.zero_grads(), f.zero_grads(), f.zero_grads()
+		f.backward2d_grad(x, grad, ref_vor=ref_vor, weight_vor=1., weight_div=1., direct=direct, vor=vor, div=div)
+		boundary_constraint = 0.
+		if self.lam > 0. and boundary_1 is not None:
+			bx, bv = np.asarray(boundary_1[0], np.float32), np.asarray(boundary_1[1], np.float32)
+			out, _ = f.forward(bx, need_grad=False)
+			f.backward2d_val(bx, out, ref=bv, weight=self.lam, direct=direct)
+			boundary_constraint += np.abs(np.asarray(out, np.float64) - bv).mean()
+		total = [np.asarray(d, np.float64).copy() for d in direct]
+		for k in range(4):
+			g1, g2 = np.asarray(vor[k], np.float64).copy(), np.asarray(div[k], np.float64).copy()
+			if (g1 * g2).sum() < 0.:
+				n1, n2 = g1 / np.sqrt((g1 ** 2).sum()), g2 / np.sqrt((g2 ** 2).sum())
+				g1, g2 = g1 - (g1 * n2).sum() * n2, g2 - (g2 * n1).sum() * n1
+			total[k] = total[k] + g1 + g2
+		if self.lam > 0. and boundary_2 is not None:
+			bx, bn, br = [np.asarray(a, np.float32) for a in boundary_2]
+			out, _ = f.forward(bx, need_grad=False)
+			bd = f.zero_grads()
+			f.backward2d_val(bx, out, normals=bn, normal_ref=br, weight_boundary=self.lam, direct=bd)
+			for k in range(4):
+				total[k] = total[k] + np.asarray(bd[k], np.float64)
+			boundary_constraint += np.abs((np.asarray(out, np.float64) * bn).sum(axis=1) - br).mean()
+		grad = np.asarray(grad, np.float64)
+		loss_vor = np.abs(grad[:, 1, 0] - grad[:, 0, 1] - ref_vor).mean()
+		loss_div = ((grad[:, 0, 0] + grad[:, 1, 1]) ** 2).mean()
+		s = self.params[1]
+		ratio = np.exp(s.max(axis=1) - s.min(axis=1))
+		loss_aniso = (np.where(ratio >= 1.5, ratio, 1.5) - 1.5).mean()
+		vol = np.exp(-s.sum(axis=1))
+		r = vol / vol.mean()
+		loss_vol = ((r - 1.) ** 2).mean()
+		gs = np.zeros_like(s)
+		kmax, kmin = s.argmax(axis=1), s.argmin(axis=1)
+		on = (ratio >= 1.5) & (kmax != kmin)
+		idx = np.arange(N)
+		gs[idx[on], kmax[on]] += 10. * ratio[on] / N
+		gs[idx[on], kmin[on]] -= 10. * ratio[on] / N
+		gs += (-10. * 2. / N * r * (r - (r ** 2).mean()))[:, None]
+		total[1] = total[1] + gs
+		dpos = self.params[0] - self.positions_org
+		loss_delta_pos = (dpos ** 2).mean()
+		total[0] = total[0] + .5 * 2. * dpos / dpos.size
+		loss_tot = loss_vor + loss_div + 10. * loss_aniso + 10. * loss_vol + .5 * loss_delta_pos + self.lam * boundary_constraint
+		for k in range(4):
+			shape = self.params[k].shape
+			self.params[k] = self.opt[k].step(self.params[k], total[k].reshape(shape))
+			self.opt[k].schedule(float(np.float32(loss_tot)))
+		self.grid_scale = grid_scale_of(self.tau, np.asarray(self.params[1], np.float32), self.mgs, self.ext)
+		return loss_tot

@@ -204,3 +204,26 @@ def test_optimisation_oracle_matches_reference_project(epochs):
 		assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
 		assert np.abs(d_got - d_ref).max() <= 2e-2 * np.abs(d_ref).max(), (nm, np.abs(d_got - d_ref).max() / np.abs(d_ref).max())
 	assert pr.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
+
+
+@pytest.mark.parametrize('epochs', [1, 3])
+def test_optimisation_oracle_matches_reference_project_2d(epochs):
+	"""OracleProjector2D against the reference's OWN 2D project() run through the shim (tests/golden/make_golden_project2d.py)"""
+	import os
+	import oracle.oracle as orc
+	g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref2d_project.npz')))
+	tau, mgs = float(g['tau']), float(g['min_grid_scale'])
+	dom = tuple(float(v) for v in g['domain'])
+	ext = orc.extended_bounds(2, dom, mgs)
+	prev = orc.OracleGSR(2, ext, g['cur_positions'], g['scalings'], g['rotations'], g['values'], tau, mgs, precision='f64')
+	pr = orc.OracleProjector2D(dom, [g['new_positions'], g['scalings'], g['rotations'], g['values']], prev, float(g['dt']), float(g['boundary_lambda']), tau, mgs, dom)
+	for k in range(epochs):
+		pr.iterate(g['samples'][k], (g['b1_data'][k], g['b1_val'][k]), (g['b2_data'][k], g['b2_normal'][k], g['b2_ref'][k]))
+	before = dict(positions=g['new_positions'], scalings=g['scalings'], rotations=g['rotations'], values=g['values'])
+	for nm, got in zip(('positions', 'scalings', 'rotations', 'values'), pr.params):
+		want = g[f'after{epochs}_{nm}']
+		got = got.reshape(want.shape)
+		d_ref, d_got = want.astype(np.float64) - before[nm], got - before[nm]
+		assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
+		assert np.abs(d_got - d_ref).max() <= 2e-2 * np.abs(d_ref).max(), (nm, np.abs(d_got - d_ref).max() / np.abs(d_ref).max())
+	assert pr.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
