@@ -227,3 +227,23 @@ def test_optimisation_oracle_matches_reference_project_2d(epochs):
 		assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
 		assert np.abs(d_got - d_ref).max() <= 2e-2 * np.abs(d_ref).max(), (nm, np.abs(d_got - d_ref).max() / np.abs(d_ref).max())
 	assert pr.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
+
+
+@pytest.mark.parametrize('epochs', [1, 3])
+def test_fit_oracle_matches_reference_fit(epochs):
+	"""OracleFit3D against the reference's OWN fit_velocity_with_gradient run through the shim (tests/golden/make_golden_fit3d.py)"""
+	import os
+	import oracle.oracle as orc
+	g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref3d_fit.npz')))
+	bounds = (0., 1.) * 3
+	N = g['positions'].shape[0]
+	mgs = orc.default_min_grid_scale(3, bounds, N)
+	fit = orc.OracleFit3D(bounds, [g['positions'], g['scalings'], g['rotations'], g['values']], g['lrs'], 5e-3, mgs)
+	for k in range(epochs):
+		fit.iterate(g['samples'][k], g['ref_val'][k], g['ref_grad'][k])
+	for nm, got in zip(('positions', 'scalings', 'rotations', 'values'), fit.params):
+		want = g[f'after{epochs}_{nm}']
+		d_ref, d_got = want.astype(np.float64) - g[nm], got - g[nm]
+		assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
+		assert np.abs(d_got - d_ref).max() <= 2e-2 * np.abs(d_ref).max(), (nm, np.abs(d_got - d_ref).max() / np.abs(d_ref).max())
+	assert fit.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
