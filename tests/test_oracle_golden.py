@@ -247,3 +247,32 @@ def test_fit_oracle_matches_reference_fit(epochs):
 		assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
 		assert np.abs(d_got - d_ref).max() <= 2e-2 * np.abs(d_ref).max(), (nm, np.abs(d_got - d_ref).max() / np.abs(d_ref).max())
 	assert fit.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
+
+
+def test_oracle_adam_and_plateau_scheduler_match_torch():
+	"""the oracle's Adam / ReduceLROnPlateau restatement (oracle._Adam) against torch.optim on a random gradient and metric
+	sequence long enough for the scheduler to fire several times (the project goldens are too short for that)"""
+	import torch
+	import oracle.oracle as orc
+	rng = np.random.default_rng(11)
+	p0 = rng.normal(size=(7, 3))
+	t = torch.tensor(p0, dtype=torch.float64, requires_grad=True)
+	opt = torch.optim.Adam([t], lr=3e-3)
+	sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=.9, patience=4)
+	mine = orc._Adam(3e-3, patience=4, factor=.9)
+	p = p0.copy()
+	metric = 1.
+	fired = 0
+	for k in range(200):
+		g = rng.normal(size=p0.shape) * (1. if k % 7 else 1e-9)	# now and then a vanishing gradient: the eps term matters
+		metric = metric * (.97 if (k // 20) % 2 == 0 else 1.01)	# improving, then stagnating, in turns
+		t.grad = torch.tensor(g)
+		opt.step()
+		sch.step(metric)
+		p = mine.step(p, g)
+		lr_before = mine.lr
+		mine.schedule(metric)
+		fired += mine.lr != lr_before
+		assert mine.lr == pytest.approx(opt.param_groups[0]['lr'], rel=1e-12), k
+		np.testing.assert_allclose(p, t.detach().numpy(), rtol=1e-10, atol=1e-14)
+	assert fired >= 3
