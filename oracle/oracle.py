@@ -571,3 +571,49 @@ class OracleFit3D:
 			self.opt[k].schedule(float(np.float32(loss)))
 		self.grid_scale = grid_scale_of(self.tau, np.asarray(self.params[1], np.float32), self.mgs, self.ext)
 		return loss
+
+
+class OracleFit2D:
+	"""fit_velocity_with_gradient of 2D/initialize.py:10-41 on oracle fields: value loss (get_losses, weight 1) and gradient loss
+	(get_grad_losses, weight_grad 1) into one gradient set, anisotropy and volume regularisers with weight 1, Adam x4 +
+	ReduceLROnPlateau x4 (factor .9, patience 50) at the learning rates set by the caller, grid rebuild"""
+
+	def __init__(self, bounds, params, lrs, tau, min_grid_scale, precision='f64', nthreads=1):
+		self.bounds, self.tau, self.mgs = tuple(bounds), float(tau), float(min_grid_scale)
+		self.ext = extended_bounds(2, self.bounds, self.mgs)
+		self.params = [np.array(p, np.float64) for p in params]
+		self.prec, self.nthreads = precision, nthreads
+		self.opt = [_Adam(lr, patience=50, factor=.9) for lr in lrs]
+		self.grid_scale = None
+
+	def iterate(self, data, ref_val, ref_grad):
+		p = self.params
+		f = OracleGSR(2, self.ext, p[0], p[1], p[2], p[3], self.tau, self.mgs, precision=self.prec, nthreads=self.nthreads)
+		N = f.N
+		x = np.asarray(data, np.float32)
+		val, grad = f.forward(x)
+		direct = f.zero_grads()
+		f.backward2d_val(x, val, ref=ref_val, weight=1., direct=direct)
+		f.backward2d_grad(x, grad, ref_grad=ref_grad, weight_grad=1., direct=direct)
+		total = [np.asarray(d, np.float64).copy() for d in direct]
+		s = p[1]
+		ratio = np.exp(s.max(axis=1) - s.min(axis=1))
+		loss_aniso = (np.where(ratio >= 1.5, ratio, 1.5) - 1.5).mean()
+		vol = np.exp(-s.sum(axis=1))
+		r = vol / vol.mean()
+		loss_vol = ((r - 1.) ** 2).mean()
+		gs = np.zeros_like(s)
+		kmax, kmin = s.argmax(axis=1), s.argmin(axis=1)
+		on = (ratio >= 1.5) & (kmax != kmin)
+		idx = np.arange(N)
+		gs[idx[on], kmax[on]] += ratio[on] / N
+		gs[idx[on], kmin[on]] -= ratio[on] / N
+		gs += (-2. / N * r * (r - (r ** 2).mean()))[:, None]
+		total[1] = total[1] + gs
+		loss = np.abs(np.asarray(val, np.float64) - ref_val).mean() + np.abs(np.asarray(grad, np.float64) - ref_grad).mean() + loss_aniso + loss_vol
+		for k in range(4):
+			shape = self.params[k].shape
+			self.params[k] = self.opt[k].step(self.params[k], total[k].reshape(shape))
+			self.opt[k].schedule(float(np.float32(loss)))
+		self.grid_scale = grid_scale_of(self.tau, np.asarray(self.params[1], np.float32), self.mgs, self.ext)
+		return loss

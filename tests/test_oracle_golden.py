@@ -276,3 +276,22 @@ def test_oracle_adam_and_plateau_scheduler_match_torch():
 		assert mine.lr == pytest.approx(opt.param_groups[0]['lr'], rel=1e-12), k
 		np.testing.assert_allclose(p, t.detach().numpy(), rtol=1e-10, atol=1e-14)
 	assert fired >= 3
+
+
+@pytest.mark.parametrize('epochs', [1, 3])
+def test_fit_oracle_matches_reference_fit_2d(epochs):
+	"""OracleFit2D against the reference's OWN 2D fit_velocity_with_gradient run through the shim (tests/golden/make_golden_fit2d.py)"""
+	import os
+	import oracle.oracle as orc
+	g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref2d_fit.npz')))
+	dom = tuple(float(v) for v in g['domain'])
+	fit = orc.OracleFit2D(dom, [g['positions'], g['scalings'], g['rotations'], g['values']], g['lrs'], float(g['tau']), float(g['min_grid_scale']))
+	for k in range(epochs):
+		fit.iterate(g['samples'][k], g['ref_val'][k], g['ref_grad'][k])
+	for nm, got in zip(('positions', 'scalings', 'rotations', 'values'), fit.params):
+		want = g[f'after{epochs}_{nm}']
+		got = got.reshape(want.shape)
+		d_ref, d_got = want.astype(np.float64) - g[nm], got - g[nm]
+		assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
+		assert np.abs(d_got - d_ref).max() <= 2e-2 * np.abs(d_ref).max(), (nm, np.abs(d_got - d_ref).max() / np.abs(d_ref).max())
+	assert fit.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
