@@ -35,7 +35,8 @@ class StepCfg(C.Structure):
 				('sched_patience', C.c_int32),
 				('w_aniso', C.c_float), ('w_vol', C.c_float), ('w_valreg', C.c_float), ('w_dpos', C.c_float),
 				('aniso_ratio', C.c_float), ('pcgrad', C.c_int32),
-				('grid_coef', C.c_double), ('min_grid_scale', C.c_double), ('grid_scale_tau0', C.c_double)]
+				('grid_coef', C.c_double), ('min_grid_scale', C.c_double), ('grid_scale_tau0', C.c_double),
+				('keep_clock', C.c_int32), ('grid_scale_out', C.c_void_p)]
 
 
 class LossSrc(C.Structure):
@@ -45,6 +46,7 @@ class LossSrc(C.Structure):
 # indices into the device-resident optimiser state (include/gsr_b200.h)
 STATE_SCALARS = 64
 ST_T, ST_BEST, ST_BAD, ST_LR, ST_GRID_SCALE, ST_MIN_S, ST_LOSS_TOT, ST_L_ANISO, ST_L_VOL, ST_L_VALREG, ST_L_DPOS = 0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 13
+ST_CLOCK = 22
 
 
 class GsrError(RuntimeError):

@@ -2,13 +2,21 @@
 Drop-in replacement of the reference's 3D/advance.py: AdvectedCovectorField, clone_velocity_field,
 advect_covector_field and project keep their names, arguments and behaviour.
 
-project() has two implementations of the same iteration:
-  * fused=True (default): the whole iteration stays on the device — sample binning, RK4 pull-back of the previous
-    field, forward, atomics-free backward, boundary pass, then ONE fused step (PCGrad projection, closed-form
-    regularisers, Adam x4, ReduceLROnPlateau x4, next grid_scale) and the hash rebuild; the host reads scalars only
-    every `check_iter` iterations for the early-stop rule.
+project() has three executions of the same iteration:
+  * pipelined (fused=True and the STOCK generators of this module — BoxSampler / LatticeGenerator / BoxSurfaceSampler, the
+    objects advance() builds, standing for default_data_generator / default_test_generator / sample_on_box of
+    3D/advance.py:339-342 and 3D/init_cond.py:227-249): the samples are drawn on the device by counter-based Philox kernels,
+    ten iterations form one captured CUDA graph with the pull-back, the forward pass and the boundary pass on forked streams
+    (timestep3d.ShardedProjector), the host only replays the graph and reads three numbers every `check_iter` iterations for
+    the early-stop rule.  This is the measured path of bench.py.
+  * fused=True with arbitrary generator callables: the same device-resident iteration (sample binning, RK4 pull-back of the
+    previous field, forward, atomics-free backward, boundary pass, then ONE fused step — PCGrad projection, closed-form
+    regularisers, Adam x4, ReduceLROnPlateau x4, next grid_scale — and the hash rebuild), launched eagerly because the
+    generators run on the host side every iteration.
   * fused=False: the reference's structure (get_losses + torch autograd regularisers + torch.optim) on top of the
     same CUDA kernels — >= 8 host syncs per iteration like the reference; kept for API fidelity and as a cross-check.
+
+advance() / advance_frame() are the time loop of 3D/advance.py:381-393 as functions (the reference runs it at module level).
 
 Deliberate deviations from the reference, both in clone_velocity_field: `test_data` is
 generated before its first use, and the neighbour mask is converted to bool before `~` (the 2D reference does both).
@@ -51,6 +59,53 @@ class AdvectedCovectorField:
 		return self.velocity_field.advected_vorticity(x, self.time_step, need_hel=need_hel)
 
 
+
+# ---- the stock generators of the reference's driver, as objects that project() recognises ----------------------------------------
+class BoxSampler:
+	"""default_data_generator of 3D/advance.py:339-340: one uniform sample per Gaussian in the box (`n` is ignored there too)"""
+
+	def __init__(self, x_min, x_max, y_min, y_max, z_min, z_max):
+		self.box = (float(x_min), float(x_max), float(y_min), float(y_max), float(z_min), float(z_max))
+		self.gsr_sampler = ('box', self.box)
+
+	def __call__(self, n, gaussian_splatting, restrict=None):
+		b, dev = self.box, _dev()
+		return (torch.rand_like(gaussian_splatting.positions.detach(), device=dev) * torch.tensor([b[1] - b[0], b[3] - b[2], b[5] - b[4]], device=dev)
+				+ torch.tensor([b[0], b[2], b[4]], device=dev))
+
+
+class LatticeGenerator:
+	"""default_test_generator of 3D/advance.py:341-342: the visualisation lattice (the same tensor on every call, so the engine
+	keeps its ordering); `points` may hold this process's share of the lattice in a sharded run"""
+
+	def __init__(self, x_min, x_max, y_min, y_max, z_min, z_max, x_N, y_N, z_N, points=None, total=None):
+		self.args = (x_min, x_max, y_min, y_max, z_min, z_max, x_N, y_N, z_N)
+		self._points = points
+		self.total = int(total if total is not None else x_N * y_N * z_N)	# points of the whole lattice (all processes)
+
+	def __call__(self, gaussian_splatting=None):
+		if self._points is None:
+			self._points = get_grid_points(*self.args)
+		return self._points
+
+
+class BoxSurfaceSampler:
+	"""sample_on_box (3D/init_cond.py:227-249) on a fixed box: n points on the faces with inward normals"""
+
+	def __init__(self, x_min, x_max, y_min, y_max, z_min, z_max):
+		self.box = (float(x_min), float(x_max), float(y_min), float(y_max), float(z_min), float(z_max))
+		self.gsr_sampler = ('box_surface', self.box)
+
+	def __call__(self, n):
+		from .init_cond3d import sample_on_box
+		return sample_on_box(n, *self.box)
+
+
+def _stock(gen, kind):
+	tag = getattr(gen, 'gsr_sampler', None)
+	return tag is not None and tag[0] == kind
+
+
 def _regularisers(scalings, stop_gradient=None):
 	"""anisotropy hinge at ratio 1.5 and volume uniformity (3D/advance.py:107-115, :237-241)"""
 	aniso_ratio = 1.5
@@ -72,8 +127,16 @@ def clone_velocity_field(res, velocity_field, x_min, x_max, y_min, y_max, z_min,
 	"""copy velocity_field into res, split over-stretched Gaussians and refit the new ones (3D/advance.py:51-165)"""
 	device = _dev()
 	with torch.no_grad():
-		res.positions, res.scalings = velocity_field.positions.clone(), velocity_field.scalings.clone()
-		res.rotations, res.values = velocity_field.rotations.clone(), velocity_field.values.clone()
+		same = res is not velocity_field and all(getattr(res, nm).shape == getattr(velocity_field, nm).shape and getattr(res, nm).requires_grad
+												 for nm in ('positions', 'scalings', 'rotations', 'values'))
+		if same:
+			# copy INTO res's tensors: the values are what the reference's `.clone()` gives, and the storage stays where a captured
+			# iteration graph of this field expects it (a split below still replaces the tensors, as in the reference)
+			for nm in ('positions', 'scalings', 'rotations', 'values'):
+				getattr(res, nm).copy_(getattr(velocity_field, nm))
+		else:
+			res.positions, res.scalings = velocity_field.positions.clone(), velocity_field.scalings.clone()
+			res.rotations, res.values = velocity_field.rotations.clone(), velocity_field.values.clone()
 		res.N = res.positions.shape[0]
 		stop_gradient = torch.ones((res.N,), dtype=torch.bool, device=device)
 		lo = torch.tensor([res.x_min, res.y_min, res.z_min], dtype=torch.float32, device=device)
@@ -86,6 +149,9 @@ def clone_velocity_field(res, velocity_field, x_min, x_max, y_min, y_max, z_min,
 				print(f'Add {need_split.sum()} particles. {ratio.max()}')
 			if not need_split.any():
 				break
+			if same:	# leave the shared storage alone from here on
+				res.positions, res.scalings, res.rotations, res.values = [getattr(res, nm).detach().clone() for nm in ('positions', 'scalings', 'rotations', 'values')]
+				same = False
 			prec = res.get_variances()[need_split]
 			new_pos = torch.distributions.MultivariateNormal(res.positions[need_split], precision_matrix=(prec + prec.transpose(-1, -2)) * .5).sample((2,)).flatten(0, 1)
 			new_pos.clamp_(lo, hi)
@@ -162,8 +228,12 @@ def advect_covector_field(covector_field, velocity_field, dt, x_min=None, x_max=
 	if x_min is not None:
 		device = _dev()
 		new_positions.clamp_(torch.tensor([x_min, y_min, z_min], dtype=torch.float32, device=device), torch.tensor([x_max, y_max, z_max], dtype=torch.float32, device=device))
-	new_positions.requires_grad_()
-	covector_field.positions = new_positions
+	if covector_field.positions.requires_grad and covector_field.positions.shape == new_positions.shape:
+		with torch.no_grad():
+			covector_field.positions.copy_(new_positions)	# same values as the reference's rebinding, same storage for captured graphs
+	else:
+		new_positions.requires_grad_()
+		covector_field.positions = new_positions
 	covector_field.zero_grad()
 
 
@@ -266,13 +336,21 @@ class FusedProjector:
 
 def project(gaussian_velocity, reference_field, x_min, x_max, y_min, y_max, z_min, z_max, data_generator, test_data_generator,
 			boundary_generator=None, boundary_lambda=0., batch_size=8192, max_epoch=3000, patience=500, verbose=1, frame_id=None,
-			fused=True, check_iter=100, history=None):
+			fused=True, check_iter=100, history=None, pipelined=None, rank=0, world=1, lattice_world=None, sample_seed=42, census=None, probe=None,
+			use_graph=True):
 	"""
 	Solve one time step's projection by first-order optimisation (3D/advance.py:182-316): fit the vorticity and helicity
 	of the advected covector field while driving the divergence to zero.  Early stop: every `check_iter` iterations the
 	test losses must improve by 0.1 %, or `patience` iterations without improvement on all three end the phase.
 	Returns the number of iterations run.  (The reference's loss-curve PNG, :317-331, is not produced; pass a dict as
 	`history` to collect the same series.)
+
+	Beyond the reference's signature: `pipelined` (None = automatically when the generators are this module's stock objects)
+	selects the captured-graph execution; rank / world shard the samples over processes (the losses are means over samples, so the
+	normalisers use the global counts and ONE exchange per iteration sums the gradient accumulators: timestep3d); lattice_world
+	(default: world) is the number of processes that share the test lattice — the test generator then returns this process's share
+	and carries the whole lattice's point count in `.total`; sample_seed keys the device sample generators; census / probe /
+	use_graph are measurement hooks of bench.py.
 	"""
 	gv = gaussian_velocity
 	gv.positions_lr, gv.scalings_lr, gv.rotations_lr, gv.values_lr = [PROJECT_LRS[k] for k in ('positions', 'scalings', 'rotations', 'values')]
@@ -282,6 +360,18 @@ def project(gaussian_velocity, reference_field, x_min, x_max, y_min, y_max, z_mi
 	if not fused:
 		return _project_unfused(gv, reference_field, data_generator, test_data_generator, boundary_generator, boundary_lambda,
 								batch_size, max_epoch, patience, verbose, check_iter, history)
+	use_boundary = bool(boundary_lambda and boundary_generator)
+	stock = _stock(data_generator, 'box') and (not use_boundary or _stock(boundary_generator, 'box_surface'))
+	if pipelined is None:
+		pipelined = stock
+	if pipelined:
+		if not stock:
+			raise ValueError('the pipelined projection draws its samples on the device: pass BoxSampler / BoxSurfaceSampler generators')
+		return _project_pipelined(gv, reference_field, data_generator, test_data_generator, boundary_generator if use_boundary else None, boundary_lambda,
+								  batch_size, max_epoch, patience, verbose, check_iter, history, rank, world, world if lattice_world is None else lattice_world,
+								  sample_seed, census, probe, use_graph)
+	if world > 1:
+		raise ValueError('sharded projection needs the pipelined path')
 	fp = FusedProjector(gv, reference_field, boundary_lambda if boundary_generator else 0., patience=50)
 	names = ('loss_vor', 'loss_hel', 'loss_div')
 	if verbose:
@@ -319,6 +409,138 @@ def project(gaussian_velocity, reference_field, x_min, x_max, y_min, y_max, z_mi
 			print('[projection] Total epoch:', max_epoch, '(Reached maximum iteration number)')
 	fp.finish()
 	return epochs
+
+
+class _EarlyStop:
+	"""the stopping rule of 3D/advance.py:289-314: every test, a loss must improve by 0.1 % or its stale counter grows"""
+
+	def __init__(self, names, patience, check_iter):
+		self.names, self.patience, self.check_iter = names, patience, check_iter
+		self.best = {k: np.inf for k in names}
+		self.stale = {k: 0 for k in names}
+
+	def update(self, cur):
+		for k in self.names:
+			if cur[k] < self.best[k] * (1. - 1e-3):
+				self.best[k], self.stale[k] = cur[k], 0
+			else:
+				self.stale[k] += self.check_iter
+		return all(self.stale[k] >= self.patience for k in self.names)
+
+
+def _project_pipelined(gv, reference_field, data_generator, test_data_generator, boundary_generator, boundary_lambda, batch_size, max_epoch, patience,
+					   verbose, check_iter, history, rank, world, lattice_world, sample_seed, census, probe, use_graph):
+	"""project() on the captured, pipelined iteration (timestep3d.ShardedProjector).  The projector of a (field, previous field)
+	pair — buffers, optimiser state, the captured graph — is kept on the field object and reused by every later time step."""
+	from . import timestep3d
+	cur = reference_field.velocity_field
+	box = data_generator.gsr_sampler[1]
+	bbox = boundary_generator.gsr_sampler[1] if boundary_generator is not None else None
+	lam = float(boundary_lambda) if boundary_generator is not None else 0.
+	key = (id(cur), gv.N, int(batch_size), lam, box, bbox, float(reference_field.time_step), rank, world, int(sample_seed))
+	cache = gv.__dict__.setdefault('_pipelines', {})
+	fp = cache.get(key)
+	if fp is None:
+		cache.clear()	# one live projector per field: its buffers are sized by N and its graph holds this pair's pointers
+		fp = timestep3d.ShardedProjector(gv, reference_field, lam, gv.N, int(batch_size), world=world, rank=rank, box=box, boundary_box=bbox, seed=int(sample_seed))
+		cache[key] = fp
+	else:
+		fp.ref = reference_field
+		fp.restart()
+	fp.lattice_world = lattice_world
+	names = ('loss_vor', 'loss_hel', 'loss_div')
+	test = test_data_generator(gv)
+	total = getattr(test_data_generator, 'total', None)
+	if verbose:
+		t = fp.evaluate_global(test, total).tolist()
+		print(f'[projection] loss_vor: {t[0]}, loss_hel: {t[1]}, loss_div: {t[2]}')
+	stop = _EarlyStop(names, patience, check_iter)
+	st_time = time.time()
+	fp.begin(census)
+	epochs, done = max_epoch, 0
+	while done < max_epoch:
+		n = min(check_iter, max_epoch - done)
+		fp.run_iterations(n, census=census, use_graph=use_graph)
+		done += n
+		if n < check_iter:
+			break
+		t = fp.evaluate_global(test_data_generator(gv), total, probe=probe, census=census).tolist()	# the only host sync of the loop
+		cur_l = dict(zip(names, t[:3]))
+		if history is not None:
+			history.setdefault('test', []).append(cur_l)
+			history.setdefault('state', []).append(fp.stepper.scalars()[:16])
+		if verbose:
+			print(f'[projection] loss_vor: {t[0]}, loss_hel: {t[1]}, loss_div: {t[2]}, time: {time.time() - st_time}')
+			st_time = time.time()
+		if stop.update(cur_l):
+			epochs = done
+			if verbose:
+				print('[projection] Total epoch:', epochs)
+			break
+	else:
+		if verbose:
+			print('[projection] Total epoch:', max_epoch, '(Reached maximum iteration number)')
+	fp.finish()
+	return epochs
+
+
+def advance_frame(gaussian_velocity, new_gaussian_velocity, x_min, x_max, y_min, y_max, z_min, z_max, time_step, data_generator, test_data_generator,
+				  boundary_generator=None, boundary_lambda=0., frame_id=None, max_epoch=20000, patience=500, verbose=1, fields=True, **project_kw):
+	"""
+	One pass of the reference's time loop (3D/advance.py:383-387, :389-390): clone (split over-stretched Gaussians), advect the
+	Gaussians, project, swap; then the two output fields of the frame on the test lattice — |vorticity| and divergence, what the
+	reference hands to write_vti.  Returns (gaussian_velocity, new_gaussian_velocity, epochs, (vorticity_norm, divergence) | None):
+	the first is the field of the new frame.
+	"""
+	gv, new = gaussian_velocity, new_gaussian_velocity
+	clone_velocity_field(new, gv, x_min, x_max, y_min, y_max, z_min, z_max, data_generator, test_data_generator, reinitialize=False, max_epoch=20000, verbose=verbose)
+	advect_covector_field(new, gv, time_step, new.x_min, new.x_max, new.y_min, new.y_max, new.z_min, new.z_max)
+	epochs = project(new, AdvectedCovectorField(gv, gv, time_step, x_min, x_max, y_min, y_max, z_min, z_max), x_min, x_max, y_min, y_max, z_min, z_max,
+					 data_generator, test_data_generator, boundary_lambda=boundary_lambda, boundary_generator=boundary_generator, max_epoch=max_epoch,
+					 patience=patience, verbose=verbose, frame_id=frame_id, **project_kw)
+	gv, new = new, gv
+	out = None
+	if fields:
+		lattice = test_data_generator(gv)
+		vor = curl(gv.gradient(lattice)).norm(dim=-1)	# the reference evaluates the gradient once per written field (:374-377, :389-390)
+		div = gv.gradient(lattice).diagonal(dim1=-2, dim2=-1).sum(dim=-1)
+		census = project_kw.get('census')
+		if census is not None:
+			census.count(gv._engine, lattice, 2, lattice=True)
+		out = (vor, div)
+	return gv, new, epochs, out
+
+
+def advance(gaussian_velocity, new_gaussian_velocity, x_min, x_max, y_min, y_max, z_min, z_max, time_step, last_time, boundary_generator=None,
+			boundary_lambda=0., visualize_res=(128, 128, 128), out_dir=None, start_frame=0, max_epoch=20000, patience=500, verbose=1, on_frame=None,
+			**project_kw):
+	"""
+	The time loop of 3D/advance.py:381-393: frames until `last_time`, each one advance_frame() with the stock generators; with
+	`out_dir` the frame's vorticity_<k>.vti, divergence_<k>.vti and gaussian_velocity_<k>.pt are written as the reference does;
+	`on_frame(k, field, vorticity_norm, divergence)` is called after every frame.  Returns the two field objects (current first).
+	"""
+	import os
+	data_gen = BoxSampler(x_min, x_max, y_min, y_max, z_min, z_max)
+	test_gen = LatticeGenerator(x_min, x_max, y_min, y_max, z_min, z_max, *visualize_res)
+	gv, new = gaussian_velocity, new_gaussian_velocity
+	seed0 = int(project_kw.pop('sample_seed', 42))
+	seeds = {id(gv): seed0, id(new): seed0 + 1}	# the two fields alternate as the optimised one: each keeps its own sample stream
+	t, cnt = 0., start_frame + 1
+	while t < last_time:
+		gv, new, _, (vor, div) = advance_frame(gv, new, x_min, x_max, y_min, y_max, z_min, z_max, time_step, data_gen, test_gen, boundary_generator=boundary_generator,
+											   boundary_lambda=boundary_lambda, frame_id=cnt, max_epoch=max_epoch, patience=patience, verbose=verbose,
+											   sample_seed=seeds[id(new)], **project_kw)
+		if verbose:
+			print(f'Wrote frame {cnt}')
+		if out_dir is not None:
+			gsr3d.write_vti_array(vor.reshape(visualize_res), x_min, x_max, y_min, y_max, z_min, z_max, os.path.join(out_dir, f'vorticity_{cnt}.vti'))
+			gsr3d.write_vti_array(div.reshape(visualize_res), x_min, x_max, y_min, y_max, z_min, z_max, os.path.join(out_dir, f'divergence_{cnt}.vti'))
+			gv.save(os.path.join(out_dir, f'gaussian_velocity_{cnt}.pt'))
+		if on_frame is not None:
+			on_frame(cnt, gv, vor, div)
+		cnt += 1
+		t += time_step
+	return gv, new
 
 
 def _project_unfused(gv, reference_field, data_generator, test_data_generator, boundary_generator, boundary_lambda,

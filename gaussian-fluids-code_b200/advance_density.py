@@ -40,14 +40,47 @@ class DensityAdvector:
 			out[i0:i0 + 32] = ((rl[..., 0] >= radius - thick) & ((X - nearest).norm(dim=-1) <= thick)).float()
 		return out
 
-	def advect(self, gaussian_velocity, dt, density_a, density_b=None):
-		"""advected_density (3D/advance_density.py:52-58) for one or two fields; returns the new field(s)"""
+	def advect(self, gaussian_velocity, dt, density_a, density_b=None, x_range=None, out=None):
+		"""advected_density (3D/advance_density.py:52-58) for one or two fields; returns the new field(s).  x_range = (begin, end):
+		only those x planes are computed — the rest of the returned field(s) is left as `out` holds it (SlabSharding)"""
 		gv = gaussian_velocity
 		gv._engine.ensure_packed(gv._params())
-		out_a = torch.empty_like(density_a)
-		out_b = torch.empty_like(density_b) if density_b is not None else None
-		gv._engine.advect_density(self.axes, self.domain, -dt, density_a, out_a, density_b, out_b)
+		out_a = out[0] if out is not None else torch.empty_like(density_a)
+		out_b = (out[1] if out is not None else torch.empty_like(density_b)) if density_b is not None else None
+		gv._engine.advect_density(self.axes, self.domain, -dt, density_a, out_a, density_b, out_b, x_range=x_range)
 		return out_a if density_b is None else (out_a, out_b)
+
+
+class SlabSharding:
+	"""
+	The density lattice shared between the GPUs of a box by slabs of x planes (config 5 of BASELINE.json: 512^3 on 8 GPUs): every
+	rank advects its own slab; a back-traced voxel reads the old density at most `halo` planes outside the slab (the flow moves
+	|u| dt per frame, a fraction of a plane at the reference's settings), so after every frame the ranks exchange `halo` planes
+	with their two neighbours — point-to-point, no collective.  Every rank keeps full-shape arrays of which its slab +- halo is valid.
+	"""
+
+	def __init__(self, nx, rank, world, halo=4):
+		self.nx, self.rank, self.world, self.halo = nx, rank, world, halo
+		self.begin, self.end = rank * nx // world, (rank + 1) * nx // world
+
+	def x_range(self):
+		return self.begin, self.end
+
+	def exchange(self, *fields):
+		"""send this slab's outermost `halo` planes to the neighbours, receive theirs (torch.distributed point-to-point)"""
+		if self.world == 1:
+			return
+		import torch.distributed as dist
+		h, ops = self.halo, []
+		for f in fields:
+			if self.rank > 0:
+				ops.append(dist.P2POp(dist.isend, f[self.begin:self.begin + h], self.rank - 1))
+				ops.append(dist.P2POp(dist.irecv, f[self.begin - h:self.begin], self.rank - 1))
+			if self.rank < self.world - 1:
+				ops.append(dist.P2POp(dist.isend, f[self.end - h:self.end], self.rank + 1))
+				ops.append(dist.P2POp(dist.irecv, f[self.end:self.end + h], self.rank + 1))
+		for r in dist.batch_isend_irecv(ops):
+			r.wait()
 
 
 def advected_density_reference(density, gaussian_velocity, dt, domain):

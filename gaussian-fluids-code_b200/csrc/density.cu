@@ -13,6 +13,7 @@ namespace gsr {
 struct LatticeArgs {
 	const float *xs, *ys, *zs;	// axis coordinates (NX), (NY), (NZ) — torch.linspace of the reference's get_grid_points
 	int nx, ny, nz;
+	int x_begin, x_end;		// the slab of x planes this launch computes (a process's share of the lattice); the whole lattice: 0, nx
 	float lo[3], hi[3];		// the domain [x_min, x_max] x ... the back-traced points are clamped to, and the lattice spans
 };
 
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(128, 4) advect_density_kernel(TiledArgs a, Lat
 	if (threadIdx.x == 0) sh.staged = 0;	// candidates come straight from global memory / L1 (compact warps, no ordering pass)
 	__syncthreads();
 	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int bi = blockIdx.x * 8 + 4 * (w >> 1), bj = blockIdx.y * 8 + 4 * (w & 1), bk = blockIdx.z * 8;
+	const int bi = L.x_begin + blockIdx.x * 8 + 4 * (w >> 1), bj = blockIdx.y * 8 + 4 * (w & 1), bk = blockIdx.z * 8;
 	constexpr int P = DN_P;
 	float x0[P], x1[P], x2[P], px[P], py[P], pz[P], v[P][3], vs[P][3], dummy[P][9];
 	bool ok[P];
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(128, 4) advect_density_kernel(TiledArgs a, Lat
 	for (int p = 0; p < P; p++) {
 		const int q = 32 * p + lane;
 		vi[p] = bi + q / 32; vj[p] = bj + (q / 8) % 4; vk[p] = bk + q % 8;
-		ok[p] = vi[p] < L.nx && vj[p] < L.ny && vk[p] < L.nz;
+		ok[p] = vi[p] < L.x_end && vj[p] < L.ny && vk[p] < L.nz;
 		px[p] = x0[p] = ok[p] ? __ldg(L.xs + vi[p]) : 0.f;
 		py[p] = x1[p] = ok[p] ? __ldg(L.ys + vj[p]) : 0.f;
 		pz[p] = x2[p] = ok[p] ? __ldg(L.zs + vk[p]) : 0.f;
@@ -86,12 +87,14 @@ __global__ void __launch_bounds__(128, 4) advect_density_kernel(TiledArgs a, Lat
 
 using namespace gsr;
 
-extern "C" int gsr_advect_density(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,
-				  const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, const float *domain, float dt,
-				  const float *density_a, const float *density_b, float *out_a, float *out_b, void *stream)
+extern "C" int gsr_advect_density_slab(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,
+				       const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, int x_begin, int x_end, const float *domain, float dt,
+				       const float *density_a, const float *density_b, float *out_a, float *out_b, void *stream)
 {
 	Grid g;
 	if (!make_grid(d, g) || g.D != 3 || !cell_start || !packed || !xs || !ys || !zs || nx < 2 || ny < 2 || nz < 2 || !domain || !density_a || !out_a) return GSR_EINVAL;
+	if (x_begin < 0 || x_end > nx || x_begin > x_end) return GSR_EINVAL;
+	if (x_begin == x_end) return GSR_OK;
 	if ((density_b != nullptr) != (out_b != nullptr) || density_a == out_a || (density_b && density_b == out_b)) return GSR_EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
 	TiledArgs a;
@@ -99,12 +102,19 @@ extern "C" int gsr_advect_density(const gsr_grid_desc *d, const int32_t *cell_st
 	a.cell_start = cell_start; a.packed = (const float4 *)packed; a.cull = cull;
 	a.x = nullptr; a.Q = 0; a.perm = nullptr; a.scs = nullptr; a.tile_row = nullptr; a.cap = 0;
 	LatticeArgs L;
-	L.xs = xs; L.ys = ys; L.zs = zs; L.nx = nx; L.ny = ny; L.nz = nz;
+	L.xs = xs; L.ys = ys; L.zs = zs; L.nx = nx; L.ny = ny; L.nz = nz; L.x_begin = x_begin; L.x_end = x_end;
 	for (int k = 0; k < 3; k++) { L.lo[k] = domain[2 * k]; L.hi[k] = domain[2 * k + 1]; }
-	dim3 grid((nx + 7) / 8, (ny + 7) / 8, (nz + 7) / 8);
+	dim3 grid((x_end - x_begin + 7) / 8, (ny + 7) / 8, (nz + 7) / 8);
 	g_launches += 1;
 	if (density_b) advect_density_kernel<2><<<grid, 128, 0, st>>>(a, L, dt, density_a, density_b, out_a, out_b);
 	else advect_density_kernel<1><<<grid, 128, 0, st>>>(a, L, dt, density_a, nullptr, out_a, nullptr);
 	GSR_CHECK_LAUNCH();
 	return GSR_OK;
+}
+
+extern "C" int gsr_advect_density(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,
+				  const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, const float *domain, float dt,
+				  const float *density_a, const float *density_b, float *out_a, float *out_b, void *stream)
+{
+	return gsr_advect_density_slab(d, cell_start, packed, cull, xs, ys, zs, nx, ny, nz, 0, nx, domain, dt, density_a, density_b, out_a, out_b, stream);
 }

@@ -155,6 +155,7 @@ __device__ __forceinline__ void step_reduce_tail(const gsr_step_cfg &cfg, int N,
 	// Adam bias corrections for step t (torch: step_size = lr / (1 - beta1^t), denom = sqrt(v)/sqrt(1 - beta2^t) + eps)
 	const double t = (double)st[GSR_ST_T] + 1.;
 	st[GSR_ST_T] = (float)t;
+	st[GSR_ST_CLOCK] += 1.f;
 	const double bc1 = 1. - pow((double)cfg.beta1, t), bc2 = 1. - pow((double)cfg.beta2, t);
 	for (int g = 0; g < 4; g++) {
 		st[C_LRUSED + g] = st[GSR_ST_LR + g];
@@ -323,6 +324,7 @@ __device__ __forceinline__ void step_grid_scale(const gsr_step_cfg &cfg, float *
 	double gs = cfg.grid_scale_tau0;
 	if (cfg.grid_coef > 0.) gs = fmax(cfg.grid_coef * exp(-(double)min_s), cfg.min_grid_scale);
 	st[GSR_ST_GRID_SCALE] = (float)gs;
+	if (cfg.grid_scale_out) *cfg.grid_scale_out = (float)gs;
 	st[GSR_ST_MIN_S] = __int_as_float(0x7f800000);
 }
 
@@ -402,6 +404,7 @@ __device__ __forceinline__ void step_reduce_tail_split(const gsr_step_cfg &cfg, 
 		st[C_BC2] = (float)(1. / sqrt(bc_sm[1]));
 	} else if (tid == 5) {
 		st[GSR_ST_T] = (float)((double)st[GSR_ST_T] + 1.);
+		st[GSR_ST_CLOCK] += 1.f;
 	}
 }
 
@@ -646,6 +649,7 @@ __global__ void init_state_kernel(float *st, size_t n_moments, gsr_step_cfg cfg)
 		float v = 0.f;
 		if (i == GSR_ST_BEST || i == GSR_ST_MIN_S) v = __int_as_float(0x7f800000);
 		if (i >= GSR_ST_LR && i < GSR_ST_LR + 4) v = cfg.lr[i - GSR_ST_LR];
+		if (i == GSR_ST_CLOCK && cfg.keep_clock) return;	// the sample clock runs on across optimisation phases
 		st[i] = v;
 	}
 }

@@ -79,11 +79,17 @@ class HashEngine:
 		self.cell_start = self.sorted_id = self.packed = self.cull = None
 		self._packed_key = None
 		self._bin_cache = {}
+		# grid_scale lives in a persistent device scalar per field: the kernels always read it from there (desc.grid_scale_dev), so a
+		# CUDA graph captured while this field had another grid_scale — e.g. the pull-back of the previous field inside the
+		# iteration graph of the other field — bins with the current value on every replay
+		self.gs_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
 
 	# ---- hash -------------------------------------------------------------------------------------
 	def set_grid(self, ext_bounds, dims, grid_scale, tau):
 		self.ext_bounds, self.dims = list(ext_bounds), list(dims)
 		self.desc = host.make_desc(self.D, ext_bounds, dims, grid_scale, tau)
+		self.gs_dev.fill_(float(grid_scale))	# stream-ordered; rounds to f32 exactly as the descriptor's host copy does
+		self.desc.grid_scale_dev = self.gs_dev.data_ptr()
 		self.ncell = host.n_cells(self.D, dims)
 
 	def build(self, positions, want_ref_format=False, params=None):
@@ -164,7 +170,7 @@ class HashEngine:
 		key = None
 		if need_tiles and not need_cells:
 			key = (x.data_ptr(), x._version, Q, tuple(self.dims))
-			gs_now = None if self.desc.grid_scale_dev else float(self.desc.grid_scale)
+			gs_now = None	# grid_scale is device-resident: orderings are refreshed by age
 			ent = self._bin_cache.get(key)
 			# reuse while young; when both grid_scales are known on the host, also require them to be close (the ordering
 			# only matters for locality, see the docstring)
@@ -313,13 +319,16 @@ class HashEngine:
 											  ptr(data), ptr(normal), stream()), 'gsr_sample_box_surface')
 		return data, normal
 
-	def advect_density(self, axes, domain, dt, density_a, out_a, density_b=None, out_b=None):
-		"""gsr_advect_density: semi-Lagrangian step of one or two density fields on the lattice spanned by `axes` = (xs, ys, zs)"""
+	def advect_density(self, axes, domain, dt, density_a, out_a, density_b=None, out_b=None, x_range=None):
+		"""gsr_advect_density(_slab): semi-Lagrangian step of one or two density fields on the lattice spanned by `axes` = (xs, ys, zs);
+		x_range = (begin, end): only those x planes of the outputs are computed (a process's slab)"""
 		xs, ys, zs = axes
 		dom = (C.c_float * 6)(*[float(v) for v in domain])
-		check(self.lib.gsr_advect_density(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True), ptr(self.cull),
-										  ptr(xs), ptr(ys), ptr(zs), C.c_int(xs.numel()), C.c_int(ys.numel()), C.c_int(zs.numel()), dom, C.c_float(dt),
-										  ptr(density_a, name='density'), ptr(density_b, allow_none=True), ptr(out_a), ptr(out_b, allow_none=True), stream()), 'gsr_advect_density')
+		x0, x1 = x_range if x_range is not None else (0, xs.numel())
+		check(self.lib.gsr_advect_density_slab(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True), ptr(self.cull),
+											   ptr(xs), ptr(ys), ptr(zs), C.c_int(xs.numel()), C.c_int(ys.numel()), C.c_int(zs.numel()), C.c_int(int(x0)), C.c_int(int(x1)),
+											   dom, C.c_float(dt), ptr(density_a, name='density'), ptr(density_b, allow_none=True), ptr(out_a), ptr(out_b, allow_none=True),
+											   stream()), 'gsr_advect_density')
 
 	def sample_losses(self, val, grad, refs, Q):
 		"""gsr_sample_losses: the 8 loss slots of include/gsr_b200.h summed over the samples (device tensor, no sync)"""
@@ -363,20 +372,24 @@ class FusedStepper:
 		cfg.grid_coef = float(np.sqrt(-2. * np.log(tau))) if tau else 0.
 		cfg.min_grid_scale = float(min_grid_scale)
 		cfg.grid_scale_tau0 = float(max(ext_bounds[2 * k + 1] - ext_bounds[2 * k] for k in range(D)))
+		cfg.grid_scale_out = engine.gs_dev.data_ptr()	# every step also leaves the next grid_scale in the field's persistent scalar
 		self.cfg = cfg
 		self.N = None
 		self.state = None
 
-	def init(self, scalings):
+	def init(self, scalings, keep_clock=True):
+		"""start an optimisation phase; keep_clock: the sample clock (state[ST_CLOCK], the iteration number the sample generators
+		read) runs on from the previous phase on the same state instead of restarting at 0"""
 		N = scalings.shape[0]
 		self.N = N
 		nfl = self.e.lib.gsr_step_state_floats(C.c_int(self.e.D), C.c_int64(N))
-		if self.state is None or self.state.numel() != nfl:	# a restart on the same N keeps the buffers (and captured graphs) valid
+		fresh = self.state is None or self.state.numel() != nfl
+		if fresh:	# a restart on the same N keeps the buffers (and captured graphs) valid
 			self.state = torch.empty(nfl, dtype=torch.float32, device=self.e.device)
 			self.ws = torch.empty(self.e.lib.gsr_step_ws_bytes(C.c_int(self.e.D), C.c_int64(N)), dtype=torch.uint8, device=self.e.device)
+		self.cfg.keep_clock = 0 if (fresh or not keep_clock) else 1
 		check(self.e.lib.gsr_step_init(C.byref(self.cfg), C.c_int64(N), ptr(scalings.detach()), ptr(self.state), stream()), 'gsr_step_init')
-		# from now on the engine's kernels read grid_scale from the device-resident state
-		self.e.desc.grid_scale_dev = self.state.data_ptr() + 4 * _lib.ST_GRID_SCALE
+		# (gsr_step_init and every gsr_step write the grid_scale into the state AND into engine.gs_dev, which the kernels read)
 
 	def step(self, params, acc, mask, extra=(), loss_srcs=(), positions_org=None, rebuild=False):
 		"""one optimiser iteration (gsr_step); rebuild=True also rebuilds the engine's hash and packed records from the updated
@@ -407,13 +420,17 @@ class FusedStepper:
 								  ptr(acc, allow_none=True, align16=True), C.c_int(mask), ex, srcs, C.c_int(len(loss_srcs)),
 								  ptr(positions_org, allow_none=True), ptr(self.state), ptr(self.ws, torch.uint8), C.c_size_t(self.ws.numel()), stream()), 'gsr_step')
 
+	@property
+	def clock(self):
+		"""device scalar (1,) holding the running iteration number for the sample generators"""
+		return self.state[_lib.ST_CLOCK:_lib.ST_CLOCK + 1]
+
 	def scalars(self):
 		"""host copy of the scalar block (synchronises)"""
 		return self.state[:_lib.STATE_SCALARS].tolist()
 
 	def detach(self):
-		"""hand grid_scale back to the host descriptor (synchronises once)"""
+		"""the final grid_scale as a host number (synchronises once); the kernels keep reading the field's device scalar"""
 		gs = float(self.state[_lib.ST_GRID_SCALE].item())
-		self.e.desc.grid_scale_dev = None
 		self.e.desc.grid_scale = gs
 		return gs

@@ -296,7 +296,13 @@ def write_vti(field, x_min, x_max, y_min, y_max, z_min, z_max, save_filename, x_
 	the XML is written by hand (ascii, point data, x fastest as VTK expects).
 	"""
 	XYZ = get_grid_points(x_min, x_max, y_min, y_max, z_min, z_max, x_N, y_N, z_N)
-	V = field(XYZ).reshape(x_N, y_N, z_N).detach().cpu().numpy()
+	write_vti_array(field(XYZ).reshape(x_N, y_N, z_N), x_min, x_max, y_min, y_max, z_min, z_max, save_filename)
+
+
+def write_vti_array(values, x_min, x_max, y_min, y_max, z_min, z_max, save_filename):
+	"""the file of write_vti for values already sampled on the (x_N, y_N, z_N) lattice of get_grid_points"""
+	x_N, y_N, z_N = values.shape
+	V = values.detach().cpu().numpy()
 	sx, sy, sz = (x_max - x_min) / x_N, (y_max - y_min) / y_N, (z_max - z_min) / z_N
 	data = ' '.join(f'{v:.7g}' for v in V.ravel(order='F'))
 	with open(save_filename, 'w') as fd:

@@ -1,6 +1,14 @@
 """
-The fixed-work 3D time step used for measurement: the work of one `advance.py` frame with the iteration
-count pinned to the reference's minimum, because the reference's own count is data dependent:
+The pipelined execution of `advance3d.project` and the fixed-work 3D time step used for measurement.
+
+ShardedProjector is what `advance3d.project()` runs on when it is given the stock generators: the samples are drawn on the
+device (counter-based Philox kernels keyed by the optimiser state's running sample clock), ten iterations form one captured CUDA
+graph, and everything that does not depend on the updated Gaussians is moved off the iteration's critical cycle — the next
+iteration's samples and their hashes are prepared right after the step (beside the Gaussian hash), the RK4 pull-back reference of
+those samples runs on its own stream until the next adjoint kernel needs it.
+
+LeapfrogTimestep is one frame of `3D/advance.py` through that API (advance3d.advance_frame) with the iteration count pinned to the
+reference's minimum, because the reference's own count is data dependent:
 
     clone (copy, no split)  ->  advect (RK4 positions only, Q = N)
     ->  `iters` (600) project iterations, each { RK4 pull-back reference (5 evaluations), forward + backward with the
@@ -9,17 +17,17 @@ count pinned to the reference's minimum, because the reference's own count is da
     ->  a test pass { RK4 pull-back + forward on the test_res^3 lattice } every 100 iterations
     ->  swap, two forward passes on the lattice (the |vorticity| and divergence fields the reference writes as VTI).
 
-Multi-GPU (one process per GPU): sample points are sharded — every rank draws its own N training and 8192 boundary
-samples (global Q = world * N, the loss normalisers use the global counts) and its own test_res^3 share of a lattice that
-is world times finer along z (fixed work per rank: weak scaling);
-Gaussian parameters, hash and optimiser state are replicated; ONE exchange per iteration sums the compact gradient
-accumulators and the loss partial sums (a single kernel over NVLink peer memory, csrc/xrank.cu; NCCL all-reduce as the
-fallback), after which every rank runs the identical fused step, so the replicas stay bit-identical without a broadcast.
-
-Schedule of an iteration (ShardedProjector): the iteration is a strict cycle — forward needs the rebuilt hash, the step needs
-every gather — so everything that does not depend on the updated Gaussians is moved off it: the next iteration's samples and
-their hashes are prepared right after the step (beside the Gaussian hash), and the RK4 pull-back reference of those samples
-runs on its own stream until the next adjoint kernel needs it.  Ten iterations form one captured CUDA graph.
+Multi-GPU (one process per GPU), two modes:
+  * scaling='weak': sample points are sharded — every rank draws its own N training and 8192 boundary samples (global
+    Q = world * N, the loss normalisers use the global counts) and its own test_res^3 share of a lattice that is world times finer
+    along z (fixed work per rank); Gaussian parameters, hash and optimiser state are replicated; ONE exchange per iteration sums
+    the compact gradient accumulators and the loss partial sums (a single kernel over NVLink peer memory, csrc/xrank.cu; NCCL
+    all-reduce as the fallback), after which every rank runs the identical fused step, so the replicas stay bit-identical without
+    a broadcast.
+  * scaling='strong': the reference's frame itself, made faster — the fixed test_res^3 lattice (80 % of the frame's sample
+    evaluations at the reference's size) is split over the ranks by z planes, no collective on the data path; the 600
+    training iterations on N = 1000 Gaussians are latency bound and run replicated (sharding them would only add an exchange to
+    every 40 us iteration).
 """
 import ctypes as C
 import os
@@ -31,15 +39,18 @@ from .init_cond3d import sample_on_box
 from .synth import make_fast3d, synthetic_field
 
 
-def shard_lattice(test_res, rank, world, device):
+def shard_lattice(test_res, rank, world, device, scaling='weak'):
 	"""
-	This rank's share of the test / output lattice, fixed work per rank: the job evaluates a
-	test_res x test_res x (world * test_res) lattice and rank r owns its z planes r, r + world, ...
-	(world = 1: the reference's test_res^3 lattice, 3D/GSR.py:719-725).
+	This rank's share of the test / output lattice (world = 1: the reference's test_res^3 lattice, 3D/GSR.py:719-725).
+	weak:   fixed work per rank — the job evaluates a test_res x test_res x (world * test_res) lattice, rank r owns its z planes
+	        r, r + world, ...
+	strong: fixed job — the test_res^3 lattice itself, rank r owns its z planes r, r + world, ...
+	Returns (points, number of points of the whole job's lattice).
 	"""
 	ax = torch.linspace(0., 1., test_res, device=device)
-	az = torch.linspace(0., 1., test_res * world, device=device)[rank::world]
-	return torch.stack(torch.meshgrid(ax, ax, az, indexing='ij'), dim=-1).reshape(-1, 3).contiguous()
+	nz = test_res * world if scaling == 'weak' else test_res
+	az = torch.linspace(0., 1., nz, device=device)[rank::world]
+	return torch.stack(torch.meshgrid(ax, ax, az, indexing='ij'), dim=-1).reshape(-1, 3).contiguous(), test_res * test_res * nz
 
 
 def flat_layout(N, nblk, nblkb, AF=12):
@@ -49,13 +60,25 @@ def flat_layout(N, nblk, nblkb, AF=12):
 
 
 class Census:
-	"""device-side counter of candidate visits (the benchmark's unit of work)"""
+	"""device-side counter of candidate visits (the benchmark's unit of work); the visits made on the test / output lattice are
+	also kept apart (in the strong-scaling mode only those are shared between the ranks, the training visits are replicated)"""
 
 	def __init__(self, device):
-		self.c = torch.zeros(2, dtype=torch.int64, device=device)	# [candidate visits C, accepted pairs P]
+		self.c = torch.zeros(2, dtype=torch.int64, device=device)	# [candidate visits C, accepted pairs P], everything
+		self.lat = torch.zeros(2, dtype=torch.int64, device=device)	# the lattice passes' share of it
+
+	def count(self, engine, x, evals, lattice=False):
+		before = self.c.clone() if lattice else None
+		engine.count_pairs(x, self.c, evals, True)
+		if lattice:
+			self.lat += self.c - before
 
 	def value(self):
 		c = self.c.tolist()
+		return int(c[0]), int(c[1])
+
+	def lattice_value(self):
+		c = self.lat.tolist()
 		return int(c[0]), int(c[1])
 
 
@@ -108,11 +131,18 @@ class PeerExchange:
 class ShardedProjector(advance3d.FusedProjector):
 	"""FusedProjector whose accumulators and loss partials live in one flat buffer that is all-reduced once per iteration"""
 
-	def __init__(self, gv, reference_field, boundary_lambda, Q, Qb, world=1, patience=50):
+	def __init__(self, gv, reference_field, boundary_lambda, Q, Qb, world=1, rank=0, patience=50, box=(0., 1.) * 3, boundary_box=None, seed=42):
 		super().__init__(gv, reference_field, boundary_lambda, patience=patience)
 		e = gv._engine
-		self.world = world
+		self.world, self.rank = world, rank
+		self.lattice_world = world	# processes sharing the test lattice (LeapfrogTimestep: also > 1 in the strong mode, where world == 1 here)
 		self.Q, self.Qb = Q, Qb
+		self.box, self.boundary_box, self.seed = tuple(box), tuple(boundary_box or box), seed
+		dev = gsr3d.device
+		# persistent sample buffers: the device samplers write them, the captured graph reads them
+		self._x = torch.empty((Q, 3), dtype=torch.float32, device=dev)
+		self._xb, self._nb = torch.empty((Qb, 3), dtype=torch.float32, device=dev), torch.empty((Qb, 3), dtype=torch.float32, device=dev)
+		self.graph, self.unit, self.per_iter, self.graph_launches = None, 0, 0, 0
 		N = gv.N
 		nblk, nblkb = e.lib.gsr_loss_blocks(Q), e.lib.gsr_loss_blocks(Qb)
 		lay = flat_layout(N, nblk, nblkb)
@@ -137,12 +167,30 @@ class ShardedProjector(advance3d.FusedProjector):
 		self._samplers = self._prep = self._ident = None
 		if self.peer:
 			self.peer.new_phase()
+		self.set_samplers(self.draw_samples, self.draw_boundary_binned if self.boundary_lambda else None)
 
-	def restart(self):
-		"""begin a new project phase on the same buffers: fresh optimiser state, fresh hash"""
+	# ---- device samplers (one kernel each; the iteration number comes from the state's running sample clock) ----------------------
+	def draw_samples(self):
+		"""this rank's training samples of the coming iteration: uniform in the box, Q = N (3D/advance.py:339-340)"""
+		return self.gv._engine.sample_box(self.box, self._x, self.seed, 2 * self.rank, self.stepper.clock)
+
+	def draw_boundary(self):
+		"""sample_on_box(Qb) (3D/init_cond.py:227-249)"""
+		return self.gv._engine.sample_box_surface(self.boundary_box, self._xb, self._nb, self.seed, 2 * self.rank + 1, self.stepper.clock)
+
+	def draw_boundary_binned(self):
+		"""draw_boundary + the engine's ordering of the batch, one launch: ((points, normals), Bins)"""
+		bins = self.gv._engine.sample_box_surface_binned(self.boundary_box, self._xb, self._nb, self.seed, 2 * self.rank + 1, self.stepper.clock, tag='pb')
+		return (self._xb, self._nb), bins
+
+	def restart(self, keep_clock=True):
+		"""begin a new project phase on the same buffers: fresh optimiser state, fresh hash; the sample clock runs on, so the new
+		phase draws new samples (keep_clock=False: replay the first phase's samples)"""
 		if self.peer:
 			self.peer.new_phase()
-		self.stepper.init(self.gv.scalings)
+		if getattr(self, '_drop_clock', False):	# LeapfrogTimestep.reset(): replay from the first sample
+			keep_clock, self._drop_clock = False, False
+		self.stepper.init(self.gv.scalings, keep_clock=keep_clock)
 		self._rebuild()
 		cur = self.ref.velocity_field
 		cur._engine._packed_key = None
@@ -311,123 +359,123 @@ class ShardedProjector(advance3d.FusedProjector):
 		self._join_prepared(join_ref=join_all)
 
 
+
+	# ---- a phase: begin(), run_iterations() as often as needed, finish() -----------------------------------------------------------
+	def begin(self, census=None):
+		"""prepare the samples of the phase's first iteration"""
+		self.prime(census)
+		self._parity = 0
+
+	def run_iterations(self, n, census=None, use_graph=True):
+		"""
+		n pipelined iterations.  Iterations run in units of `unit` — one captured CUDA graph per projector (a replay costs ~5 us of
+		launch overhead, tools/graph_probe.py, so several iterations share one; the peer-memory exchange alternates between two
+		buffers, so a unit then holds whole pairs) — and a remainder eagerly.  The first unit of a new projector runs eagerly (it
+		sizes every scratch buffer), then the graph is captured.
+		"""
+		unit = int(os.environ.get('GSR_GRAPH_UNIT', '0'))
+		if unit <= 0:
+			unit = self.unit or next(u for u in (10, 4, 2, 1) if n % u == 0 and not (self.peer and u % 2))
+		if self.peer and (unit % 2 or n % 2):
+			raise ValueError('with the peer-memory exchange iterations run in pairs')
+		e = self.gv._engine
+
+		def body(k_iters, cen=None):
+			for k in range(k_iters):
+				self.iterate(None, None, cen, parity=(self._parity + k) & 1, join_all=(k == k_iters - 1))
+
+		done = 0
+		graphed = use_graph and census is None
+		if graphed and self.graph is None and n >= 2 * unit:
+			side = torch.cuda.Stream()
+			side.wait_stream(torch.cuda.current_stream())
+			with torch.cuda.stream(side):
+				l0 = e.lib.gsr_launch_count()
+				body(unit)	# eager warm-up (it counts)
+				self.per_iter = e.lib.gsr_launch_count() - l0
+				done += unit
+			torch.cuda.current_stream().wait_stream(side)
+			self.graph, self.unit = torch.cuda.CUDAGraph(), unit
+			with torch.cuda.graph(self.graph):
+				body(unit)
+			self.graph_launches -= self.per_iter	# the capture pass bumped the host counter without running anything
+		while done < n:
+			if graphed and self.graph is not None and n - done >= self.unit:
+				self.graph.replay()
+				self.graph_launches += self.per_iter	# kernels of this library inside one replay
+				done += self.unit
+			else:
+				k = min(unit, n - done)
+				body(k, census)
+				done += k
+				self._parity = (self._parity + k) & 1
+
+	def evaluate_global(self, data, total=None, probe=None, census=None):
+		"""the test losses over the WHOLE lattice: `data` is this rank's share, `total` the number of points of all ranks"""
+		Q = data.shape[0]
+		sums = self.evaluate(data, probe=probe) * Q
+		if census is not None:
+			census.count(self.ref.velocity_field._engine, data, 5, lattice=True)
+			census.count(self.gv._engine, data, 1, lattice=True)
+		if self.lattice_world > 1:
+			torch.distributed.all_reduce(sums)
+		return sums / float(total or Q)
+
 class LeapfrogTimestep:
-	def __init__(self, n=10, dt=.02, iters=600, Qb=8192, test_res=128, boundary_lambda=10., rank=0, world=1, seed=42, check_iter=100, use_graph=True):
+	def __init__(self, n=10, dt=.02, iters=600, Qb=8192, test_res=128, boundary_lambda=10., rank=0, world=1, seed=42, check_iter=100, use_graph=True,
+				 scaling='weak'):
 		self.n, self.dt, self.iters, self.Qb, self.test_res, self.boundary_lambda = n, dt, iters, Qb, test_res, boundary_lambda
-		self.rank, self.world, self.check_iter, self.use_graph = rank, world, check_iter, use_graph
+		self.rank, self.world, self.check_iter, self.use_graph, self.scaling = rank, world, check_iter, use_graph, scaling
 		P, S, R, V, mgs, _ = synthetic_field(n, seed)
 		self.params0 = (P, S, R, V)
 		self.cur = make_fast3d(P, S, R, V, 5e-3, mgs)
 		self.new = make_fast3d(P, S, R, V, 5e-3, mgs)
 		self.N = self.cur.N
 		dev = gsr3d.device
-		self.lattice = shard_lattice(test_res, rank, world, dev)
+		self.lattice, total = shard_lattice(test_res, rank, world, dev, scaling)
+		box = (0., 1.) * 3
+		self.data_gen = advance3d.BoxSampler(*box)
+		self.test_gen = advance3d.LatticeGenerator(*box, test_res, test_res, test_res, points=self.lattice, total=total)
+		self.boundary_gen = advance3d.BoxSurfaceSampler(*box) if boundary_lambda else None
+		# strong scaling: the training iterations run replicated (no exchange); only the lattice is shared
+		self.train_world = world if scaling == 'weak' else 1
 		self.last_test = None
-		self.graph_launches = 0
-		self._proj = {}
-		self._x = torch.empty((self.N, 3), dtype=torch.float32, device=dev)
-		self._xb, self._nb = torch.empty((Qb, 3), dtype=torch.float32, device=dev), torch.empty((Qb, 3), dtype=torch.float32, device=dev)
-		self._lo = torch.tensor([self.new.x_min, self.new.y_min, self.new.z_min], dtype=torch.float32, device=dev)
-		self._hi = torch.tensor([self.new.x_max, self.new.y_max, self.new.z_max], dtype=torch.float32, device=dev)
+		self.probe = None
+		self._seeds = {id(self.cur): seed, id(self.new): seed + 1}	# each field keeps its own sample stream when it is the optimised one
+		self._fields0 = (self.cur, self.new)
 
-	def reset(self, params=None):
-		"""restore both fields to the given (default: initial) parameters — used between timed steps and by the e2e path"""
+	@property
+	def graph_launches(self):
+		"""kernels of this library launched from inside graph replays so far (the host-side launch counter does not see them)"""
+		return sum(fp.graph_launches for f in (self.cur, self.new) for fp in f.__dict__.get('_pipelines', {}).values())
+
+	def reset(self, params=None, reset_clock=True):
+		"""restore both fields to the given (default: initial) parameters and the initial roles (which object is the current field, which
+		the one being optimised; with reset_clock the sample clocks too, so that the next step repeats the first) — used between
+		timed steps and by the e2e path"""
+		self.cur, self.new = self._fields0
 		P, S, R, V = params if params is not None else [torch.as_tensor(a) for a in self.params0]
 		with torch.no_grad():
 			for f in (self.cur, self.new):
 				for t, src in zip((f.positions, f.scalings, f.rotations, f.values), (P, S, R, V)):
 					t.copy_(torch.as_tensor(src), non_blocking=True)
 				f.zero_grad()
-
-	def _samples(self, fp):
-		"""this rank's training samples of the current iteration: U[0,1]^3, Q = N (3D/advance.py:339-340), one kernel"""
-		return fp.gv._engine.sample_box((0., 1.) * 3, self._x, 42, 2 * self.rank, fp.stepper.state[:1])
-
-	def _boundary(self, fp):
-		"""sample_on_box(Qb) on the unit cube (3D/init_cond.py:227-249), one kernel"""
-		return fp.gv._engine.sample_box_surface((0., 1.) * 3, self._xb, self._nb, 42, 2 * self.rank + 1, fp.stepper.state[:1])
-
-	def _boundary_binned(self, fp):
-		"""_boundary + the engine's ordering of the batch, one launch: ((points, normals), Bins)"""
-		bins = fp.gv._engine.sample_box_surface_binned((0., 1.) * 3, self._xb, self._nb, 42, 2 * self.rank + 1, fp.stepper.state[:1], tag='pb')
-		return (self._xb, self._nb), bins
-
-	def _projector(self, new, cur):
-		"""the persistent projector (buffers, optimiser state, captured iteration graph) of one (new, cur) orientation"""
-		key = id(new)
-		ent = self._proj.get(key)
-		if ent is None:
-			ref = advance3d.AdvectedCovectorField(cur, cur, self.dt, 0., 1., 0., 1., 0., 1.)
-			ent = {'fp': ShardedProjector(new, ref, self.boundary_lambda, self.N, self.Qb, world=self.world), 'graph': None, 'per_iter': 0}
-			self._proj[key] = ent
-		else:
-			ent['fp'].restart()
-		return ent
+				if reset_clock:
+					for fp in f.__dict__.get('_pipelines', {}).values():
+						fp._drop_clock = True
 
 	def step(self, census=None):
+		"""one frame through the public API: advance3d.advance_frame (clone -> advect -> project -> swap -> the two output fields)"""
 		cur, new = self.cur, self.new
-		# clone (no Gaussian is over-stretched in the synthetic field: the common path of 3D/advance.py:91-92)
-		with torch.no_grad():
-			for a, b in zip((new.positions, new.scalings, new.rotations, new.values), (cur.positions, cur.scalings, cur.rotations, cur.values)):
-				a.copy_(b)
-			# advect (3D/advance.py:167-180), written into the persistent positions tensor so that the captured graph stays valid
-			pos = cur.advection_rk4(new.positions.detach(), self.dt)
-			pos.clamp_(self._lo, self._hi)
-			new.positions.copy_(pos)
-		new.zero_grad()
 		if census is not None:
-			cur._engine.count_pairs(new.positions.detach(), census.c, 4, True)
-		# project, fixed iteration count; the iteration is captured once per orientation into a CUDA graph and replayed
-		ent = self._projector(new, cur)
-		fp = ent['fp']
-		fp.set_samplers(lambda: self._samples(fp), (lambda: self._boundary_binned(fp)) if self.boundary_lambda else None)
-		fp.prime(census)
-		one = lambda parity, cen=None, last=True: fp.iterate(None, None, cen, parity=parity, join_all=last)
-		# iterations per captured graph: a replay costs ~5 us of launch overhead (tools/graph_probe.py), so several iterations share
-		# one; the peer-memory exchange alternates between two buffers, so a graph then holds whole pairs of iterations
-		unit = int(os.environ.get('GSR_GRAPH_UNIT', '0'))
-		if unit <= 0:
-			unit = next(u for u in (10, 4, 2, 1) if self.iters % u == 0 and self.check_iter % u == 0 and not (fp.peer and u % 2))
-		if (fp.peer and unit % 2) or self.iters % unit or self.check_iter % unit:
-			raise ValueError('iters and check_iter must be multiples of the iterations per graph (even with the peer-memory exchange)')
-		body = lambda: [one(k & 1, last=(k == unit - 1)) for k in range(unit)]
-		done = 0
-		if self.use_graph and census is None and ent['graph'] is None:
-			side = torch.cuda.Stream()
-			side.wait_stream(torch.cuda.current_stream())
-			with torch.cuda.stream(side):
-				for _ in range(max(1, 2 // unit)):	# eager warm-up iterations (they count): sizes every scratch buffer
-					l0 = new._engine.lib.gsr_launch_count()
-					body()
-					ent['per_iter'] = new._engine.lib.gsr_launch_count() - l0
-					done += unit
-			torch.cuda.current_stream().wait_stream(side)
-			ent['graph'] = torch.cuda.CUDAGraph()
-			with torch.cuda.graph(ent['graph']):
-				body()
-			self.graph_launches -= ent['per_iter']	# the capture pass bumped the host counter without running anything
-		graph = ent['graph'] if (self.use_graph and census is None) else None
-		while done < self.iters:
-			if graph is not None:
-				graph.replay()
-				self.graph_launches += ent['per_iter']	# kernels of this library inside one replay
-			else:
-				for k in range(unit):
-					one(k & 1, census)
-			done += unit
-			if done % self.check_iter == 0:
-				self.last_test = fp.evaluate(self.lattice, probe=getattr(self, 'probe', None))
-				if census is not None:
-					cur._engine.count_pairs(self.lattice, census.c, 5, True)
-					new._engine.count_pairs(self.lattice, census.c, 1, True)
-		fp.finish()
-		if fp.peer:
-			fp.peer.check()
-		self.cur, self.new = new, cur
-		# the two output fields (|vorticity| and divergence on the lattice)
-		g = self.cur.gradient(self.lattice)
-		vor = advance3d.curl(g).norm(dim=-1)
-		div = self.cur.gradient(self.lattice).diagonal(dim1=-2, dim2=-1).sum(dim=-1)
-		if census is not None:
-			self.cur._engine.count_pairs(self.lattice, census.c, 2, True)
+			cur._engine.count_pairs(cur.positions.detach(), census.c, 4, True)	# the advect pass (RK4 positions only)
+		hist = {}
+		self.cur, self.new, _, (vor, div) = advance3d.advance_frame(
+			cur, new, 0., 1., 0., 1., 0., 1., self.dt, self.data_gen, self.test_gen, boundary_generator=self.boundary_gen,
+			boundary_lambda=self.boundary_lambda, max_epoch=self.iters, patience=10 ** 9, verbose=0, batch_size=self.Qb, check_iter=self.check_iter,
+			rank=self.rank if self.train_world > 1 else 0, world=self.train_world, census=census, probe=self.probe, use_graph=self.use_graph,
+			history=hist, lattice_world=self.world, sample_seed=self._seeds[id(new)])
+		if hist.get('test'):
+			t = hist['test'][-1]
+			self.last_test = torch.tensor([t['loss_vor'], t['loss_hel'], t['loss_div']])
 		return vor, div

@@ -222,6 +222,10 @@ typedef struct {
 	double grid_coef;	/* sqrt(-2 ln tau) in host double (3D/GSR.py:249); 0 when tau == 0 */
 	double min_grid_scale;
 	double grid_scale_tau0;	/* the constant grid_scale used when tau == 0 (3D/GSR.py:251) */
+	int32_t keep_clock;	/* gsr_step_init: leave GSR_ST_CLOCK as it is (the state has been initialised before) */
+	float *grid_scale_out;	/* optional DEVICE scalar that also receives the next grid_scale: the hash descriptor's grid_scale_dev
+				 * of the field being optimised, so that every kernel launched on that field — also from a CUDA
+				 * graph captured earlier — bins with the current value */
 } gsr_step_cfg;
 
 /* one source of sample-loss partial sums and its weights in the scheduler metric:
@@ -247,6 +251,9 @@ typedef struct {
 #define GSR_ST_L_VALREG 12
 #define GSR_ST_L_DPOS 13
 #define GSR_ST_LOSS_SRC 14	/* [14..21] sum over sources of the raw loss slots divided by nothing (plain sums) */
+#define GSR_ST_CLOCK 22		/* steps taken since the state was created: like GSR_ST_T, but gsr_step_init keeps it when
+				 * cfg->keep_clock != 0 — the iteration number for the sample generators, so that successive
+				 * optimisation phases (time steps) draw fresh samples (the reference draws from one running RNG) */
 size_t gsr_step_state_floats(int D, int64_t N);
 size_t gsr_step_ws_bytes(int D, int64_t N);
 /* zero the moments, t = 0, best = +inf, lrs = cfg->lr, grid_scale from the current scalings */
@@ -304,6 +311,11 @@ int gsr_sample_box_surface(const float *box, int64_t n, uint64_t seed, uint32_t 
 int gsr_advect_density(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed, const float *cull,
 		       const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, const float *domain, float dt,
 		       const float *density_a, const float *density_b, float *out_a, float *out_b, void *stream);
+/* the same for the x planes [x_begin, x_end) only — one process's slab of a lattice shared between GPUs (the fields keep their full
+ * (nx, ny, nz) shape: the back-trace of a slab voxel may read the old density a few planes outside the slab) */
+int gsr_advect_density_slab(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed, const float *cull,
+			    const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, int x_begin, int x_end, const float *domain, float dt,
+			    const float *density_a, const float *density_b, float *out_a, float *out_b, void *stream);
 
 /* ---- measurement helpers (bench.py work census and roofline denominators) ------------------------ */
 /* counts[0] (device uint64) += candidate visits C for one evaluation of the Q points (occupancy of each point's 27 (9)-cell

@@ -329,6 +329,28 @@ def interp_val(field, positions, domain, real=np.float64, nthreads=0):
 # per-timestep optimisation: project() of 3D/advance.py:183-287 and step() of 3D/GSR.py:144-152, :704-716
 # ---------------------------------------------------------------------------------------------
 
+def dense_torch_value_gradient(positions, scalings, rotations, values, x):
+	"""
+	The reference's DENSE representation (GaussianSplatting3D, 3D/GSR.py:93-130: every Gaussian at every point, no truncation, no
+	hash) as torch ops on whatever device the tensors live on: Sigma^-1 = (R S)(R S)^T with S = diag(exp(s)) (:93-116),
+	u = sum_i v_i exp(-1/2 d^T Sigma^-1 d) (:118-122) and grad u = -sum_i v_i g_i (Sigma^-1 d)^T (:124-130).  O(N Q) memory.
+	Used as the CPU baseline "B2" of bench.py and as a tau = 0 cross-check.  Returns (u, grad u).
+	"""
+	import torch
+	q = rotations / (rotations ** 2).sum(-1, keepdim=True) ** .5
+	r, a, b, c = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+	R = torch.stack([1 - 2 * (b * b + c * c), 2 * (a * b - r * c), 2 * (a * c + r * b),
+					 2 * (a * b + r * c), 1 - 2 * (a * a + c * c), 2 * (b * c - r * a),
+					 2 * (a * c - r * b), 2 * (b * c + r * a), 1 - 2 * (a * a + b * b)], -1).reshape(-1, 3, 3)
+	A = R @ torch.diag_embed(torch.exp(scalings))
+	sigma_inv = A @ A.transpose(-1, -2)
+	d = x[:, None, :] - positions[None, :, :]
+	w = (sigma_inv[None] @ d[..., None]).squeeze(-1)
+	per = values[None] * torch.exp(-.5 * (d * w).sum(-1))[..., None]
+	grad = -(per[..., :, None] * w[..., None, :]).sum(1)
+	return per.sum(1), grad
+
+
 class _Adam:
 	"""torch.optim.Adam (defaults: betas .9/.999, eps 1e-8, no weight decay) + ReduceLROnPlateau(mode='min', threshold 1e-4 rel,
 	cooldown 0, eps 1e-8) for one parameter tensor, in float64 (torch works in the tensor's float32)"""
@@ -435,6 +457,9 @@ class OracleProjector3D:
 				total[k] = total[k] + np.asarray(bd[k], np.float64)
 			boundary_constraint = np.abs((np.asarray(bval, np.float64) * bn).sum(axis=1)).mean()
 		loss_tot = loss_vor + loss_div + 10. * loss_aniso + 10. * loss_vol + self.lam * boundary_constraint	# (:256: no helicity term)
+		# what the step consumes (for the parity tests): the raw sets, the total gradient, the scheduler metric
+		self.last = {'vor': [np.asarray(a, np.float64).copy() for a in vor], 'div': [np.asarray(a, np.float64).copy() for a in div],
+					 'total': [np.asarray(a, np.float64).copy() for a in total], 'metric': float(loss_tot), 'lr': [o.lr for o in self.opt]}
 		# step (3D/GSR.py:144-152, :714-716): Adam x4, schedulers x4 on the same metric, new grid
 		for k in range(4):
 			self.params[k] = self.opt[k].step(self.params[k], total[k])

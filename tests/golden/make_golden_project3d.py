@@ -98,9 +98,35 @@ if __name__ == '__main__':
 		def bnd_gen(batch):
 			d, nrm = bnd[it['b']]; it['b'] += 1
 			return d.clone(), nrm.clone()
+		# recorders: the raw vorticity / divergence gradient sets as get_losses_ti leaves them (before project()'s PCGrad projection),
+		# and, at every step(), the total .grad (projected sets + autograd regularisers + boundary pass) with the scheduler metric
+		rec = {'sets': [], 'grads': [], 'metric': [], 'lr': []}
+		NAMES = ('positions', 'scalings', 'rotations', 'values')
+		orig_get_losses, orig_step = new.get_losses, new.step
+
+		def get_losses(x, *a, **kw):
+			res = orig_get_losses(x, *a, **kw)
+			if kw.get('vor_positions_grad') is not None:
+				rec['sets'].append({f'{t}_{nm}': kw[f'{t}_{nm}_grad'].detach().numpy().copy() for t in ('vor', 'div') for nm in NAMES})
+			return res
+
+		def step(metrics):
+			rec['grads'].append({nm: getattr(new, nm).grad.detach().numpy().copy() for nm in NAMES})
+			rec['metric'].append(float(metrics))
+			rec['lr'].append([o.param_groups[0]['lr'] for o in new.optimizers])
+			return orig_step(metrics)
+		new.get_losses, new.step = get_losses, step
 		mod.project(new, ref, 0., 1., 0., 1., 0., 1., data_gen, lambda gv: None, boundary_generator=bnd_gen, boundary_lambda=BOUNDARY_LAMBDA,
 					batch_size=QB, max_epoch=epochs, patience=500, verbose=0, frame_id=0)
-		assert it['k'] == epochs and it['b'] == epochs
+		assert it['k'] == epochs and it['b'] == epochs and len(rec['sets']) == epochs and len(rec['grads']) == epochs
+		if epochs == max(EPOCHS):
+			for k in range(epochs):
+				for key, v in rec['sets'][k].items():
+					out[f'it{k + 1}_{key}_grad'] = v	# raw set, before PCGrad
+				for nm in NAMES:
+					out[f'it{k + 1}_total_{nm}_grad'] = rec['grads'][k][nm]	# .grad at step(): what Adam consumes
+				out[f'it{k + 1}_metric'] = np.float64(rec['metric'][k])
+				out[f'it{k + 1}_lr_used'] = np.array(rec['lr'][k])
 		for name in ('positions', 'scalings', 'rotations', 'values'):
 			out[f'after{epochs}_{name}'] = getattr(new, name).detach().numpy().copy()
 		out[f'after{epochs}_grid_scale'] = np.float64(new.grid_scale)

@@ -29,14 +29,27 @@ def _worker(rank, world, port, out_dir):
 		from gaussian_fluids_code_b200 import timestep3d
 		# 1. lattice shards: disjoint, union = the (res, res, world * res) lattice, equal work per rank
 		res = 6
-		mine = timestep3d.shard_lattice(res, rank, world, 'cpu')
-		assert mine.shape == (res ** 3, 3)
+		mine, total = timestep3d.shard_lattice(res, rank, world, 'cpu')
+		assert mine.shape == (res ** 3, 3) and total == world * res ** 3
 		gathered = [torch.empty_like(mine) for _ in range(world)]
 		dist.all_gather(gathered, mine)
 		allpts = torch.cat(gathered)
 		full = torch.stack(torch.meshgrid(torch.linspace(0, 1, res), torch.linspace(0, 1, res), torch.linspace(0, 1, res * world), indexing='ij'), -1).reshape(-1, 3)
 		key = lambda t: sorted(map(tuple, (t * 1e6).round().to(torch.int64).tolist()))
 		assert key(allpts) == key(full)
+		# 1b. strong scaling: the reference's own res^3 lattice, split by z planes — disjoint, union = the lattice
+		res2 = 6
+		mine2, total2 = timestep3d.shard_lattice(res2, rank, world, 'cpu', scaling='strong')
+		assert total2 == res2 ** 3 and mine2.shape[0] == res2 ** 3 // world
+		gathered = [torch.empty_like(mine2) for _ in range(world)]
+		dist.all_gather(gathered, mine2)
+		full2 = torch.stack(torch.meshgrid(*[torch.linspace(0, 1, res2)] * 3, indexing='ij'), -1).reshape(-1, 3)
+		assert key(torch.cat(gathered)) == key(full2)
+		# 1c. the test losses of the whole lattice from the shards: sum of the shards' loss sums over the total point count
+		loss = (mine2.double() ** 2).sum(-1)
+		sums = loss.sum()[None]
+		dist.all_reduce(sums)
+		assert abs(float(sums) / total2 - float((full2.double() ** 2).sum(-1).mean())) < 1e-9
 		# 2. flat all-reduce buffer layout
 		lay = timestep3d.flat_layout(10, 3, 5)
 		assert lay['acc'] == (0, 360) and lay['lp'] == (360, 384) and lay['lpb'] == (384, 424) and lay['total'] == 424

@@ -206,6 +206,31 @@ def test_optimisation_oracle_matches_reference_project(epochs):
 	assert pr.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
 
 
+def test_optimisation_oracle_gradients_match_reference_project():
+	"""the quantities the reference's step() consumes, iteration by iteration: the raw vorticity / divergence gradient sets as
+	get_losses_ti leaves them, the total .grad after project()'s PCGrad projection + autograd regularisers + boundary pass, the
+	scheduler metric and the learning rates in use — recorded inside the reference's own project() (make_golden_project3d.py).
+	The parameter updates of the test above cannot see a wrong gradient magnitude (Adam's first step is lr * sign(g)); this can."""
+	import os
+	import oracle.oracle as orc
+	g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref3d_project.npz')))
+	tau, mgs = float(g['tau']), float(g['min_grid_scale'])
+	bounds = (0., 1.) * 3
+	prev = orc.OracleGSR(3, orc.extended_bounds(3, bounds, mgs), g['cur_positions'], g['scalings'], g['rotations'], g['values'], tau, mgs, precision='f64')
+	pr = orc.OracleProjector3D(bounds, [g['new_positions'], g['scalings'], g['rotations'], g['values']], prev, float(g['dt']), float(g['boundary_lambda']), tau, mgs)
+	for k in range(3):
+		pr.iterate(g['samples'][k], (g['boundary_data'][k], g['boundary_normal'][k]))
+		tol = 2e-5 * 3 ** k	# the golden is an f32 run; later iterations start from parameters that already differ by rounding
+		for j, nm in enumerate(('positions', 'scalings', 'rotations', 'values')):
+			for tag in ('vor', 'div'):
+				want = g[f'it{k + 1}_{tag}_{nm}_grad']
+				assert rel_err(pr.last[tag][j], want) < tol, (k, tag, nm, rel_err(pr.last[tag][j], want))
+			want = g[f'it{k + 1}_total_{nm}_grad']
+			assert rel_err(pr.last['total'][j], want) < tol, (k, 'total', nm, rel_err(pr.last['total'][j], want))
+		assert pr.last['metric'] == pytest.approx(float(g[f'it{k + 1}_metric']), rel=1e-5)
+		np.testing.assert_allclose(pr.last['lr'], g[f'it{k + 1}_lr_used'], rtol=1e-12)
+
+
 @pytest.mark.parametrize('epochs', [1, 3])
 def test_optimisation_oracle_matches_reference_project_2d(epochs):
 	"""OracleProjector2D against the reference's OWN 2D project() run through the shim (tests/golden/make_golden_project2d.py)"""
@@ -295,3 +320,14 @@ def test_fit_oracle_matches_reference_fit_2d(epochs):
 		assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
 		assert np.abs(d_got - d_ref).max() <= 2e-2 * np.abs(d_ref).max(), (nm, np.abs(d_got - d_ref).max() / np.abs(d_ref).max())
 	assert fit.grid_scale == pytest.approx(float(g[f'after{epochs}_grid_scale']), rel=2e-6)
+
+
+def test_dense_torch_restatement_matches_reference_dense_class():
+	"""oracle.dense_torch_value_gradient (the CPU baseline B2 of bench.py) against the golden made by executing the reference's
+	own GaussianSplatting3D.__call__ / gradient (3D/GSR.py:93-130) in float64"""
+	import torch
+	from oracle.oracle import dense_torch_value_gradient
+	g = load_golden('ref_dense_f64.npz')
+	T = lambda k: torch.tensor(g[k], dtype=torch.float64)
+	u, grad = dense_torch_value_gradient(T('d3_in_positions'), T('d3_in_scalings'), T('d3_in_rotations'), T('d3_in_values'), T('d3_in_x'))
+	assert rel_err(u.numpy(), g['d3_val']) < 1e-12 and rel_err(grad.numpy(), g['d3_grad']) < 1e-12
