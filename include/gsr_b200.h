@@ -303,6 +303,20 @@ int gsr_sample_box(const float *box, int64_t n, uint64_t seed, uint32_t stream_i
 int gsr_sample_box_surface(const float *box, int64_t n, uint64_t seed, uint32_t stream_id, const float *iteration_dev, float *data, float *normal,
 			   void *stream);
 
+/* ---- a8 / N4: reseeding of over-stretched Gaussians (clone_velocity_field, 3D/advance.py:51-94, 2D/advance.py:58-93) ---------------
+ * gsr_split_flags: flags[i] = exp(max_k s_ik - min_k s_ik) >= ratio_threshold (2 in 3D, 1.5 in 2D); *count (device) = how many.
+ * gsr_split_apply: the N + n_split Gaussians after the split — kept ones first in their old order, then the children as
+ *   [first samples of all parents | second samples of all parents] (the reference's `.sample((2,)).flatten(0, 1)` / `.repeat(2, 1)`):
+ *   child position = mu + chol(Sigma) z, Sigma^-1 = R diag(e^{2s}) R^T, clamped to clamp_box (host, {x_min, x_max, ...}; NULL: no
+ *   clamp, as in 2D); child scalings = the parent's with log_axis added on the longest axis and log_all subtracted everywhere
+ *   (3D: ln 2, ln 2 / 3; 2D: ln 1.5, 0); rotations and values copied; out_stop_gradient = 1 for kept, 0 for children.
+ *   flag_prefix: exclusive scan of flags.  normals: (2, n_split, D) standard normals (device) or NULL = Philox + Box-Muller from `seed`. */
+int gsr_split_flags(int D, const float *scalings, int64_t N, float ratio_threshold, int32_t *flags, int32_t *count, void *stream);
+int gsr_split_apply(int D, const float *positions, const float *scalings, const float *rotations, const float *values, int64_t N,
+		    const int32_t *flags, const int32_t *flag_prefix, int64_t n_split, const float *normals, uint64_t seed,
+		    const float *clamp_box, float log_axis, float log_all,
+		    float *out_positions, float *out_scalings, float *out_rotations, float *out_values, int32_t *out_stop_gradient, void *stream);
+
 /* ---- N1: passive density advection on a regular lattice  (advected_density + ti_get_interp_val, 3D/advance_density.py:25-63):
  *          per voxel, RK4 back-trace by `dt` (callers pass -dt) through the field, clamp to `domain`, trilinear resampling of the
  *          old density — one kernel, no lattice or back-traced coordinates in memory.  xs/ys/zs: the lattice's axis coordinates

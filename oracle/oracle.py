@@ -547,6 +547,8 @@ class OracleProjector2D:
 		loss_delta_pos = (dpos ** 2).mean()
 		total[0] = total[0] + .5 * 2. * dpos / dpos.size
 		loss_tot = loss_vor + loss_div + 10. * loss_aniso + 10. * loss_vol + .5 * loss_delta_pos + self.lam * boundary_constraint
+		self.last = {'vor': [np.asarray(a, np.float64).copy() for a in vor], 'div': [np.asarray(a, np.float64).copy() for a in div],
+					 'total': [np.asarray(a, np.float64).copy() for a in total], 'metric': float(loss_tot), 'lr': [o.lr for o in self.opt]}
 		for k in range(4):
 			shape = self.params[k].shape
 			self.params[k] = self.opt[k].step(self.params[k], total[k].reshape(shape))
@@ -591,6 +593,7 @@ class OracleFit3D:
 		gs += (-2. / N * r * (r - (r ** 2).mean()))[:, None]
 		total[1] = total[1] + gs
 		loss = np.abs(np.asarray(val, np.float64) - ref_val).mean() + np.abs(np.asarray(grad, np.float64) - ref_grad).mean() + loss_aniso + loss_vol
+		self.last = {'total': [np.asarray(a, np.float64).copy() for a in total], 'metric': float(loss), 'lr': [o.lr for o in self.opt]}
 		for k in range(4):
 			self.params[k] = self.opt[k].step(self.params[k], total[k])
 			self.opt[k].schedule(float(np.float32(loss)))
@@ -636,6 +639,7 @@ class OracleFit2D:
 		gs += (-2. / N * r * (r - (r ** 2).mean()))[:, None]
 		total[1] = total[1] + gs
 		loss = np.abs(np.asarray(val, np.float64) - ref_val).mean() + np.abs(np.asarray(grad, np.float64) - ref_grad).mean() + loss_aniso + loss_vol
+		self.last = {'total': [np.asarray(a, np.float64).copy() for a in total], 'metric': float(loss), 'lr': [o.lr for o in self.opt]}
 		for k in range(4):
 			shape = self.params[k].shape
 			self.params[k] = self.opt[k].step(self.params[k], total[k].reshape(shape))

@@ -91,7 +91,12 @@ if __name__ == '__main__':
 		def data_gen(batch):
 			x = torch.tensor(samples[it['k']]); it['k'] += 1
 			return x
+		rec = {}
+		ti_shim.record_steps(gv, rec)	# total .grad, metric and lrs at every step()
 		mod.fit_velocity_with_gradient(gv, lambda x: target(x)[0], lambda x: target(x)[1], data_gen, batch_size=Q, max_epoch=epochs, verbose=0)
+		if epochs == max(EPOCHS):
+			assert len(rec['grads']) == epochs
+			ti_shim.store_steps(out, rec)
 		for name in ('positions', 'scalings', 'rotations', 'values'):
 			out[f'after{epochs}_{name}'] = getattr(gv, name).detach().numpy().copy()
 		out[f'after{epochs}_grid_scale'] = np.float64(gv.grid_scale)

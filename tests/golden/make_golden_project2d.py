@@ -104,9 +104,13 @@ if __name__ == '__main__':
 		def gen2(batch):
 			k = it['b2']; it['b2'] += 1
 			return torch.tensor(b2_data[k]), torch.tensor(b2_nrm[k]), torch.tensor(b2_ref[k])
+		rec = {}
+		ti_shim.record_steps(new, rec, 'get_grad_losses')	# raw vor / div sets, total .grad, metric and lrs at every step()
 		mod.project(new, ref, data_gen, lambda gv: None, boundary_generator_1=gen1, boundary_generator_2=gen2, boundary_lambda=BOUNDARY_LAMBDA,
 					batch_size=QB, max_epoch=epochs, patience=500, verbose=0)
-		assert it['k'] == epochs and it['b1'] == epochs and it['b2'] == epochs
+		assert it['k'] == epochs and it['b1'] == epochs and it['b2'] == epochs and len(rec['grads']) == epochs and len(rec['sets']) == epochs
+		if epochs == max(EPOCHS):
+			ti_shim.store_steps(out, rec)
 		for name in ('positions', 'scalings', 'rotations', 'values'):
 			out[f'after{epochs}_{name}'] = getattr(new, name).detach().numpy().copy()
 		out[f'after{epochs}_grid_scale'] = np.float64(new.grid_scale)

@@ -297,3 +297,38 @@ class IdxArr(np.ndarray):
 
 	def __iter__(self):
 		return iter(np.ndindex(*self.shape))
+
+
+def record_steps(gv, rec, set_method=None):
+	"""TEST INFRASTRUCTURE: wrap gv.step (and the loss method that fills the vor_* / div_* gradient sets) so that, at every
+	optimiser step of the reference's own loop, the total .grad Adam consumes, the scheduler metric, the learning rates in use and
+	the raw gradient sets (before the loop's PCGrad projection) are copied into `rec`"""
+	names = ('positions', 'scalings', 'rotations', 'values')
+	orig_step = gv.step
+
+	def step(metrics):
+		rec.setdefault('grads', []).append({nm: getattr(gv, nm).grad.detach().numpy().copy() for nm in names})
+		rec.setdefault('metric', []).append(float(metrics))
+		rec.setdefault('lr', []).append([o.param_groups[0]['lr'] for o in gv.optimizers])
+		return orig_step(metrics)
+	gv.step = step
+	if set_method:
+		orig = getattr(gv, set_method)
+
+		def losses(x, *a, **kw):
+			res = orig(x, *a, **kw)
+			if kw.get('vor_positions_grad') is not None:
+				rec.setdefault('sets', []).append({f'{t}_{nm}': kw[f'{t}_{nm}_grad'].detach().numpy().copy() for t in ('vor', 'div') for nm in names})
+			return res
+		setattr(gv, set_method, losses)
+
+
+def store_steps(out, rec):
+	for k, grads in enumerate(rec.get('grads', [])):
+		for nm, v in grads.items():
+			out[f'it{k + 1}_total_{nm}_grad'] = v
+		out[f'it{k + 1}_metric'] = np.float64(rec['metric'][k])
+		out[f'it{k + 1}_lr_used'] = np.array(rec['lr'][k])
+	for k, sets in enumerate(rec.get('sets', [])):
+		for key, v in sets.items():
+			out[f'it{k + 1}_{key}_grad'] = v

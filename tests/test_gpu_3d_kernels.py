@@ -148,6 +148,55 @@ def test_against_oracle_seeded(n, Q):
 			assert rel_err(a, b) < 5e-4, (tag, nm, rel_err(a, b))
 
 
+@pytest.mark.parametrize('n,Q', [(10, 1000), (10, 6000), (20, 8000), (40, 30000)])
+def test_backward_at_benchmark_scale_is_1e5_on_the_clean_set(n, Q):
+	"""
+	Why the test above needs 5e-4 for the backward pass, and what holds at the north-star tolerance.  The L1 losses differentiate to
+	sign(residual): a sample whose vorticity / helicity residual is within the forward pass's f32 rounding of zero can take the
+	other sign on the GPU than in the float64 oracle, and then a whole +-w term of that sample flips (likewise a pair inside the
+	borderline band of the truncation test appears or disappears).  Those samples are identified with the oracle — residuals
+	below 1e-4 of the residual scale, pairs within 1e-4 q_max of the cut — and left out: on the remaining samples the GPU
+	gradients of every parameter tensor, both gradient sets, agree with the float64 oracle to 1e-5 (f32 accumulation of ~30-60
+	signed terms per Gaussian).  With all samples the error is a handful of flipped +-w terms (each 1 / Q of the loss): loosely bounded.
+	"""
+	from oracle.oracle import OracleGSR, extended_bounds
+	tau = 5e-3
+	P, S, R, V, mgs, gen = synthetic(n)
+	o = make_fast3d(P, S, R, V, tau, mgs)
+	orc = OracleGSR(3, extended_bounds(3, (0., 1.) * 3, mgs), P, S, R, V, tau, mgs, precision='f64', nthreads=8)
+	X = torch.rand((Q, 3), generator=gen)
+	ref_vor = torch.randn((Q, 3), generator=gen) * .1
+	ref_hel = torch.randn((Q,), generator=gen) * .1
+	oval, ograd = orc.forward(X.numpy())
+	om = np.stack((ograd[:, 2, 1] - ograd[:, 1, 2], ograd[:, 0, 2] - ograd[:, 2, 0], ograd[:, 1, 0] - ograd[:, 0, 1]), -1)
+	r_vor = np.abs(om - ref_vor.numpy().astype(np.float64))
+	r_hel = np.abs((oval * om).sum(-1) - ref_hel.numpy().astype(np.float64))
+	risky = (r_vor.min(axis=1) < 1e-4 * np.abs(om).max()) | (r_hel < 1e-4 * np.abs((oval * om).sum(-1)).max()) | (orc.classify_pairs(X.numpy())[1] > 0)
+	assert risky.mean() < .05
+
+	def both(sel):
+		"""(GPU sets, oracle sets) on the samples `sel`, normalised by the same count"""
+		Xs, rv, rh = X[sel].contiguous(), ref_vor[sel].contiguous(), ref_hel[sel].contiguous()
+		acc = {f'{tag}_{nm}_grad': torch.zeros_like(getattr(o, nm)) for tag in ('vor', 'div') for nm in NAMES}
+		o.get_losses(Xs.cuda(), ref_vor=rv.cuda(), weight_vor=1., ref_hel=rh.cuda(), weight_hel=1., weight_div=1., **acc)
+		direct, vor, div = orc.zero_grads(), orc.zero_grads(), orc.zero_grads()
+		v, g_ = orc.forward(Xs.numpy())
+		orc.backward3d(Xs.numpy(), v, g_, ref_vor=rv.numpy(), weight_vor=1., ref_hel=rh.numpy(), weight_hel=1., weight_div=1., direct=direct, vor=vor, div=div)
+		return acc, {'vor': vor, 'div': div}
+	keep = torch.from_numpy(~risky)
+	acc, orc_sets = both(keep)
+	for tag in ('vor', 'div'):
+		for nm, b in zip(NAMES, orc_sets[tag]):
+			a = acc[f'{tag}_{nm}_grad'].cpu().numpy()
+			assert rel_err(a, b) < TOL, (tag, nm, rel_err(a, b))
+	# all samples: at most the risky samples' terms differ — each is one sample's share 1 / Q of the loss
+	acc, orc_sets = both(torch.ones(Q, dtype=torch.bool))
+	for tag in ('vor', 'div'):
+		for nm, b in zip(NAMES, orc_sets[tag]):
+			a = acc[f'{tag}_{nm}_grad'].cpu().numpy()
+			assert rel_err(a, b) < (5e-2 if risky.any() else TOL), (tag, nm, rel_err(a, b), int(risky.sum()))
+
+
 @pytest.mark.parametrize('n,Q', [(10, 3000), (20, 12000), (30, 40000), (34, 70000), (10, 8192), (10, 16384), (12, 33), (10, 1025)])
 def test_hash_paths_agree(n, Q):
 	"""the single-launch hash (n <= 16384), the single-CTA stable counting sort of small sample batches (Q <= 16384 on <= 3200

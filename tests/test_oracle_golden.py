@@ -331,3 +331,45 @@ def test_dense_torch_restatement_matches_reference_dense_class():
 	T = lambda k: torch.tensor(g[k], dtype=torch.float64)
 	u, grad = dense_torch_value_gradient(T('d3_in_positions'), T('d3_in_scalings'), T('d3_in_rotations'), T('d3_in_values'), T('d3_in_x'))
 	assert rel_err(u.numpy(), g['d3_val']) < 1e-12 and rel_err(grad.numpy(), g['d3_grad']) < 1e-12
+
+
+def _check_steps(g, last, k, sets=True):
+	"""one iteration's pre-step quantities against the golden recorded inside the reference's own loop (see the 3D project test)"""
+	tol = 2e-5 * 3 ** k
+	for j, nm in enumerate(('positions', 'scalings', 'rotations', 'values')):
+		for tag in (('vor', 'div') if sets else ()):
+			want = g[f'it{k + 1}_{tag}_{nm}_grad']
+			assert rel_err(last[tag][j].reshape(want.shape), want) < tol, (k, tag, nm, rel_err(last[tag][j].reshape(want.shape), want))
+		want = g[f'it{k + 1}_total_{nm}_grad']
+		assert rel_err(last['total'][j].reshape(want.shape), want) < tol, (k, 'total', nm, rel_err(last['total'][j].reshape(want.shape), want))
+	assert last['metric'] == pytest.approx(float(g[f'it{k + 1}_metric']), rel=1e-5)
+	np.testing.assert_allclose(last['lr'], g[f'it{k + 1}_lr_used'], rtol=1e-12)
+
+
+def test_optimisation_oracle_gradients_match_reference_project_2d():
+	"""2D: raw vorticity / divergence sets of get_grad_losses, total .grad (value samples, PCGrad, normal samples, regularisers
+	incl. the position drift), metric and lrs at every step() of the reference's own 2D project()"""
+	import oracle.oracle as orc
+	g = load_golden('ref2d_project.npz')
+	tau, mgs = float(g['tau']), float(g['min_grid_scale'])
+	dom = tuple(float(v) for v in g['domain'])
+	prev = orc.OracleGSR(2, orc.extended_bounds(2, dom, mgs), g['cur_positions'], g['scalings'], g['rotations'], g['values'], tau, mgs, precision='f64')
+	pr = orc.OracleProjector2D(dom, [g['new_positions'], g['scalings'], g['rotations'], g['values']], prev, float(g['dt']), float(g['boundary_lambda']), tau, mgs, dom)
+	for k in range(3):
+		pr.iterate(g['samples'][k], (g['b1_data'][k], g['b1_val'][k]), (g['b2_data'][k], g['b2_normal'][k], g['b2_ref'][k]))
+		_check_steps(g, pr.last, k)
+
+
+@pytest.mark.parametrize('D', [3, 2])
+def test_fit_oracle_gradients_match_reference_fit(D):
+	"""the total .grad, the metric and the lrs at every step() of the reference's own fit_velocity_with_gradient (3D and 2D)"""
+	import oracle.oracle as orc
+	g = load_golden(f'ref{D}d_fit.npz')
+	if D == 3:
+		bounds = (0., 1.) * 3
+		fit = orc.OracleFit3D(bounds, [g['positions'], g['scalings'], g['rotations'], g['values']], g['lrs'], 5e-3, orc.default_min_grid_scale(3, bounds, g['positions'].shape[0]))
+	else:
+		fit = orc.OracleFit2D(tuple(float(v) for v in g['domain']), [g['positions'], g['scalings'], g['rotations'], g['values']], g['lrs'], float(g['tau']), float(g['min_grid_scale']))
+	for k in range(3):
+		fit.iterate(g['samples'][k], g['ref_val'][k], g['ref_grad'][k])
+		_check_steps(g, fit.last, k, sets=False)
