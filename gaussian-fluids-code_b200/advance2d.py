@@ -55,33 +55,18 @@ def _regularisers(scalings, mask=None):
 	return loss_aniso
 
 
-def clone_velocity_field(res, velocity_field, data_generator, test_data_generator, batch_size=512, max_epoch=3000, patience=500, verbose=1):
-	"""copy velocity_field into res, split Gaussians with axis ratio >= 1.5 in two and refit the new ones (2D/advance.py:58-158)"""
-	device = _dev()
+def clone_velocity_field(res, velocity_field, data_generator, test_data_generator, batch_size=512, max_epoch=3000, patience=500, verbose=1, normals=None, seed=0):
+	"""
+	Copy velocity_field into res, split Gaussians with axis ratio >= 1.5 into two samples of their own distribution (once) and fit
+	the new ones — and their neighbours — to the old field while everything else stays frozen (2D/advance.py:58-158).  The split
+	runs on the device (reseed.py / csrc/split.cu); `normals` ((2, n_split, 2) standard-normal draws) and `seed` reproduce a split.
+	"""
+	from . import reseed
 	with torch.no_grad():
-		res.positions, res.scalings = velocity_field.positions.detach().clone(), velocity_field.scalings.detach().clone()
-		res.rotations, res.values = velocity_field.rotations.detach().clone(), velocity_field.values.detach().clone()
+		for nm in ('positions', 'scalings', 'rotations', 'values'):
+			setattr(res, nm, getattr(velocity_field, nm).detach().clone())
 		res.N = res.positions.shape[0]
-		ratio = torch.exp(res.scalings.max(dim=-1).values - res.scalings.min(dim=-1).values)
-		need_split = ratio >= 1.5
-		n_split = int(need_split.sum().item())
-		if n_split:
-			prec = res.get_variances()[need_split]
-			pos = torch.distributions.MultivariateNormal(res.positions[need_split], precision_matrix=(prec + prec.transpose(-1, -2)) * .5).sample((2,)).flatten(0, 1)
-			rot = res.rotations[need_split].repeat(2)
-			scal = res.scalings[need_split].repeat(2, 1)
-			axis1 = scal[:, 1] < scal[:, 0]
-			scal[axis1, 1] += np.log(1.5)
-			scal[~axis1, 0] += np.log(1.5)
-			val = res.values[need_split].repeat(2, 1)
-			keep = ~need_split
-			res.positions = torch.cat([res.positions[keep], pos], dim=0)
-			res.rotations = torch.cat([res.rotations[keep], rot], dim=0)
-			res.scalings = torch.cat([res.scalings[keep], scal], dim=0)
-			res.values = torch.cat([res.values[keep], val], dim=0)
-			res.N = res.positions.shape[0]
-		stop_gradient = torch.zeros((res.N,), dtype=torch.bool, device=device)
-		stop_gradient[:res.N - 2 * n_split] = True
+		stop_gradient, n_split = reseed.split_all(res, 2, normals=[normals] if normals is not None else None, seed=seed, rounds=1)
 	res.unfreeze()
 	res.zero_grad()
 	if n_split == 0:
@@ -91,7 +76,7 @@ def clone_velocity_field(res, velocity_field, data_generator, test_data_generato
 		print(f'[clone] Add {n_split} particles.')
 	sg = stop_gradient.int()
 
-	def get_losses(data, backward=True):
+	def losses(data, backward):
 		ref_grad, ref_val = velocity_field.gradient(data, need_val=True)
 		if backward:
 			val = res.get_losses(data, ref=ref_val, weight=1., stop_gradient=sg)
@@ -106,26 +91,9 @@ def clone_velocity_field(res, velocity_field, data_generator, test_data_generato
 			(loss_aniso + loss_vol).backward()
 		return loss + loss_grad + loss_aniso + loss_vol, loss, loss_grad
 
-	res.set_lr(positions_lr=1e-2, rotations_lr=5e-2, scalings_lr=5e-2, values_lr=5e-3)
+	res.set_lr(positions_lr=1e-2, rotations_lr=5e-2, scalings_lr=5e-2, values_lr=5e-3)	# 2D/advance.py:120
 	res.initialize_optimizers()
-	check_iter = 100
-	best = [np.inf, np.inf]
-	stale = [0, 0]
-	for epoch in range(max_epoch):
-		loss_tot, _, _ = get_losses(data_generator(batch_size, res, ~stop_gradient))
-		res.step(loss_tot)
-		if epoch % check_iter == check_iter - 1:
-			with torch.no_grad():
-				_, loss, loss_grad = get_losses(test_data_generator(res), backward=False)
-			for k, v in enumerate((loss.item(), loss_grad.item())):
-				if v < best[k] * (1. - 1e-3):
-					best[k], stale[k] = v, 0
-				else:
-					stale[k] += check_iter
-			if verbose:
-				print(f'[clone] loss: {loss.item()}, loss_grad: {loss_grad.item()}')
-			if stale[0] >= patience and stale[1] >= patience:
-				break
+	reseed.refit(res, losses, data_generator, test_data_generator, ~stop_gradient, batch_size, max_epoch, patience, verbose)
 	return res
 
 

@@ -123,57 +123,36 @@ def _regularisers(scalings, stop_gradient=None):
 
 
 def clone_velocity_field(res, velocity_field, x_min, x_max, y_min, y_max, z_min, z_max, data_generator, test_data_generator,
-						 reinitialize=False, batch_size=8192, max_epoch=3000, patience=500, verbose=1):
-	"""copy velocity_field into res, split over-stretched Gaussians and refit the new ones (3D/advance.py:51-165)"""
-	device = _dev()
+						 reinitialize=False, batch_size=8192, max_epoch=3000, patience=500, verbose=1, normals=None, seed=0):
+	"""
+	Copy velocity_field into res, split over-stretched Gaussians (axis ratio >= 2, repeatedly) into two samples of their own
+	distribution and fit the new ones — and their neighbours — to the old field with the value + gradient losses while everything
+	else stays frozen (3D/advance.py:51-165).  The split runs on the device (reseed.py / csrc/split.cu); `normals` (a list of
+	(2, n_split, 3) standard-normal draws, one per round) and `seed` are for reproducing a split.
+	"""
+	from . import reseed
+	names = ('positions', 'scalings', 'rotations', 'values')
 	with torch.no_grad():
-		same = res is not velocity_field and all(getattr(res, nm).shape == getattr(velocity_field, nm).shape and getattr(res, nm).requires_grad
-												 for nm in ('positions', 'scalings', 'rotations', 'values'))
+		same = res is not velocity_field and all(getattr(res, nm).shape == getattr(velocity_field, nm).shape and getattr(res, nm).requires_grad for nm in names)
 		if same:
 			# copy INTO res's tensors: the values are what the reference's `.clone()` gives, and the storage stays where a captured
-			# iteration graph of this field expects it (a split below still replaces the tensors, as in the reference)
-			for nm in ('positions', 'scalings', 'rotations', 'values'):
+			# iteration graph of this field expects it (a split below replaces the tensors, as in the reference)
+			for nm in names:
 				getattr(res, nm).copy_(getattr(velocity_field, nm))
 		else:
-			res.positions, res.scalings = velocity_field.positions.clone(), velocity_field.scalings.clone()
-			res.rotations, res.values = velocity_field.rotations.clone(), velocity_field.values.clone()
+			for nm in names:
+				setattr(res, nm, getattr(velocity_field, nm).detach().clone())
 		res.N = res.positions.shape[0]
-		stop_gradient = torch.ones((res.N,), dtype=torch.bool, device=device)
-		lo = torch.tensor([res.x_min, res.y_min, res.z_min], dtype=torch.float32, device=device)
-		hi = torch.tensor([res.x_max, res.y_max, res.z_max], dtype=torch.float32, device=device)
-		while True:
-			min_scalings, split_axes = res.scalings.min(dim=-1)
-			ratio = torch.exp(res.scalings.max(dim=-1).values - min_scalings)
-			need_split = ratio >= 2.
-			if verbose:
-				print(f'Add {need_split.sum()} particles. {ratio.max()}')
-			if not need_split.any():
-				break
-			if same:	# leave the shared storage alone from here on
-				res.positions, res.scalings, res.rotations, res.values = [getattr(res, nm).detach().clone() for nm in ('positions', 'scalings', 'rotations', 'values')]
-				same = False
-			prec = res.get_variances()[need_split]
-			new_pos = torch.distributions.MultivariateNormal(res.positions[need_split], precision_matrix=(prec + prec.transpose(-1, -2)) * .5).sample((2,)).flatten(0, 1)
-			new_pos.clamp_(lo, hi)
-			new_rot = res.rotations[need_split].repeat(2, 1)
-			res.scalings[need_split, split_axes[need_split]] += np.log(2.)
-			res.scalings[need_split] -= np.log(2.) / 3.
-			new_scal = res.scalings[need_split].repeat(2, 1)
-			new_val = res.values[need_split].repeat(2, 1)
-			keep = ~need_split
-			res.positions = torch.cat([res.positions[keep], new_pos], dim=0)
-			res.rotations = torch.cat([res.rotations[keep], new_rot], dim=0)
-			res.scalings = torch.cat([res.scalings[keep], new_scal], dim=0)
-			res.values = torch.cat([res.values[keep], new_val], dim=0)
-			res.N = res.positions.shape[0]
-			stop_gradient = torch.cat([stop_gradient[keep], torch.zeros((new_pos.shape[0],), dtype=torch.bool, device=device)], dim=0)
+		stop_gradient, n_split = reseed.split_all(res, 3, clamp_box=(res.x_min, res.x_max, res.y_min, res.y_max, res.z_min, res.z_max), normals=normals, seed=seed,
+												  verbose=verbose)
 	res.unfreeze()
 	res.zero_grad()
-	if stop_gradient.all():
+	if n_split == 0:
 		return res
+	# the neighbours of the new Gaussians train too (3D/advance.py:101; the reference applies `~` to an int32 mask there: B.3)
 	stop_gradient = torch.logical_and(stop_gradient, ~res.get_all_neighbors(res.positions[~stop_gradient].detach().contiguous()).bool())
 
-	def get_losses(data, backward=True):
+	def losses(data, backward):
 		ref_val, ref_grad = velocity_field.get_losses(data)
 		if backward:
 			val, grad = res.get_losses(data, ref_val=ref_val, weight_val=1., ref_grad=ref_grad, weight_grad=1., stop_gradient=stop_gradient)
@@ -185,38 +164,11 @@ def clone_velocity_field(res, velocity_field, x_min, x_max, y_min, y_max, z_min,
 			(loss_aniso + loss_vol).backward()
 		return loss_val + loss_grad + loss_aniso + loss_vol, loss_val, loss_grad, loss_aniso, loss_vol
 
-	res.positions_lr = res.rotations_lr = res.scalings_lr = res.values_lr = 1e-3
+	res.positions_lr = res.rotations_lr = res.scalings_lr = res.values_lr = 1e-3	# 3D/advance.py:118-121
 	res.initialize_optimizers()
 	for s in res.schedulers:
 		s.factor = .9
-	test_data = test_data_generator(res)
-	_, loss_val, loss_grad, loss_aniso, loss_vol = get_losses(test_data, backward=False)
-	if verbose:
-		print(f'[clone] loss: {loss_val.item()}, loss_grad: {loss_grad.item()}, loss_aniso: {loss_aniso.item()}, loss_vol: {loss_vol.item()}')
-	st_time = time.time()
-	check_iter = 100
-	best = {'val': np.inf, 'grad': np.inf}
-	stale = {'val': 0, 'grad': 0}
-	for epoch in range(max_epoch):
-		data = data_generator(batch_size, res, ~stop_gradient)
-		loss_tot, loss_val, loss_grad, loss_aniso, loss_vol = get_losses(data)
-		res.step(loss_tot)
-		if epoch % check_iter == check_iter - 1:
-			test_data = test_data_generator(res)
-			_, loss_val, loss_grad, loss_aniso, loss_vol = get_losses(test_data, backward=False)
-			for key, cur in (('val', loss_val.item()), ('grad', loss_grad.item())):
-				if cur < best[key] * (1. - 1e-3):
-					best[key], stale[key] = cur, 0
-				else:
-					stale[key] += check_iter
-			if verbose:
-				print(f'[clone] loss: {loss_val.item()}, loss_grad: {loss_grad.item()}, loss_aniso: {loss_aniso.item()}, loss_vol: {loss_vol.item()}, time: {time.time() - st_time}')
-				st_time = time.time()
-			if stale['val'] >= patience and stale['grad'] >= patience:
-				print('[clone] Total epoch:', epoch + 1)
-				break
-	else:
-		print('[clone] Total epoch:', max_epoch, '(Reached maximum iteration number)')
+	reseed.refit(res, losses, data_generator, test_data_generator, ~stop_gradient, batch_size, max_epoch, patience, verbose)
 	return res
 
 
@@ -411,23 +363,6 @@ def project(gaussian_velocity, reference_field, x_min, x_max, y_min, y_max, z_mi
 	return epochs
 
 
-class _EarlyStop:
-	"""the stopping rule of 3D/advance.py:289-314: every test, a loss must improve by 0.1 % or its stale counter grows"""
-
-	def __init__(self, names, patience, check_iter):
-		self.names, self.patience, self.check_iter = names, patience, check_iter
-		self.best = {k: np.inf for k in names}
-		self.stale = {k: 0 for k in names}
-
-	def update(self, cur):
-		for k in self.names:
-			if cur[k] < self.best[k] * (1. - 1e-3):
-				self.best[k], self.stale[k] = cur[k], 0
-			else:
-				self.stale[k] += self.check_iter
-		return all(self.stale[k] >= self.patience for k in self.names)
-
-
 def _project_pipelined(gv, reference_field, data_generator, test_data_generator, boundary_generator, boundary_lambda, batch_size, max_epoch, patience,
 					   verbose, check_iter, history, rank, world, lattice_world, sample_seed, census, probe, use_graph):
 	"""project() on the captured, pipelined iteration (timestep3d.ShardedProjector).  The projector of a (field, previous field)
@@ -454,7 +389,8 @@ def _project_pipelined(gv, reference_field, data_generator, test_data_generator,
 	if verbose:
 		t = fp.evaluate_global(test, total).tolist()
 		print(f'[projection] loss_vor: {t[0]}, loss_hel: {t[1]}, loss_div: {t[2]}')
-	stop = _EarlyStop(names, patience, check_iter)
+	from .reseed import EarlyStop
+	stop = EarlyStop(names, patience, check_iter)
 	st_time = time.time()
 	fp.begin(census)
 	epochs, done = max_epoch, 0

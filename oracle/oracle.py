@@ -351,6 +351,49 @@ def dense_torch_value_gradient(positions, scalings, rotations, values, x):
 	return per.sum(1), grad
 
 
+def split_gaussians(D, positions, scalings, rotations, values, normals, clamp_box=None):
+	"""
+	The reseeding split of clone_velocity_field, one round, in float64: 3D/advance.py:63-90 (axis ratio >= 2; children's scalings:
+	the split axis += ln 2, every axis -= ln 2 / 3; children clamped to the extended domain) and 2D/advance.py:66-88 (ratio >= 1.5;
+	the smaller of the two log inverse radii += ln 1.5; no clamp).  Child positions = mu + chol(Sigma) z with Sigma^-1 =
+	R diag(e^{2s}) R^T symmetrised — what torch.distributions.MultivariateNormal(mu, precision_matrix=...).sample((2,)) returns for
+	the standard-normal draws z = `normals` (2, n_split, D).  Returns (positions, scalings, rotations, values, stop_gradient) in the
+	reference's layout: kept Gaussians first, then [first samples | second samples].
+	"""
+	P, S, R, V = [np.asarray(a, np.float64) for a in (positions, scalings, rotations, values)]
+	ratio = np.exp(S.max(axis=1) - S.min(axis=1))
+	split = ratio >= (2. if D == 3 else 1.5)
+	ns = int(split.sum())
+	keep = ~split
+	if D == 3:
+		q = R[split] / np.sqrt((R[split] ** 2).sum(axis=1, keepdims=True))
+		r, a, b, c = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+		Rm = np.stack([1 - 2 * (b * b + c * c), 2 * (a * b - r * c), 2 * (a * c + r * b), 2 * (a * b + r * c), 1 - 2 * (a * a + c * c), 2 * (b * c - r * a),
+					   2 * (a * c - r * b), 2 * (b * c + r * a), 1 - 2 * (a * a + b * b)], -1).reshape(-1, 3, 3)
+	else:
+		th = R[split].reshape(-1)
+		Rm = np.stack([np.cos(th), -np.sin(th), np.sin(th), np.cos(th)], -1).reshape(-1, 2, 2)
+	prec = np.einsum('nij,nj,nkj->nik', Rm, np.exp(2. * S[split]), Rm)
+	prec = .5 * (prec + prec.transpose(0, 2, 1))
+	L = np.linalg.cholesky(np.linalg.inv(prec)) if ns else np.zeros((0, D, D))
+	z = np.asarray(normals, np.float64).reshape(2, ns, D)
+	child = P[split][None] + np.einsum('nij,cnj->cni', L, z)
+	Sc = S[split].copy()
+	if D == 3:
+		ax = Sc.argmin(axis=1)
+		Sc[np.arange(ns), ax] += np.log(2.)
+		Sc -= np.log(2.) / 3.
+	else:
+		ax = (Sc[:, 1] < Sc[:, 0]).astype(int)
+		Sc[np.arange(ns), ax] += np.log(1.5)
+	if clamp_box is not None:
+		lo, hi = np.asarray(clamp_box[0::2], np.float64), np.asarray(clamp_box[1::2], np.float64)
+		child = np.minimum(np.maximum(child, lo), hi)
+	rep = lambda a: np.concatenate([a[keep], a[split], a[split]], axis=0)
+	return (np.concatenate([P[keep], child.reshape(2 * ns, D)], axis=0), np.concatenate([S[keep], Sc, Sc], axis=0), rep(R), rep(V),
+			np.concatenate([np.ones(int(keep.sum()), bool), np.zeros(2 * ns, bool)]))
+
+
 class _Adam:
 	"""torch.optim.Adam (defaults: betas .9/.999, eps 1e-8, no weight decay) + ReduceLROnPlateau(mode='min', threshold 1e-4 rel,
 	cooldown 0, eps 1e-8) for one parameter tensor, in float64 (torch works in the tensor's float32)"""

@@ -68,3 +68,111 @@ def test_clone_splits_and_refits_2d():
 	after = new(x)
 	assert torch.isfinite(after).all()
 	assert float((after - before).abs().mean() / before.abs().mean()) < .35
+
+
+def test_clone2d_matches_reference_golden():
+	"""the reference's OWN 2D clone_velocity_field (2D/advance.py:58-158, run through the Taichi shim with its MultivariateNormal
+	draws recorded: tests/golden/make_golden_clone2d.py) against the device split + refit: the field right after the split, the
+	stop_gradient mask after the neighbours of the new Gaussians are unfrozen (integer-exact), the total .grad / metric / lrs at
+	every refit step and the parameters after 1 and 3 steps"""
+	from helpers import NAMES, load_golden, rel_err
+	from test_gpu_gradients_golden import T, check_steps, record_steps
+	from gaussian_fluids_code_b200 import advance2d, gsr2d
+	gsr2d.device = torch.device('cuda', 0)
+	g = load_golden('ref2d_clone.npz')
+	dom = [float(v) for v in g['domain']]
+
+	def field():
+		gv = gsr2d.GaussianSplattingFast(*dom, g['positions'], dim=2)
+		with torch.no_grad():
+			gv.scalings.copy_(T(g['scalings'])); gv.rotations.copy_(T(g['rotations']).reshape(gv.rotations.shape)); gv.values.copy_(T(g['values']))
+		gv.reinitialize_grid()
+		gv.zero_grad()
+		return gv
+	for epochs in (1, 3):
+		src, res = field(), field()
+		snap, masks, rec = {}, [], {}
+		orig_unfreeze, orig_get_losses = res.unfreeze, res.get_losses
+
+		def unfreeze():
+			for nm in NAMES:
+				snap[nm] = getattr(res, nm).detach().cpu().numpy().copy()
+			return orig_unfreeze()
+
+		def get_losses(x, *a, **kw):
+			if kw.get('stop_gradient') is not None:
+				masks.append(kw['stop_gradient'].detach().cpu().numpy().copy())
+			return orig_get_losses(x, *a, **kw)
+		res.unfreeze, res.get_losses = unfreeze, get_losses
+		record_steps(res, rec)
+		datas = iter([T(x) for x in g['samples']])
+		advance2d.clone_velocity_field(res, src, lambda n, gs, restrict=None: next(datas), lambda gs: T(g['test_points']), batch_size=g['samples'].shape[1],
+									   max_epoch=epochs, patience=500, verbose=0, normals=T(g['normals']))
+		assert res.N == g['split_positions'].shape[0]
+		for nm in NAMES:
+			want = g[f'split_{nm}']
+			assert rel_err(snap[nm].reshape(want.shape), want) < 2e-6, nm
+		np.testing.assert_array_equal(masks[0].astype(bool), g['stop_gradient'].astype(bool))
+		check_steps(g, rec, epochs, sets=False)
+		for nm in NAMES:
+			want = g[f'after{epochs}_{nm}']
+			got = getattr(res, nm).detach().cpu().numpy().reshape(want.shape)
+			assert rel_err(got, want) < 1e-5, nm
+			d_ref, d_got = want - g[f'split_{nm}'], got - g[f'split_{nm}'].reshape(want.shape)
+			assert rel_err(d_got, d_ref) < 2e-2, (nm, rel_err(d_got, d_ref))
+
+
+@pytest.mark.parametrize('D', [3, 2])
+def test_device_split_matches_oracle_and_draws_the_right_distribution(D):
+	"""gsr_split_flags + gsr_split_apply against oracle.split_gaussians for given normal draws (3D rule: ratio >= 2, children
+	clamped, repeated rounds handled by the caller; 2D rule: ratio >= 1.5), and — with the built-in Philox draws — the children's
+	sample mean and covariance against mu and Sigma of their parents"""
+	from helpers import rel_err
+	import oracle.oracle as orc
+	from gaussian_fluids_code_b200 import gsr2d, gsr3d, reseed
+	gsr3d.device = gsr2d.device = torch.device('cuda', 0)
+	gen = torch.Generator().manual_seed(5)
+	N = 4000
+	P = torch.rand((N, D), generator=gen) * .6 + .2
+	S = torch.randn((N, D), generator=gen) * .25 + 3.
+	R = torch.randn((N, 4), generator=gen) if D == 3 else (torch.rand((N,), generator=gen) * 6.28 - 3.14)
+	V = torch.randn((N, D), generator=gen)
+
+	class F_:
+		pass
+	f = F_()
+	f.positions, f.scalings, f.rotations, f.values, f.N = P.cuda(), S.cuda(), R.cuda(), V.cuda(), N
+	ratio = torch.exp(S.max(-1).values - S.min(-1).values)
+	ns = int((ratio >= (2. if D == 3 else 1.5)).sum())
+	assert 100 < ns < N
+	z = torch.randn((2, ns, D), generator=gen)
+	box = (0., 1.) * D if D == 3 else None
+	n, flags = reseed.split_once(f, D, clamp_box=box, normals=z)
+	assert n == ns and int(flags.sum()) == ns
+	want = orc.split_gaussians(D, P.numpy(), S.numpy(), R.numpy(), V.numpy(), z.numpy(), clamp_box=box)
+	for got, w in zip((f.positions, f.scalings, f.rotations, f.values), want[:4]):
+		assert rel_err(got.detach().cpu().numpy().reshape(w.shape), w) < 5e-6
+	# Philox draws: many children of ONE parent distribution -> mean and covariance
+	M = 20000
+	one = F_()
+	s1 = torch.tensor([3.0, 3.9, 3.3][:D]) if D == 3 else torch.tensor([3.0, 3.6])
+	one.positions = torch.full((M, D), .5).cuda()
+	one.scalings = s1.repeat(M, 1).cuda()
+	one.rotations = (torch.tensor([.3, -.5, .7, .2]).repeat(M, 1) if D == 3 else torch.full((M,), .4)).cuda()
+	one.values = torch.zeros((M, D)).cuda()
+	one.N = M
+	n, _ = reseed.split_once(one, D, seed=11)
+	assert n == M
+	kids = one.positions.detach()[-2 * M:].double().cpu().numpy()
+	# Sigma of the parent from the oracle's own construction
+	q = one.rotations[:1].double().cpu().numpy()
+	if D == 3:
+		q = q / np.sqrt((q ** 2).sum())
+		r, a, b, c = q[0]
+		Rm = np.array([[1 - 2 * (b * b + c * c), 2 * (a * b - r * c), 2 * (a * c + r * b)], [2 * (a * b + r * c), 1 - 2 * (a * a + c * c), 2 * (b * c - r * a)],
+					   [2 * (a * c - r * b), 2 * (b * c + r * a), 1 - 2 * (a * a + b * b)]])
+	else:
+		Rm = np.array([[np.cos(.4), -np.sin(.4)], [np.sin(.4), np.cos(.4)]])
+	Sigma = Rm @ np.diag(np.exp(-2. * s1.double().numpy())) @ Rm.T
+	assert np.abs(kids.mean(0) - .5).max() < 4. * np.sqrt(Sigma.max() / (2 * M))
+	assert np.abs(np.cov(kids.T) - Sigma).max() < .05 * np.abs(Sigma).max()

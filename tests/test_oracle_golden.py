@@ -373,3 +373,16 @@ def test_fit_oracle_gradients_match_reference_fit(D):
 	for k in range(3):
 		fit.iterate(g['samples'][k], g['ref_val'][k], g['ref_grad'][k])
 		_check_steps(g, fit.last, k, sets=False)
+
+
+def test_split_restatement_matches_reference_clone_2d():
+	"""oracle.split_gaussians (the reseeding split of clone_velocity_field) against the golden recorded inside the reference's own
+	2D clone_velocity_field (tests/golden/make_golden_clone2d.py): the field right after the split for the recorded normal draws"""
+	import oracle.oracle as orc
+	g = load_golden('ref2d_clone.npz')
+	P, S, R, V, stop = orc.split_gaussians(2, g['positions'], g['scalings'], g['rotations'], g['values'], g['normals'])
+	assert P.shape[0] == g['split_positions'].shape[0] == g['positions'].shape[0] + g['normals'].shape[1]
+	assert rel_err(P, g['split_positions']) < 2e-6 and rel_err(S, g['split_scalings']) < 1e-6
+	assert rel_err(R.reshape(-1), g['split_rotations'].reshape(-1)) < 1e-7 and rel_err(V, g['split_values']) < 1e-7
+	# untouched Gaussians far from every child stay frozen in the golden; children never are
+	assert not g['stop_gradient'][~stop].any() and (g['stop_gradient'] <= stop).all()
