@@ -21,8 +21,23 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+	"""One builder at a time (ranks of a multi-process launch all import the package: the first one in builds, the others wait on
+	the lock and find the library fresh); objects go to a per-process directory and the library is renamed into place, so a
+	reader never maps a half-written file."""
 	if not force and not needs_build():
 		return SO
+	import fcntl
+	with open(os.path.join(CSRC, '.build.lock'), 'w') as lock:
+		fcntl.flock(lock, fcntl.LOCK_EX)
+		try:
+			if not force and not needs_build():
+				return SO
+			return _build_locked(verbose)
+		finally:
+			fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
 	nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 	objs, procs = [], []
 	os.makedirs(os.path.join(CSRC, 'build'), exist_ok=True)
@@ -37,8 +52,10 @@ def build(force=False, verbose=False):
 			print(out)
 		if p.returncode != 0:
 			raise RuntimeError('nvcc failed: ' + ' '.join(cmd) + '\n' + out)
-	cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', SO] + objs
+	tmp = f'{SO}.{os.getpid()}.tmp'
+	cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', tmp] + objs
 	subprocess.run(cmd, check=True)
+	os.replace(tmp, SO)
 	return SO
 
 

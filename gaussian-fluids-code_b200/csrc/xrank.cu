@@ -11,6 +11,7 @@
 // iteration's gather while a slower peer is still summing this one.  The wait is bounded: on a timeout the kernel raises an
 // error flag instead of hanging the GPU.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace gsr {
 
@@ -30,12 +31,14 @@ __device__ __forceinline__ float4 ld_peer4(const float4 *p)
 
 constexpr int XR_THREADS = 256;
 constexpr int XR_MAX_WORLD = 16;
-constexpr unsigned XR_SPIN_LIMIT = 1u << 21;	// polls of the local signal pad (~1 s) before giving up; once the flag is up nobody waits again
+constexpr unsigned XR_SPIN_LIMIT = 1u << 23;	// default polls of the local signal pad (a few seconds: first-use module loads and graph
+						// captures on a peer are legitimate skew) before giving up; once the flag is up nobody waits again
 
 struct XrankArgs {
 	const float4 *peer[XR_MAX_WORLD];	// every rank's buffer of this parity (own rank included), n4 float4 each
 	uint32_t *sig[XR_MAX_WORLD];		// every rank's signal pad: slot [sender rank] holds the sender's last complete epoch
 	int rank, world;
+	unsigned spin_limit;
 };
 
 __global__ void __launch_bounds__(XR_THREADS) xrank_sum_kernel(XrankArgs a, size_t n4, const float *__restrict__ iter_dev, const int32_t *__restrict__ base_dev,
@@ -50,14 +53,22 @@ __global__ void __launch_bounds__(XR_THREADS) xrank_sum_kernel(XrankArgs a, size
 		const uint32_t *mine = a.sig[a.rank] + threadIdx.x;
 		unsigned spins = 0;
 		while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-			if (++spins > XR_SPIN_LIMIT) {
+			if (++spins > a.spin_limit) {
 				atomicExch(err, 1);
 				break;
 			}
 		}
 	}
 	__syncthreads();
+	// a peer that never published (or an earlier timeout): its buffer is not this epoch's — hand the step ZERO sample gradients
+	// instead of a sum over stale data (the step then only applies the regularisers; the caller sees the sticky flag at its next
+	// check and raises), so the parameters stay finite and the replicas do not silently diverge on garbage
+	const bool bad = *((volatile int32_t *)err) != 0;
 	for (size_t i = (size_t)blockIdx.x * XR_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * XR_THREADS) {
+		if (bad) {
+			out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+			continue;
+		}
 		float4 s = ld_peer4(a.peer[0] + i);
 		for (int r = 1; r < a.world; r++) {
 			const float4 v = ld_peer4(a.peer[r] + i);
@@ -86,6 +97,11 @@ extern "C" int gsr_xrank_sum(const void *const *peer_bufs, void *const *peer_sig
 	}
 	a.rank = rank;
 	a.world = world;
+	static const unsigned spin = []() {
+		const char *e = getenv("GSR_XRANK_SPIN_LIMIT");	// polls before a missing peer is declared lost
+		return e ? (unsigned)strtoul(e, nullptr, 10) : XR_SPIN_LIMIT;
+	}();
+	a.spin_limit = spin;
 	const size_t n4 = (size_t)n_floats / 4;
 	int blocks = (int)((n4 + XR_THREADS - 1) / XR_THREADS);
 	if (blocks > kSMs) blocks = kSMs;	// all CTAs resident: every one of them polls the signal pad

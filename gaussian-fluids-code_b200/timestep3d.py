@@ -114,7 +114,9 @@ class PeerExchange:
 		dist.barrier()	# every rank's buffers are zeroed and mapped before anyone signals
 
 	def new_phase(self):
-		"""epochs are base + iteration + 1: a new optimisation phase (iteration counter back to 0) moves the base past the old ones"""
+		"""epochs are base + iteration + 1: a new optimisation phase (iteration counter back to 0) moves the base past the old ones;
+		a timeout flag of the previous phase is reported here at the latest"""
+		self.check()
 		self._base_host += 100000
 		self.base.fill_(self._base_host)
 
@@ -413,6 +415,8 @@ class ShardedProjector(advance3d.FusedProjector):
 	def evaluate_global(self, data, total=None, probe=None, census=None):
 		"""the test losses over the WHOLE lattice: `data` is this rank's share, `total` the number of points of all ranks"""
 		Q = data.shape[0]
+		if self.peer:
+			self.peer.check()	# (this call synchronises anyway) a lost peer is reported within check_iter iterations, not at the end of the phase
 		sums = self.evaluate(data, probe=probe) * Q
 		if census is not None:
 			census.count(self.ref.velocity_field._engine, data, 5, lattice=True)

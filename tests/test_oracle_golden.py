@@ -386,3 +386,30 @@ def test_split_restatement_matches_reference_clone_2d():
 	assert rel_err(R.reshape(-1), g['split_rotations'].reshape(-1)) < 1e-7 and rel_err(V, g['split_values']) < 1e-7
 	# untouched Gaussians far from every child stay frozen in the golden; children never are
 	assert not g['stop_gradient'][~stop].any() and (g['stop_gradient'] <= stop).all()
+
+
+def test_clone_refit_gradients_match_reference_clone_2d():
+	"""the first refit iteration of the reference's 2D clone_velocity_field (2D/advance.py:96-120): value + gradient L1 losses of
+	the split field against the source field with the frozen Gaussians skipped (GSR.py:291, :404).  The recorded batches lie inside
+	the split parents' support — elsewhere res == src up to rounding and sign(val - ref) is a coin flip in any implementation."""
+	import oracle.oracle as orc
+	g = load_golden('ref2d_clone.npz')
+	tau, mgs = float(g['tau']), float(g['min_grid_scale'])
+	ext = orc.extended_bounds(2, tuple(float(v) for v in g['domain']), mgs)
+	src = orc.OracleGSR(2, ext, g['positions'], g['scalings'], g['rotations'], g['values'], tau, mgs)
+	res = orc.OracleGSR(2, ext, g['split_positions'], g['split_scalings'], g['split_rotations'], g['split_values'], tau, mgs)
+	assert np.array_equal(res.mark_neighbors(g['split_positions'][-2 * g['normals'].shape[1]:]).astype(bool) | (np.arange(res.N) >= g['positions'].shape[0] - g['normals'].shape[1]),
+						  ~g['stop_gradient'].astype(bool))
+	x = g['samples'][0]
+	ref_val, ref_grad = src.forward(x)
+	val, grad = res.forward(x)
+	d = res.zero_grads()
+	sg = g['stop_gradient'].astype(np.int32)
+	res.backward2d_val(x, val, ref=ref_val, weight=1., stop_gradient=sg, direct=d)
+	res.backward2d_grad(x, grad, ref_grad=ref_grad, weight_grad=1., stop_gradient=sg, direct=d)
+	for k, nm in enumerate(NAMES):
+		if nm == 'scalings':	# + the autograd regularisers, covered by the CUDA test
+			continue
+		want = g[f'it1_total_{nm}_grad']
+		assert np.abs(want).max() > 0
+		assert rel_err(np.asarray(d[k]).reshape(want.shape), want) < 2e-5, nm
