@@ -122,6 +122,9 @@ def advect_covector_field(covector_field, velocity_field, dt, advection_scheme='
 
 PROJECT_WEIGHTS = dict(vor=1., div=1., aniso=10., vol=10., delta_pos=.5)	# 2D/advance.py:198
 PROJECT_LRS = dict(positions=1e-4, scalings=1e-4, rotations=1e-4, values=1e-4)	# 2D/advance.py:261
+KARMAN_LR_RATIO = 1.201956	# 2D/initialize.py:125, :163
+INIT_PROJECT_WEIGHTS = dict(vor=1., div=10., aniso=10., vol=10., delta_pos=0.)	# 2D/initialize.py:55
+INIT_PROJECT_LRS = dict(positions=1e-4, scalings=1e-5, rotations=1e-5 * KARMAN_LR_RATIO, values=1e-4)	# 2D/initialize.py:126
 
 
 class FusedProjector2D:
@@ -207,11 +210,11 @@ class FusedProjector2D:
 		gv._engine.build(gv.positions.detach())
 
 
-def _project_unfused(gv, reference_field, data_generator, test_data_generator, b1, b2, lam, batch_size, max_epoch, patience, verbose, check_iter):
+def _project_unfused(gv, reference_field, data_generator, test_data_generator, b1, b2, lam, batch_size, max_epoch, patience, verbose, check_iter, weights=None):
 	"""the reference's formulation, statement by statement (2D/advance.py:187-302)"""
 	device = _dev()
 	positions_org = gv.positions.detach().clone()
-	w = PROJECT_WEIGHTS
+	w = dict(PROJECT_WEIGHTS, **(weights or {}))
 
 	def gradient_project(g1, g2):
 		if (g1 * g2).sum() < 0.:
@@ -268,22 +271,24 @@ def _project_unfused(gv, reference_field, data_generator, test_data_generator, b
 
 
 def project(gaussian_velocity, reference_field, data_generator, test_data_generator, boundary_generator_1=None, boundary_generator_2=None,
-			boundary_lambda=0., batch_size=512, max_epoch=3000, patience=500, verbose=1, fused=True, check_iter=100):
+			boundary_lambda=0., batch_size=512, max_epoch=3000, patience=500, verbose=1, fused=True, check_iter=100, weights=None, lrs=None):
 	"""
 	One time step's projection by first-order optimisation (2D/advance.py:187-302): match the advected vorticity, drive
 	the divergence to zero, keep the Gaussians well shaped and close to their advected positions.  Early stop: every 100
 	iterations, vorticity must improve by 0.1 % or divergence by 1 %, `patience` iterations without either ends the phase.
-	Returns the number of iterations run.
+	Returns the number of iterations run.  `weights` / `lrs` override PROJECT_WEIGHTS / PROJECT_LRS: the reference keeps a second
+	copy of this function with other constants for the Karman initial state (2D/initialize.py:44-160, INIT_PROJECT_* below).
 	"""
 	gv = gaussian_velocity
-	gv.set_lr(positions_lr=PROJECT_LRS['positions'], scalings_lr=PROJECT_LRS['scalings'], rotations_lr=PROJECT_LRS['rotations'], values_lr=PROJECT_LRS['values'])
+	lr = dict(PROJECT_LRS, **(lrs or {}))
+	gv.set_lr(positions_lr=lr['positions'], scalings_lr=lr['scalings'], rotations_lr=lr['rotations'], values_lr=lr['values'])
 	gv.initialize_optimizers(patience=50)
 	for s in gv.schedulers:
 		s.factor = .9
 	if not fused:
 		return _project_unfused(gv, reference_field, data_generator, test_data_generator, boundary_generator_1, boundary_generator_2, boundary_lambda,
-								batch_size, max_epoch, patience, verbose, check_iter)
-	fp = FusedProjector2D(gv, reference_field, boundary_lambda, patience=50)
+								batch_size, max_epoch, patience, verbose, check_iter, weights)
+	fp = FusedProjector2D(gv, reference_field, boundary_lambda, patience=50, weights=weights, lrs=lrs)
 	best, stale = [np.inf, np.inf], [0, 0]
 	epochs = max_epoch
 	st_time = time.time()
@@ -357,14 +362,46 @@ def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gra
 	e.build(gv.positions.detach())
 
 
-def simulation_initialize(scene, max_epoch=10000, verbose=1, fused=True):
-	"""SimulationInitialize of 2D/initialize.py:187-238 without the plots: lattice of Gaussians -> fit -> the frame-0 field"""
+def init_karman_velocity(gaussian_velocity, scene, reference_field, reference_gradient, data_generator, batch_size=512, max_epoch=3000, verbose=1, fused=True,
+						 project_epochs=10000):
+	"""
+	The Karman initial state (2D/initialize.py:162-185): fit the uniform inflow with ten times smaller scaling / rotation rates than
+	the other scenes, then project the fit onto the divergence-free fields that respect the obstacle and the channel walls — a
+	`project` against the field's own vorticity (dt = 0) with the initial-state constants (divergence weight 10, no position
+	anchor, lrs 1e-4 / 1e-5 / 1.2e-5 / 1e-4), boundary weight 10, samples and test lattice on the advance domain, and an early stop
+	that cannot trigger before `project_epochs` (patience = max_epoch = 10000 in the reference).
+	"""
+	gv = gaussian_velocity
+	gv.set_lr(positions_lr=1.6e-4 * 10., scalings_lr=5e-3, rotations_lr=5e-3 * KARMAN_LR_RATIO, values_lr=5e-4 * 10.)
+	fit_velocity_with_gradient(gv, reference_field, reference_gradient, data_generator, batch_size, max_epoch, verbose, fused=fused)
+	x_min, x_max, y_min, y_max = scene.scaled(scene.initialize_domain)
+	x_N, y_N = scene.particle_count
+	tmp = gsr2d.GaussianSplattingFast(x_min, x_max, y_min, y_max, gsr2d.get_grid_points(x_min, x_max, y_min, y_max, x_N, y_N).cpu().numpy(), dim=2)
+	with torch.no_grad():
+		for nm in ('positions', 'scalings', 'rotations', 'values'):
+			setattr(tmp, nm, getattr(gv, nm).detach().clone())
+		tmp.N = tmp.positions.shape[0]
+	tmp.unfreeze()
+	tmp.zero_grad()
+	b1, b2 = scene.boundary_samplers
+	ref = AdvectedCovectorField(tmp, tmp, 0., domain=scene.scaled(scene.advance_domain))
+	return project(gv, ref, lambda n, gs, restrict=None: scene.data_generator(gs), lambda gs: scene.test_generator(), boundary_generator_1=b1, boundary_generator_2=b2,
+				   boundary_lambda=10., patience=project_epochs, max_epoch=project_epochs, verbose=verbose, fused=fused, weights=INIT_PROJECT_WEIGHTS, lrs=INIT_PROJECT_LRS)
+
+
+def simulation_initialize(scene, max_epoch=10000, verbose=1, fused=True, project_epochs=10000):
+	"""SimulationInitialize of 2D/initialize.py:187-238 without the plots: lattice of Gaussians -> fit (karman: -> projection onto
+	the boundary conditions) -> the frame-0 field"""
 	x_min, x_max, y_min, y_max = scene.scaled(scene.initialize_domain)
 	x_N, y_N = scene.particle_count
 	pts = gsr2d.get_grid_points(x_min, x_max, y_min, y_max, x_N, y_N).cpu().numpy()
 	gv = gsr2d.GaussianSplattingFast(x_min, x_max, y_min, y_max, pts, dim=2)
+	gen = lambda n: scene.data_generator(gv, domain=scene.initialize_domain)
+	if scene.name == 'karman':
+		init_karman_velocity(gv, scene, scene.target_velocity, scene.target_gradient, gen, max_epoch=max_epoch, verbose=verbose, fused=fused, project_epochs=project_epochs)
+		return gv
 	gv.set_lr(positions_lr=1.6e-3, scalings_lr=5e-2, rotations_lr=5e-2, values_lr=5e-3)
-	fit_velocity_with_gradient(gv, scene.target_velocity, scene.target_gradient, lambda n: scene.data_generator(gv), max_epoch=max_epoch, verbose=verbose, fused=fused)
+	fit_velocity_with_gradient(gv, scene.target_velocity, scene.target_gradient, gen, max_epoch=max_epoch, verbose=verbose, fused=fused)
 	return gv
 
 

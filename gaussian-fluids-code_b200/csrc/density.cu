@@ -38,7 +38,7 @@ constexpr int DN_P = 4;
 
 // CTA = 8 x 8 x 8 voxels, 4 warps; warp w owns the 4 x 4 x 8 block at (4 (w / 2), 4 (w % 2), 0); slot p of lane l is voxel
 // v = 32 p + l of that block, (v / 32, (v / 8) % 4, v % 8).  NF density fields are advected through the same back-trace.
-template <int NF>
+template <int NF, bool COUNT = false>
 __global__ void __launch_bounds__(128, 4) advect_density_kernel(TiledArgs a, LatticeArgs L, float dt, const float *__restrict__ f0, const float *__restrict__ f1,
 								  float *__restrict__ o0, float *__restrict__ o1)
 {
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128, 4) advect_density_kernel(TiledArgs a, Lat
 	const float hdt = dt * .5f, dt6 = dt / 6.f;
 #pragma unroll 1
 	for (int st = 0; st < 4; st++) {	// RK4 of x' = u(x), positions only (3D/GSR.py:639-658)
-		warp_eval3<P, false, true>(a, sh, nullptr, px, py, pz, ok, v, dummy);
+		warp_eval3<P, false, true, COUNT>(a, sh, nullptr, px, py, pz, ok, v, dummy);
 		const float wgt = (st == 0 || st == 3) ? 1.f : 2.f, step = (st < 2) ? hdt : dt;
 #pragma unroll
 		for (int p = 0; p < P; p++) {
@@ -87,9 +87,9 @@ __global__ void __launch_bounds__(128, 4) advect_density_kernel(TiledArgs a, Lat
 
 using namespace gsr;
 
-extern "C" int gsr_advect_density_slab(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,
-				       const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, int x_begin, int x_end, const float *domain, float dt,
-				       const float *density_a, const float *density_b, float *out_a, float *out_b, void *stream)
+static int advect_density_launch(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull, const float *xs, const float *ys,
+				 const float *zs, int nx, int ny, int nz, int x_begin, int x_end, const float *domain, float dt, const float *density_a,
+				 const float *density_b, float *out_a, float *out_b, unsigned long long *executed, void *stream)
 {
 	Grid g;
 	if (!make_grid(d, g) || g.D != 3 || !cell_start || !packed || !xs || !ys || !zs || nx < 2 || ny < 2 || nz < 2 || !domain || !density_a || !out_a) return GSR_EINVAL;
@@ -101,15 +101,35 @@ extern "C" int gsr_advect_density_slab(const gsr_grid_desc *d, const int32_t *ce
 	a.P = make_params(g);
 	a.cell_start = cell_start; a.packed = (const float4 *)packed; a.cull = cull;
 	a.x = nullptr; a.Q = 0; a.perm = nullptr; a.scs = nullptr; a.tile_row = nullptr; a.cap = 0;
+	a.exec_count = executed;
 	LatticeArgs L;
 	L.xs = xs; L.ys = ys; L.zs = zs; L.nx = nx; L.ny = ny; L.nz = nz; L.x_begin = x_begin; L.x_end = x_end;
 	for (int k = 0; k < 3; k++) { L.lo[k] = domain[2 * k]; L.hi[k] = domain[2 * k + 1]; }
 	dim3 grid((x_end - x_begin + 7) / 8, (ny + 7) / 8, (nz + 7) / 8);
 	g_launches += 1;
-	if (density_b) advect_density_kernel<2><<<grid, 128, 0, st>>>(a, L, dt, density_a, density_b, out_a, out_b);
+	if (executed) {	// census variant: same arithmetic, plus the count of pair tests the culling lets through
+		if (density_b) advect_density_kernel<2, true><<<grid, 128, 0, st>>>(a, L, dt, density_a, density_b, out_a, out_b);
+		else advect_density_kernel<1, true><<<grid, 128, 0, st>>>(a, L, dt, density_a, nullptr, out_a, nullptr);
+	} else if (density_b) advect_density_kernel<2><<<grid, 128, 0, st>>>(a, L, dt, density_a, density_b, out_a, out_b);
 	else advect_density_kernel<1><<<grid, 128, 0, st>>>(a, L, dt, density_a, nullptr, out_a, nullptr);
 	GSR_CHECK_LAUNCH();
 	return GSR_OK;
+}
+
+extern "C" int gsr_advect_density_slab(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,
+				       const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, int x_begin, int x_end, const float *domain, float dt,
+				       const float *density_a, const float *density_b, float *out_a, float *out_b, void *stream)
+{
+	return advect_density_launch(d, cell_start, packed, cull, xs, ys, zs, nx, ny, nz, x_begin, x_end, domain, dt, density_a, density_b, out_a, out_b, nullptr, stream);
+}
+
+extern "C" int gsr_advect_density_census(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,
+					 const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, int x_begin, int x_end, const float *domain, float dt,
+					 const float *density_a, const float *density_b, float *out_a, float *out_b, unsigned long long *executed_pair_tests, void *stream)
+{
+	if (!executed_pair_tests) return GSR_EINVAL;
+	return advect_density_launch(d, cell_start, packed, cull, xs, ys, zs, nx, ny, nz, x_begin, x_end, domain, dt, density_a, density_b, out_a, out_b,
+				     executed_pair_tests, stream);
 }
 
 extern "C" int gsr_advect_density(const gsr_grid_desc *d, const int32_t *cell_start, const float *packed, const float *cull,

@@ -357,6 +357,7 @@ static TiledArgs make_targs(const EvalParams &P, const int32_t *cell_start, cons
 			    const int32_t *scs, const int32_t *tile_row)
 {
 	TiledArgs a;
+	a.exec_count = nullptr;
 	a.P = P; a.cell_start = cell_start; a.packed = (const float4 *)packed; a.cull = cull; a.x = x; a.Q = (int)Q; a.perm = perm; a.scs = scs; a.tile_row = tile_row;
 	a.cap = g_tiled_cap;
 	return a;

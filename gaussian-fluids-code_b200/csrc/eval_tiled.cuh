@@ -46,6 +46,7 @@ struct TiledArgs {
 	const int32_t *cell_start;
 	const float4 *packed;
 	const float *cull;	// per Gaussian (cell order): (1 + margin) / lambda_min(Sigma^-1), or NULL (no culling)
+	unsigned long long *exec_count;	// census instantiations only (COUNT): + 32 P per candidate that survives the warp's culling
 	const float *x;
 	int Q;
 	const int32_t *perm;
@@ -150,7 +151,7 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >>
 //     cull = (1 + margin) / lambda_min(Sigma^-1), from gsr_pack_gaussians) misses the bounding box of the warp's 32 P
 //     points is skipped by a uniform branch before its covariance is even loaded;
 //   * the survivors are tested on point PAIRS with packed FP32 (f32x2.cuh): 14 FFMA2/FMUL2/FADD2 per two points.
-template <int P, bool NEED_GRAD, bool PREFETCH>
+template <int P, bool NEED_GRAD, bool PREFETCH, bool COUNT = false>
 __device__ __forceinline__ void warp_eval3(const TiledArgs &a, const TileSh &sh, const float4 *srec, const float (&x)[P], const float (&y)[P],
 					   const float (&z)[P], const bool (&ok)[P], float (&u)[P][3], float (&G)[P][9])
 {
@@ -272,6 +273,7 @@ __device__ __forceinline__ void warp_eval3(const TiledArgs &a, const TileSh &sh,
 						}
 						unsigned mask = __ballot_sync(FULL, keep);
 						const unsigned smask = __ballot_sync(FULL, st_c);
+						if (COUNT && lane == 0 && mask) atomicAdd(a.exec_count, (unsigned long long)__popc(mask) * 32ull * P);
 						// survivors, in cell-sorted order; everything below is warp-uniform.  The record of the NEXT survivor
 						// is requested before the current one is evaluated (the loads are the only long-latency step left).
 						int ci = 0;

@@ -319,12 +319,19 @@ class HashEngine:
 											  ptr(data), ptr(normal), stream()), 'gsr_sample_box_surface')
 		return data, normal
 
-	def advect_density(self, axes, domain, dt, density_a, out_a, density_b=None, out_b=None, x_range=None):
+	def advect_density(self, axes, domain, dt, density_a, out_a, density_b=None, out_b=None, x_range=None, executed=None):
 		"""gsr_advect_density(_slab): semi-Lagrangian step of one or two density fields on the lattice spanned by `axes` = (xs, ys, zs);
-		x_range = (begin, end): only those x planes of the outputs are computed (a process's slab)"""
+		x_range = (begin, end): only those x planes of the outputs are computed (a process's slab); executed (1 int64, device): run the
+		census instantiation, which also adds the number of pair tests that survive the culling (measurement only)"""
 		xs, ys, zs = axes
 		dom = (C.c_float * 6)(*[float(v) for v in domain])
 		x0, x1 = x_range if x_range is not None else (0, xs.numel())
+		if executed is not None:
+			check(self.lib.gsr_advect_density_census(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True), ptr(self.cull),
+													 ptr(xs), ptr(ys), ptr(zs), C.c_int(xs.numel()), C.c_int(ys.numel()), C.c_int(zs.numel()), C.c_int(int(x0)), C.c_int(int(x1)),
+													 dom, C.c_float(dt), ptr(density_a, name='density'), ptr(density_b, allow_none=True), ptr(out_a), ptr(out_b, allow_none=True),
+													 ptr(executed, torch.int64), stream()), 'gsr_advect_density_census')
+			return
 		check(self.lib.gsr_advect_density_slab(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.packed, align16=True), ptr(self.cull),
 											   ptr(xs), ptr(ys), ptr(zs), C.c_int(xs.numel()), C.c_int(ys.numel()), C.c_int(zs.numel()), C.c_int(int(x0)), C.c_int(int(x1)),
 											   dom, C.c_float(dt), ptr(density_a, name='density'), ptr(density_b, allow_none=True), ptr(out_a), ptr(out_b, allow_none=True),

@@ -188,9 +188,10 @@ class Scene2D:
 			self.advance_domain[0] = min(self.initialize_domain[0] + (start_frame * dt) * self.info['v_magnitude'], self.visualize_domain[0])
 
 	# ---- samplers -------------------------------------------------------------------------------------------------
-	def data_generator(self, gaussian_splatting):
-		"""default_data_generator of 2D/advance.py:314-316 / initialize.py: Q = N uniform samples of the advance domain, GSR space"""
-		x_min, x_max, y_min, y_max = self.advance_domain
+	def data_generator(self, gaussian_splatting, domain=None):
+		"""default_data_generator of 2D/advance.py:314-316: Q = N uniform samples of the advance domain, GSR space (the initial fit,
+		2D/initialize.py:216-217, draws them on the initialize domain: pass it as `domain`)"""
+		x_min, x_max, y_min, y_max = domain if domain is not None else self.advance_domain
 		dev = _dev()
 		return (torch.rand_like(gaussian_splatting.positions.detach(), device=dev) * torch.tensor([x_max - x_min, y_max - y_min], device=dev)
 				+ torch.tensor([x_min, y_min], device=dev)) * self.scaling_factor

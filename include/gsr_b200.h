@@ -335,6 +335,12 @@ int gsr_advect_density_slab(const gsr_grid_desc *g, const int32_t *cell_start, c
 /* counts[0] (device uint64) += candidate visits C for one evaluation of the Q points (occupancy of each point's 27 (9)-cell
  * stencil under the reference binning: the unit of work of SURVEY 8d); when packed != NULL also counts[1] += accepted pairs P. */
 int gsr_count_pairs(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed, const float *x, int64_t Q, uint64_t *counts, void *stream);
+/* gsr_advect_density_slab, and *executed_pair_tests (device uint64) += the (voxel, candidate) pair tests the kernel really runs: a
+ * candidate that survives the warp-level culling is tested on all 32 x 4 voxels of the warp, four times (RK4).  bench.py forms the
+ * density kernel's roofline fraction from this count; gsr_count_pairs over the same voxels gives the un-culled stencil occupancy. */
+int gsr_advect_density_census(const gsr_grid_desc *g, const int32_t *cell_start, const float *packed, const float *cull,
+			      const float *xs, const float *ys, const float *zs, int nx, int ny, int nz, int x_begin, int x_end, const float *domain, float dt,
+			      const float *density_a, const float *density_b, float *out_a, float *out_b, unsigned long long *executed_pair_tests, void *stream);
 /* runs an FFMA-only / ex2.approx-only loop on every SM; returns elapsed ms via *ms (host sync inside) */
 int gsr_peak_fma(int iters, double *tflops, void *stream);
 int gsr_peak_mufu(int iters, double *tops, void *stream);

@@ -165,7 +165,7 @@ def test_device_split_matches_oracle_and_draws_the_right_distribution(D):
 	assert n == M
 	kids = one.positions.detach()[-2 * M:].double().cpu().numpy()
 	# Sigma of the parent from the oracle's own construction
-	q = one.rotations[:1].double().cpu().numpy()
+	q = one.rotations.detach()[:1].double().cpu().numpy()
 	if D == 3:
 		q = q / np.sqrt((q ** 2).sum())
 		r, a, b, c = q[0]
