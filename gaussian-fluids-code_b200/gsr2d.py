@@ -98,10 +98,18 @@ class GaussianSplatting:
 		g = torch.exp(-.5 * (d * w).sum(-1))
 		return self.values[None] * g[..., None], w
 
+	def forward_single(self, x):
+		"""u at ONE point x (2,) -> (dim,)  (2D/GSR.py:110-113)"""
+		return self._dense_terms(x[None])[0].sum(dim=1)[0]
+
 	def __call__(self, x):
 		if x.dim() == 1:
-			return self._dense_terms(x[None])[0].sum(dim=1)[0]
+			return self.forward_single(x)
 		return self._dense_terms(x)[0].sum(dim=1)
+
+	def gradient_single(self, x, need_val=False):
+		"""grad u at ONE point x (2,) -> (dim, 2) [, u]  (2D/GSR.py:123-132)"""
+		return GaussianSplatting.gradient(self, x, need_val)
 
 	def gradient(self, x, need_val=False):
 		single = x.dim() == 1
@@ -211,6 +219,17 @@ class GaussianSplattingFast(GaussianSplatting):
 
 	def __call__(self, x):
 		return self.get_losses(x)
+
+	def get_coverage(self, x):
+		"""sum_i (g_i(x) - tau)_+ at every sample: how much of the representation covers x (2D/GSR.py:594-618).  The forward kernel
+		on records packed with v = (1, 1): both components of its output are the coverage"""
+		e = self._engine
+		ones = torch.ones((self.N, 2), device=device)
+		e.ensure_packed([self.positions.detach(), self.scalings.detach(), self.rotations.detach(), ones])
+		out = torch.zeros((x.shape[0], 2), device=device)
+		e.forward(x.detach().contiguous(), out, None, accumulate=False, perm=e.bin_samples(x.detach().contiguous(), need_cells=False))
+		e._packed_key = None	# the records hold the unit values: re-pack before the next evaluation of the field itself
+		return out[:, 0].contiguous()
 
 	def get_grad_losses(self, x, ref_grad=None, weight_grad=0., ref_vor=None, weight_vor=0., weight_div=0.,
 						vor_positions_grad=None, vor_scalings_grad=None, vor_rotations_grad=None, vor_values_grad=None,

@@ -149,3 +149,29 @@ def test_against_oracle_seeded(nx, ny, bounds, Q):
 		rk_clean &= orc.classify_pairs(pts)[1] == 0
 	for a, b, nm in zip(res, ores, ('pos', 'deformation', 'val', 'grad')):
 		assert rel_err(a.cpu().numpy()[rk_clean], b[rk_clean]) < TOL, nm
+
+
+def test_coverage_and_single_point_calls():
+	"""get_coverage (2D/GSR.py:594-618) = sum_i (g_i - tau)_+ = the field with unit values (oracle forward with v = 1), and the field
+	itself is intact afterwards; forward_single / gradient_single of the dense class (2D/GSR.py:110-132) = row 0 of the batched calls"""
+	from oracle.oracle import OracleGSR, extended_bounds
+	from gaussian_fluids_code_b200 import gsr2d
+	tau, bounds = 1e-3, (0., 10., 0., 10.)
+	P, S, R, V, mgs, gen = synthetic2d(24, 24, bounds)
+	o = make_fast2d(bounds, P, S, R, V, tau, mgs)
+	X = torch.rand((1500, 2), generator=gen) * 10.
+	x = X.cuda()
+	before = o(x).clone()
+	cov = o.get_coverage(x)
+	ones = OracleGSR(2, extended_bounds(2, bounds, mgs), P, S, R, np.ones_like(V), tau, mgs, precision='f64', nthreads=4)
+	clean = ones.classify_pairs(X.numpy())[1] == 0
+	want = ones.forward(X.numpy())[0][:, 0]
+	assert cov.shape == (1500,) and rel_err(cov.cpu().numpy()[clean], want[clean]) < TOL
+	assert torch.equal(o(x), before)
+	dense = gsr2d.GaussianSplatting(P[:50], 2)
+	with torch.no_grad():
+		dense.scalings.copy_(T(S[:50])); dense.rotations.copy_(T(R[:50])); dense.values.copy_(T(V[:50]))
+	g, v = dense.gradient(x[:4], need_val=True)
+	g0, v0 = dense.gradient_single(x[0], need_val=True)
+	assert torch.allclose(g0, g[0], rtol=1e-5, atol=1e-7) and torch.allclose(v0, v[0], rtol=1e-5, atol=1e-7) and g0.shape == (2, 2)
+	assert torch.allclose(dense.forward_single(x[0]), v[0], rtol=1e-5, atol=1e-7)
