@@ -423,6 +423,37 @@ def hbm_kernels(peaks, n=100):
 	return out
 
 
+def host_overheads(ts):
+	"""what the Python / ctypes layer above the C ABI costs on the host, next to the device time of the same call: an empty C-ABI call,
+	and one public-API evaluation `field.gradient(x, need_val=True)` at Q = N (bin + forward: 2-3 C-ABI calls, a few torch allocations)"""
+	import time
+	import torch
+	from gaussian_fluids_code_b200 import _lib
+	lib = _lib.lib()
+	n = 200000
+	t0 = time.perf_counter()
+	for _ in range(n):
+		lib.gsr_launch_count()
+	call_ns = (time.perf_counter() - t0) / n * 1e9
+	gv = ts.cur
+	x = torch.rand((gv.N, 3), device=gv.positions.device)
+	for _ in range(5):
+		gv.gradient(x, need_val=True)
+	torch.cuda.synchronize()
+	reps = 200
+	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	t0 = time.perf_counter()
+	e0.record()
+	for _ in range(reps):
+		gv.gradient(x, need_val=True)
+	e1.record()
+	host_us = (time.perf_counter() - t0) / reps * 1e6	# time to ENQUEUE (no synchronisation inside the loop)
+	torch.cuda.synchronize()
+	dev_us = e0.elapsed_time(e1) / reps * 1e3
+	return {'ctypes_empty_call_ns': call_ns, 'api_gradient_host_us_per_call': host_us, 'api_gradient_device_us_per_call': dev_us, 'Q': int(gv.N),
+			'note': 'eager public-API call: the host enqueue time bounds the eager path at small N; the captured project() pipeline pays it once, at capture'}
+
+
 def timed_steps(ts, args, barrier, dev, world, dist, host_params=None, host_out=None, host_fields=None):
 	"""(ms for args.steps steps, max over ranks); with host buffers the copies are inside the timed region (the e2e number)"""
 	import torch
@@ -605,6 +636,7 @@ def run_ours(args):
 	if not args.no_kernel_table:
 		roofline['kernels'] = kernel_table(ts, args, mpeaks, ms / args.steps)
 		roofline['hbm_kernels'] = hbm_kernels(mpeaks)
+		roofline['api_overhead'] = host_overheads(ts)
 
 	out = {
 		'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': W,

@@ -234,6 +234,7 @@ def run_2d(args):
 	params0 = [p.detach().clone() for p in cur._params()]
 	N = cur.N
 	gen_fn = lambda n_, gs, restrict=None: scene.data_generator(gs)
+	gen_fn.graph_safe = True	# a pure function of torch's CUDA random stream: project() may replay its iterations from a CUDA graph
 	test_fn = lambda gs: scene.test_generator()
 	b1, b2 = scene.boundary_samplers
 	iters = args.iters
@@ -276,7 +277,8 @@ def run_2d(args):
 		step()
 	sampler = ClockSampler(local)
 	sampler.start()
-	l0 = lib.gsr_launch_count()
+	from gaussian_fluids_code_b200 import graphloop
+	l0 = lib.gsr_launch_count() + graphloop.GRAPH_LAUNCHES
 	barrier()
 	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 	e0.record()
@@ -286,7 +288,7 @@ def run_2d(args):
 	e1.record()
 	barrier()
 	ms = e0.elapsed_time(e1)
-	nl = lib.gsr_launch_count() - l0
+	nl = lib.gsr_launch_count() + graphloop.GRAPH_LAUNCHES - l0	# eager launches + those replayed from the captured iteration graphs
 	sampler.stop_flag = True
 	sampler.join()
 	host_params = [p.cpu().pin_memory() for p in params0]
@@ -330,7 +332,7 @@ def run_2d(args):
 		'roofline': {'bound': 'fp32', 'kernel': 'rk4_2d_kernel<2> on the visualisation grid (RK4 pull-back, 5 evaluations)', 'achieved': flop / (kms * 1e-3) / 1e12, 'peak': fma, 'unit': 'TFLOP/s',
 					 'frac': flop / (kms * 1e-3) / 1e12 / fma, 'traffic': None, 'avg_launch_ms': kms, 'algorithmic_flop_per_launch': flop,
 					 'step_frac': (16 * C_step + 13 * P_step) / (ms / args.steps * 1e-3) / (fma * 1e12),
-					 'note': 'the 2D step is launch / latency bound at these sizes (a few thousand samples per kernel): the eager fused path, ~25 launches per iteration'},
+					 'note': 'the 2D step is latency bound at these sizes (a few thousand samples per kernel): ~25 short kernels per iteration, replayed 10 iterations per CUDA graph (graphloop.py)'},
 		'measured_peaks': {'hbm_gbs': hbm, 'fp32_tflops_live': fma},
 	}
 	if not args.no_cpu_baseline:

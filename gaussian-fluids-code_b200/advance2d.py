@@ -18,6 +18,7 @@ import torch.nn.functional as F
 
 from . import gsr2d
 from .engine import FusedStepper
+from .graphloop import GraphedLoop
 
 
 def _dev():
@@ -271,13 +272,16 @@ def _project_unfused(gv, reference_field, data_generator, test_data_generator, b
 
 
 def project(gaussian_velocity, reference_field, data_generator, test_data_generator, boundary_generator_1=None, boundary_generator_2=None,
-			boundary_lambda=0., batch_size=512, max_epoch=3000, patience=500, verbose=1, fused=True, check_iter=100, weights=None, lrs=None):
+			boundary_lambda=0., batch_size=512, max_epoch=3000, patience=500, verbose=1, fused=True, check_iter=100, weights=None, lrs=None, use_graph=None):
 	"""
 	One time step's projection by first-order optimisation (2D/advance.py:187-302): match the advected vorticity, drive
 	the divergence to zero, keep the Gaussians well shaped and close to their advected positions.  Early stop: every 100
 	iterations, vorticity must improve by 0.1 % or divergence by 1 %, `patience` iterations without either ends the phase.
 	Returns the number of iterations run.  `weights` / `lrs` override PROJECT_WEIGHTS / PROJECT_LRS: the reference keeps a second
 	copy of this function with other constants for the Karman initial state (2D/initialize.py:44-160, INIT_PROJECT_* below).
+	use_graph: replay the iterations as a CUDA graph (graphloop.py).  That is only valid when the generators are pure device
+	functions of torch's CUDA random stream — a generator that walks a Python list would be replayed with its first batches — so
+	the default (None) turns it on only when every generator carries `graph_safe = True` (Scene2D's samplers do).
 	"""
 	gv = gaussian_velocity
 	lr = dict(PROJECT_LRS, **(lrs or {}))
@@ -289,32 +293,45 @@ def project(gaussian_velocity, reference_field, data_generator, test_data_genera
 		return _project_unfused(gv, reference_field, data_generator, test_data_generator, boundary_generator_1, boundary_generator_2, boundary_lambda,
 								batch_size, max_epoch, patience, verbose, check_iter, weights)
 	fp = FusedProjector2D(gv, reference_field, boundary_lambda, patience=50, weights=weights, lrs=lrs)
+	use_b1 = boundary_lambda > 0. and boundary_generator_1
+	use_b2 = boundary_lambda > 0. and boundary_generator_2
+
+	def iteration():	# sync-free: draws come from torch's CUDA generator, every changing scalar lives in the stepper's state
+		data = data_generator(batch_size, gv)
+		b1 = boundary_generator_1(batch_size) if use_b1 else None
+		b2 = boundary_generator_2(batch_size) if use_b2 else None
+		fp.iterate(data, b1, b2)
+	if use_graph is None:
+		use_graph = all(getattr(g, 'graph_safe', False) for g in (data_generator, boundary_generator_1 if use_b1 else data_generator, boundary_generator_2 if use_b2 else data_generator))
+	loop = GraphedLoop(iteration, unit=next(u for u in (10, 5, 2, 1) if check_iter % u == 0), enabled=use_graph)
 	best, stale = [np.inf, np.inf], [0, 0]
 	epochs = max_epoch
 	st_time = time.time()
-	for epoch in range(max_epoch):
-		data = data_generator(batch_size, gv)
-		b1 = boundary_generator_1(batch_size) if (boundary_lambda > 0. and boundary_generator_1) else None
-		b2 = boundary_generator_2(batch_size) if (boundary_lambda > 0. and boundary_generator_2) else None
-		fp.iterate(data, b1, b2)
-		if epoch % check_iter == check_iter - 1:
-			lv, ld = fp.evaluate(test_data_generator(gv)).tolist()	# the only host synchronisation: once per 100 iterations
-			for k, (v, thr) in enumerate(((lv, 1e-3), (ld, 1e-2))):
-				if v < best[k] * (1. - thr):
-					best[k], stale[k] = v, 0
-				else:
-					stale[k] += check_iter
-			if verbose:
-				print(f'[projection] loss_vor: {lv}, loss_div: {ld}, time: {time.time() - st_time}')
-				st_time = time.time()
-			if stale[0] >= patience and stale[1] >= patience:
-				epochs = epoch + 1
-				break
+	done = 0
+	while done < max_epoch:
+		k = min(check_iter, max_epoch - done)
+		loop.run(k)
+		done += k
+		if k < check_iter:
+			break
+		lv, ld = fp.evaluate(test_data_generator(gv)).tolist()	# the only host synchronisation: once per check_iter iterations
+		for j, (v, thr) in enumerate(((lv, 1e-3), (ld, 1e-2))):
+			if v < best[j] * (1. - thr):
+				best[j], stale[j] = v, 0
+			else:
+				stale[j] += check_iter
+		if verbose:
+			print(f'[projection] loss_vor: {lv}, loss_div: {ld}, time: {time.time() - st_time}')
+			st_time = time.time()
+		if stale[0] >= patience and stale[1] >= patience:
+			epochs = done
+			break
+	loop.release()
 	fp.finish()
 	return epochs
 
 
-def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gradient, data_generator, batch_size=512, max_epoch=3000, verbose=1, fused=True):
+def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gradient, data_generator, batch_size=512, max_epoch=3000, verbose=1, fused=True, use_graph=None):
 	"""
 	Initial fit of the representation to an analytic field: value L1 + gradient L1 + anisotropy + volume regularisers
 	(2D/initialize.py:10-41).  fused=True runs the iteration through gsr_step_rebuild (no PCGrad: a single gradient set).
@@ -339,7 +356,8 @@ def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gra
 	e.build(gv.positions.detach(), params=[p.detach() for p in gv._params()])
 	e._packed_key = None
 	st_time = time.time()
-	for epoch in range(max_epoch):
+
+	def iteration():
 		data = data_generator(batch_size).detach()
 		Q = data.shape[0]
 		ref_val, ref_grad = reference_field(data).contiguous(), reference_gradient(data).contiguous()
@@ -350,10 +368,19 @@ def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gra
 		acc, mask = e.backward_gather(data, bins.perm, bins.scs, val, grad, (1., 0., 1., 0., 0., 0.), {'ref_val': ref_val, 'ref_grad': ref_grad}, None, want_losses=True)
 		lp, nblk = e.last_loss_partials
 		stepper.step([p.detach() for p in gv._params()], acc, mask, loss_srcs=[(lp, nblk, [0., 0., 0., 0., 1. / Q, 1. / Q, 0., 0.])], rebuild=True)
-		if verbose and epoch % 100 == 99:
+	if use_graph is None:
+		use_graph = all(getattr(g, 'graph_safe', False) for g in (data_generator, reference_field, reference_gradient))
+	loop = GraphedLoop(iteration, unit=10, enabled=use_graph)
+	done = 0
+	while done < max_epoch:
+		k = min(100, max_epoch - done)
+		loop.run(k)
+		done += k
+		if verbose and k == 100:
 			sc = stepper.scalars()
 			print(f'loss_tot: {sc[9]}, loss_aniso: {sc[10]}, loss_vol: {sc[11]}, time: {time.time() - st_time}')
 			st_time = time.time()
+	loop.release()
 	gv.grid_scale = stepper.detach()
 	e._packed_key = None
 	for p in gv._params():
@@ -363,7 +390,7 @@ def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gra
 
 
 def init_karman_velocity(gaussian_velocity, scene, reference_field, reference_gradient, data_generator, batch_size=512, max_epoch=3000, verbose=1, fused=True,
-						 project_epochs=10000):
+						 project_epochs=10000, use_graph=None):
 	"""
 	The Karman initial state (2D/initialize.py:162-185): fit the uniform inflow with ten times smaller scaling / rotation rates than
 	the other scenes, then project the fit onto the divergence-free fields that respect the obstacle and the channel walls — a
@@ -373,7 +400,7 @@ def init_karman_velocity(gaussian_velocity, scene, reference_field, reference_gr
 	"""
 	gv = gaussian_velocity
 	gv.set_lr(positions_lr=1.6e-4 * 10., scalings_lr=5e-3, rotations_lr=5e-3 * KARMAN_LR_RATIO, values_lr=5e-4 * 10.)
-	fit_velocity_with_gradient(gv, reference_field, reference_gradient, data_generator, batch_size, max_epoch, verbose, fused=fused)
+	fit_velocity_with_gradient(gv, reference_field, reference_gradient, data_generator, batch_size, max_epoch, verbose, fused=fused, use_graph=use_graph)
 	x_min, x_max, y_min, y_max = scene.scaled(scene.initialize_domain)
 	x_N, y_N = scene.particle_count
 	tmp = gsr2d.GaussianSplattingFast(x_min, x_max, y_min, y_max, gsr2d.get_grid_points(x_min, x_max, y_min, y_max, x_N, y_N).cpu().numpy(), dim=2)
@@ -385,11 +412,13 @@ def init_karman_velocity(gaussian_velocity, scene, reference_field, reference_gr
 	tmp.zero_grad()
 	b1, b2 = scene.boundary_samplers
 	ref = AdvectedCovectorField(tmp, tmp, 0., domain=scene.scaled(scene.advance_domain))
-	return project(gv, ref, lambda n, gs, restrict=None: scene.data_generator(gs), lambda gs: scene.test_generator(), boundary_generator_1=b1, boundary_generator_2=b2,
-				   boundary_lambda=10., patience=project_epochs, max_epoch=project_epochs, verbose=verbose, fused=fused, weights=INIT_PROJECT_WEIGHTS, lrs=INIT_PROJECT_LRS)
+	gen = lambda n, gs, restrict=None: scene.data_generator(gs)
+	gen.graph_safe = True
+	return project(gv, ref, gen, lambda gs: scene.test_generator(), boundary_generator_1=b1, boundary_generator_2=b2,
+				   boundary_lambda=10., patience=project_epochs, max_epoch=project_epochs, verbose=verbose, fused=fused, weights=INIT_PROJECT_WEIGHTS, lrs=INIT_PROJECT_LRS, use_graph=use_graph)
 
 
-def simulation_initialize(scene, max_epoch=10000, verbose=1, fused=True, project_epochs=10000):
+def simulation_initialize(scene, max_epoch=10000, verbose=1, fused=True, project_epochs=10000, use_graph=None):
 	"""SimulationInitialize of 2D/initialize.py:187-238 without the plots: lattice of Gaussians -> fit (karman: -> projection onto
 	the boundary conditions) -> the frame-0 field"""
 	x_min, x_max, y_min, y_max = scene.scaled(scene.initialize_domain)
@@ -397,17 +426,19 @@ def simulation_initialize(scene, max_epoch=10000, verbose=1, fused=True, project
 	pts = gsr2d.get_grid_points(x_min, x_max, y_min, y_max, x_N, y_N).cpu().numpy()
 	gv = gsr2d.GaussianSplattingFast(x_min, x_max, y_min, y_max, pts, dim=2)
 	gen = lambda n: scene.data_generator(gv, domain=scene.initialize_domain)
+	gen.graph_safe = True
 	if scene.name == 'karman':
-		init_karman_velocity(gv, scene, scene.target_velocity, scene.target_gradient, gen, max_epoch=max_epoch, verbose=verbose, fused=fused, project_epochs=project_epochs)
+		init_karman_velocity(gv, scene, scene.target_velocity, scene.target_gradient, gen, max_epoch=max_epoch, verbose=verbose, fused=fused, project_epochs=project_epochs, use_graph=use_graph)
 		return gv
 	gv.set_lr(positions_lr=1.6e-3, scalings_lr=5e-2, rotations_lr=5e-2, values_lr=5e-3)
-	fit_velocity_with_gradient(gv, scene.target_velocity, scene.target_gradient, gen, max_epoch=max_epoch, verbose=verbose, fused=fused)
+	fit_velocity_with_gradient(gv, scene.target_velocity, scene.target_gradient, gen, max_epoch=max_epoch, verbose=verbose, fused=fused, use_graph=use_graph)
 	return gv
 
 
 def advance(scene, gaussian_velocity, new_gaussian_velocity, dt, max_epoch=20000, boundary_lambda=1., verbose=1, fused=True):
 	"""one frame of the `while t < last_time` loop of 2D/advance.py:354-365; returns (current, spare) after the swap"""
 	gen = lambda n, gs, restrict=None: scene.data_generator(gs)
+	gen.graph_safe = True
 	test = lambda gs: scene.test_generator()
 	clone_velocity_field(new_gaussian_velocity, gaussian_velocity, gen, test, max_epoch=max_epoch, verbose=verbose)
 	advect_covector_field(new_gaussian_velocity, gaussian_velocity, dt, extra_advector=scene.extra_advector)	# karman: the inlet moves with the flow

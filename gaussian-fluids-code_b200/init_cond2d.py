@@ -39,6 +39,23 @@ def _dev():
 	return gsr2d.device
 
 
+_CONSTS = {}
+
+
+def _const(values, device):
+	"""small constant tensors, uploaded once: a host->device copy per call is a synchronising pageable copy, and is not allowed
+	while the optimisation loops are being captured into a CUDA graph (graphloop.py)"""
+	import numpy as _np
+	a = _np.asarray(values, dtype=_np.float32)
+	key = (a.tobytes(), a.shape, str(device))
+	t = _CONSTS.get(key)
+	if t is None:
+		if len(_CONSTS) > 4096:
+			_CONSTS.clear()
+		t = _CONSTS[key] = torch.tensor(a, device=device)
+	return t
+
+
 def vortex_particle(x, x0, radius, magnitude, grad):
 	"""regularised point vortex and its Jacobian (2D/init_cond.py:138-156)"""
 	eps = 1e-6
@@ -85,7 +102,7 @@ def leapfrog(x, grad):
 	U, a = info['U'], info['a']
 	res = 0.
 	for k, sign in ((1, 1.), (2, 1.), (3, -1.), (4, -1.)):
-		res = res + vortex_particle(x, torch.tensor(info[f'vortex_pos{k}'], device=x.device), a, sign * U, grad)
+		res = res + vortex_particle(x, _const(info[f'vortex_pos{k}'], x.device), a, sign * U, grad)
 	return res
 
 
@@ -94,8 +111,8 @@ def vortices_pass_of(name):
 	info = other_info[name]
 
 	def field(x, grad):
-		return vortex_particle(x, torch.tensor(info['vortex_pos1'], device=x.device), info['a'], info['U'], grad) \
-			+ vortex_particle(x, torch.tensor(info['vortex_pos2'], device=x.device), info['a'], -info['U'], grad)
+		return vortex_particle(x, _const(info['vortex_pos1'], x.device), info['a'], info['U'], grad) \
+			+ vortex_particle(x, _const(info['vortex_pos2'], x.device), info['a'], -info['U'], grad)
 	return field
 
 
@@ -175,6 +192,8 @@ class Scene2D:
 	def target_gradient(self, x):
 		return self._field(x / self.scaling_factor, True)
 
+	target_velocity.graph_safe = target_gradient.graph_safe = True
+
 	def scaled(self, dom):
 		return tuple(v * self.scaling_factor for v in dom)
 
@@ -193,8 +212,8 @@ class Scene2D:
 		2D/initialize.py:216-217, draws them on the initialize domain: pass it as `domain`)"""
 		x_min, x_max, y_min, y_max = domain if domain is not None else self.advance_domain
 		dev = _dev()
-		return (torch.rand_like(gaussian_splatting.positions.detach(), device=dev) * torch.tensor([x_max - x_min, y_max - y_min], device=dev)
-				+ torch.tensor([x_min, y_min], device=dev)) * self.scaling_factor
+		return (torch.rand_like(gaussian_splatting.positions.detach(), device=dev) * _const([x_max - x_min, y_max - y_min], dev)
+				+ _const([x_min, y_min], dev)) * self.scaling_factor
 
 	def test_generator(self):
 		x_min, x_max, y_min, y_max = self.advance_domain
@@ -211,7 +230,7 @@ class Scene2D:
 		px = torch.stack([x_min + t, torch.full_like(t, x_max), x_max - t + xs + ys, torch.full_like(t, x_min)], dim=1)
 		py = torch.stack([torch.full_like(t, y_min), y_min + t - xs, torch.full_like(t, y_max), y_max - t + 2. * xs + ys], dim=1)
 		data = torch.stack([px.gather(1, edge[:, None])[:, 0], py.gather(1, edge[:, None])[:, 0]], dim=1)
-		normals = torch.tensor([[0., -1.], [1., 0.], [0., 1.], [-1., 0.]], device=dev)[edge]
+		normals = _const([[0., -1.], [1., 0.], [0., 1.], [-1., 0.]], dev)[edge]
 		return data.contiguous(), normals.contiguous(), torch.zeros(n, device=dev)
 
 	@staticmethod
@@ -220,7 +239,7 @@ class Scene2D:
 		dev = _dev()
 		theta = torch.rand(n, device=dev) * 2. * np.pi
 		nrm = torch.stack([torch.cos(theta), torch.sin(theta)], dim=1)
-		return r * nrm + torch.tensor([x, y], device=dev), nrm
+		return r * nrm + _const([x, y], dev), nrm
 
 	def _discs(self):
 		return [self.info[k] for k in ('obstacle_pos1', 'obstacle_pos2') if k in self.info] or [self.info['obstacle_pos']]
@@ -246,8 +265,8 @@ class Scene2D:
 		col = lambda v: torch.full((n,), v, device=dev)
 		data = torch.cat([torch.stack([t, col(y_min)], 1), torch.stack([t, col(y_max)], 1), torch.stack([col(x_min), t2], 1),
 						  torch.stack([col(x_max), t2], 1), torch.stack([col(x_min_v), t2], 1)], dim=0)
-		nrm = torch.tensor([[0., 1.], [0., -1.], [1., 0.], [-1., 0.], [1., 0.]], device=dev).repeat_interleave(n, dim=0)
-		val = torch.tensor([0., 0., vm, -vm, vm], device=dev).repeat_interleave(n)
+		nrm = _const([[0., 1.], [0., -1.], [1., 0.], [-1., 0.], [1., 0.]], dev).repeat_interleave(n, dim=0)
+		val = _const([0., 0., vm, -vm, vm], dev).repeat_interleave(n)
 		return data, nrm, val
 
 	def _raw_samplers(self):
@@ -273,6 +292,9 @@ class Scene2D:
 			return None
 		data, value = raw(n)
 		return (data * self.scaling_factor).contiguous(), (value * self.scaling_factor).contiguous()
+
+	# pure device functions of torch's CUDA random stream: the optimisation loops may replay them from a CUDA graph (advance2d.project)
+	boundary_sampler_1.graph_safe = boundary_sampler_2.graph_safe = True
 
 	@property
 	def boundary_samplers(self):
