@@ -281,13 +281,17 @@ def run_2d(args):
 	l0 = lib.gsr_launch_count() + graphloop.GRAPH_LAUNCHES
 	barrier()
 	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
 	e0.record()
-	for _ in range(args.steps):
+	marks[0].record()
+	for k in range(args.steps):
 		reset()
 		step()
+		marks[k + 1].record()
 	e1.record()
 	barrier()
 	ms = e0.elapsed_time(e1)
+	ms_each = [marks[k].elapsed_time(marks[k + 1]) for k in range(args.steps)]
 	nl = lib.gsr_launch_count() + graphloop.GRAPH_LAUNCHES - l0	# eager launches + those replayed from the captured iteration graphs
 	sampler.stop_flag = True
 	sampler.join()
@@ -325,7 +329,7 @@ def run_2d(args):
 		'config': {'workload': f'2D {args.scene} fixed-work timestep through advance2d (clone -> advect -> project), N={N} Gaussians ({scene.particle_count[0]}x{scene.particle_count[1]}), '
 							   f'Q=N samples/iter, {iters} project iters, dt={dt}, test grid {scene.visualize_res[0]}x{scene.visualize_res[1]}',
 				   'work_census': 'candidate visits on representative batches x the step\'s evaluation counts'},
-		'timesteps_per_s': args.steps / (ms * 1e-3), 'project_iters_per_s': args.steps * iters / (ms * 1e-3), 'pair_evals_per_step': C_step, 'accepted_pairs_per_step': P_step,
+		'ms_each_step': ms_each, 'timesteps_per_s': args.steps / (ms * 1e-3), 'project_iters_per_s': args.steps * iters / (ms * 1e-3), 'pair_evals_per_step': C_step, 'accepted_pairs_per_step': P_step,
 		'e2e': {'value': C_step * args.steps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': sum(p.numel() * 4 for p in host_params),
 				'd2h_bytes_per_step': sum(p.numel() * 4 for p in host_out), 'ms_per_step': ms_e2e / args.steps},
 		'gpu_launches': int(nl), 'clocks': sampler.summary(),

@@ -654,6 +654,250 @@ __global__ void init_state_kernel(float *st, size_t n_moments, gsr_step_cfg cfg)
 	}
 }
 
+// ---- the same step with FOUR lanes per Gaussian (N <= 1024: the reference's 3D scenes have 1000 Gaussians) --------------------
+// ncu of step_cluster_kernel at N = 1000 (profiles/README.md, round 2): 14.8 us for 2100 dependent instructions per thread at one
+// warp per scheduler — the chain rule of up to five accumulator sets, then 13 IEEE sqrt + divide of Adam, one Gaussian per thread.
+// Here a Gaussian is a group of four consecutive lanes: lane s of the group runs the chain rule of ONE set (vorticity, divergence,
+// direct, boundary) and leaves its 13 (7) parameter gradients in shared memory; then lane s owns parameters s, s + 4, s + 8 (, 12)
+// for the PCGrad dots, the regulariser gradients and Adam.  Same formulas; the float block sums are grouped differently.
+constexpr int SC4_G = 4;
+constexpr int SC4_MAX_THREADS = 512;
+constexpr int SC4_MAX_N = SC_CTAS * SC4_MAX_THREADS / SC4_G;
+int g_step_lanes4 = 1;	// GSR_TUNE_STEP_LANES4
+
+template <int D>
+__global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC4_MAX_THREADS, 1)
+step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__restrict__ scal, float *__restrict__ rot, float *__restrict__ vals,
+		     const float *__restrict__ acc, int sets_mask, const float *__restrict__ ex0, const float *__restrict__ ex1,
+		     const float *__restrict__ pos_org, LossSrcs ls, float *st)
+{
+	namespace cg = cooperative_groups;
+	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR, P = Dim<D>::P, G = SC4_G, KPL = (P + G - 1) / G;
+	cg::cluster_group cluster = cg::this_cluster();
+	__shared__ float cst[GSR_STATE_SCALARS];
+	__shared__ float wpart[SC4_MAX_THREADS / 32][S_COUNT];
+	__shared__ float part[S_COUNT];
+	__shared__ double Tsm[S_COUNT + 8];
+	__shared__ double bc_sm[2];
+	__shared__ int decay_sm;
+	__shared__ float wmin[SC4_MAX_THREADS / 32];
+	__shared__ float bmin;
+	__shared__ float Tg[SC4_MAX_THREADS / G][G][P + 1];	// parameter-space gradients of the four roles of every Gaussian of this CTA
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+	const int rank = (int)cluster.block_rank();
+	const int gl = tid / G, sub = tid % G;
+	const int i = rank * (blockDim.x / G) + gl;
+	const bool on = i < N;
+	for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x) cst[k] = st[k];
+	// ---- every load of this lane, issued together ------------------------------------------------------------------------
+	float sc[D], r[NR], a[AF], a2nd[AF];
+	// role of this lane: 0 vorticity set, 1 divergence set, 2 direct set, 3 the extra direct sets (boundary passes)
+	const float *src = nullptr, *src2 = nullptr;
+	if (on) {
+		if (sub == 0 && (sets_mask & 2)) src = acc + ((size_t)1 * N + i) * AF;
+		if (sub == 1 && (sets_mask & 4)) src = acc + ((size_t)2 * N + i) * AF;
+		if (sub == 2 && (sets_mask & 1)) src = acc + (size_t)i * AF;
+		if (sub == 3) {
+			src = ex0 ? ex0 + (size_t)i * AF : (ex1 ? ex1 + (size_t)i * AF : nullptr);
+			src2 = (ex0 && ex1) ? ex1 + (size_t)i * AF : nullptr;
+		}
+#pragma unroll
+		for (int k = 0; k < D; k++) sc[k] = scal[(size_t)D * i + k];
+#pragma unroll
+		for (int k = 0; k < NR; k++) r[k] = rot[(size_t)NR * i + k];
+	}
+#pragma unroll
+	for (int k = 0; k < AF; k++) { a[k] = src ? src[k] : 0.f; a2nd[k] = src2 ? src2[k] : 0.f; }
+	// the parameters this lane owns: k = sub + 4 j
+	float prm[KPL], mo[KPL], vo[KPL], po[KPL];
+	float *pp[KPL];
+	float *m = st + GSR_STATE_SCALARS + (size_t)i * P, *vv = st + GSR_STATE_SCALARS + (size_t)N * P + (size_t)i * P;
+#pragma unroll
+	for (int j = 0; j < KPL; j++) {
+		const int k = sub + G * j;
+		pp[j] = nullptr;
+		prm[j] = mo[j] = vo[j] = po[j] = 0.f;
+		if (on && k < P) {
+			pp[j] = k < D ? pos + (size_t)D * i + k : (k < 2 * D ? scal + (size_t)D * i + (k - D) : (k < 2 * D + NR ? rot + (size_t)NR * i + (k - 2 * D) : vals + (size_t)D * i + (k - 2 * D - NR)));
+			prm[j] = *pp[j];
+			mo[j] = m[k];
+			vo[j] = vv[k];
+			if (k < D && pos_org) po[j] = pos_org[(size_t)D * i + k];
+		}
+	}
+	if (w == nw - 1 && lane < 8) {	// weighted sums of the sample-loss partials (blocks in order, double); loads four deep
+		const int k = lane;
+		double s = 0.;
+		for (int q = 0; q < ls.n; q++) {
+			double t = 0.;
+			const float *pt = ls.partials[q] + k;
+			const int nb = ls.nblocks[q];
+			int b = 0;
+			for (; b + 4 <= nb; b += 4) {
+				const float v0 = pt[(size_t)b * 8], v1 = pt[(size_t)(b + 1) * 8], v2 = pt[(size_t)(b + 2) * 8], v3 = pt[(size_t)(b + 3) * 8];
+				t += (double)v0; t += (double)v1; t += (double)v2; t += (double)v3;
+			}
+			for (; b < nb; b++) t += (double)pt[(size_t)b * 8];
+			s += (double)ls.w[q][k] * t;
+		}
+		Tsm[S_COUNT + k] = s;
+	}
+	// ---- chain rule of this lane's set ---------------------------------------------------------------------------------------
+	{
+		float g[P];
+#pragma unroll
+		for (int k = 0; k < P; k++) g[k] = 0.f;
+		auto to_param = [&](const float *aa, float *gg) {
+			float gp[D], gs[D], gr[NR], gv[D];
+			param_grad<D>(aa, sc, r, gp, gs, gr, gv);
+#pragma unroll
+			for (int k = 0; k < D; k++) { gg[k] = gp[k]; gg[D + k] = gs[k]; gg[2 * D + NR + k] = gv[k]; }
+#pragma unroll
+			for (int k = 0; k < NR; k++) gg[2 * D + k] = gr[k];
+		};
+		if (src) to_param(a, g);
+		if (src2) {
+			float t[P];
+			to_param(a2nd, t);
+#pragma unroll
+			for (int k = 0; k < P; k++) g[k] += t[k];
+		}
+#pragma unroll
+		for (int k = 0; k < P; k++) Tg[gl][sub][k] = g[k];
+	}
+	__syncwarp();
+	// ---- this lane's parameters: PCGrad dots, regulariser moments ----------------------------------------------------------------
+	float S[S_COUNT];
+#pragma unroll
+	for (int k = 0; k < S_COUNT; k++) S[k] = 0.f;
+	float g1[KPL], g2[KPL], gd[KPL];
+	float ssum = 0.f;
+	int kmin = 0, kmax = 0;
+#pragma unroll
+	for (int k = 0; k < D; k++) {
+		if (on) {
+			ssum += sc[k];
+			if (sc[k] < sc[kmin]) kmin = k;	// first index on ties, like torch.min / torch.max
+			if (sc[k] > sc[kmax]) kmax = k;
+		}
+	}
+	float smin_k = 0.f, smax_k = 0.f;
+#pragma unroll
+	for (int k = 0; k < D; k++) { if (k == kmin) smin_k = on ? sc[k] : 0.f; if (k == kmax) smax_k = on ? sc[k] : 0.f; }
+	const float V = expf(-ssum), rho = expf(smax_k - smin_k);
+#pragma unroll
+	for (int j = 0; j < KPL; j++) {
+		const int k = sub + G * j;
+		g1[j] = g2[j] = gd[j] = 0.f;
+		if (on && k < P) {
+			const int grp = k < D ? 0 : (k < 2 * D ? 1 : (k < 2 * D + NR ? 2 : 3));
+			g1[j] = Tg[gl][0][k];
+			g2[j] = Tg[gl][1][k];
+			gd[j] = Tg[gl][2][k] + Tg[gl][3][k];
+			if ((sets_mask & 6) == 6) {
+				// one slot per group and lane: which slot is a run-time index, so add through a select over the four groups
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					S[S_DOT + q] += (q == grp) ? g1[j] * g2[j] : 0.f;
+					S[S_N1 + q] += (q == grp) ? g1[j] * g1[j] : 0.f;
+					S[S_N2 + q] += (q == grp) ? g2[j] * g2[j] : 0.f;
+				}
+			}
+			if (grp == 3) S[S_ABSV] += fabsf(prm[j]);
+			if (grp == 0 && pos_org) { const float dlt = prm[j] - po[j]; S[S_DPOS] += dlt * dlt; }
+		}
+	}
+	if (on && sub == 0) {
+		S[S_V] += V;
+		S[S_V2] += V * V;
+		S[S_ANISO] += (rho >= cfg.aniso_ratio ? rho : cfg.aniso_ratio) - cfg.aniso_ratio;
+	}
+#pragma unroll
+	for (int k = 0; k < S_COUNT; k++) {
+#pragma unroll
+		for (int o = 16; o; o >>= 1) S[k] += __shfl_xor_sync(0xffffffffu, S[k], o);
+	}
+	if (lane == 0) {
+#pragma unroll
+		for (int k = 0; k < S_COUNT; k++) wpart[w][k] = S[k];
+	}
+	__syncthreads();
+	if (tid < S_COUNT) {
+		float t = 0.f;
+		for (int ww = 0; ww < nw; ww++) t += wpart[ww][tid];
+		part[tid] = t;
+	}
+	cluster.sync();
+	if (tid < S_COUNT) {	// CTAs in order, double: the same T in every CTA
+		double t = 0.;
+#pragma unroll
+		for (int q = 0; q < SC_CTAS; q++) t += (double)*cluster.map_shared_rank(&part[tid], q);
+		Tsm[tid] = t;
+	}
+	__syncthreads();
+	if (nw >= 3) {
+		step_reduce_tail_split<D>(cfg, N, Tsm, cst, bc_sm, &decay_sm);
+	} else if (tid == 0) {
+		double T[S_COUNT + 8];
+#pragma unroll
+		for (int k = 0; k < S_COUNT + 8; k++) T[k] = Tsm[k];
+		step_reduce_tail<D>(cfg, N, T, cst);
+	}
+	__syncthreads();
+	// ---- projected gradient + regulariser gradients + Adam on this lane's parameters ----------------------------------------
+	float smin = __int_as_float(0x7f800000);
+	const float bc2 = cst[C_BC2];
+	const float rV = V / cst[C_MEANV];
+	const float cv = -cfg.w_vol * 2.f / (float)N * rV * (rV - cst[C_MEANR2]);
+	const float ca = (rho >= cfg.aniso_ratio && kmin != kmax) ? cfg.w_aniso * rho / (float)N : 0.f;
+#pragma unroll
+	for (int j = 0; j < KPL; j++) {
+		const int k = sub + G * j;
+		if (on && k < P) {
+			const int grp = k < D ? 0 : (k < 2 * D ? 1 : (k < 2 * D + NR ? 2 : 3));
+			float t = 0.f;
+			if (sets_mask & 2) t += cst[C_A1 + grp] * g1[j];
+			if (sets_mask & 4) t += cst[C_A2 + grp] * g2[j];
+			float g = t + gd[j];
+			if (grp == 1) {
+				const int ks = k - D;
+				if (ca != 0.f) g += (ks == kmax ? ca : 0.f) - (ks == kmin ? ca : 0.f);
+				g += cv;
+			}
+			if (grp == 3 && cfg.w_valreg != 0.f) g += cfg.w_valreg / (float)(N * D) * (float)((prm[j] > 0.f) - (prm[j] < 0.f));
+			if (grp == 0 && pos_org && cfg.w_dpos != 0.f) g += cfg.w_dpos * 2.f / (float)(N * D) * (prm[j] - po[j]);
+			const float mk = mo[j] + (g - mo[j]) * (1.f - cfg.beta1);
+			const float vk = vo[j] * cfg.beta2 + (1.f - cfg.beta2) * g * g;
+			const float pk = prm[j] - cst[C_STEP + grp] * (mk / (sqrtf(vk) * bc2 + cfg.eps));
+			m[k] = mk;
+			vv[k] = vk;
+			*pp[j] = pk;
+			if (grp == 1) smin = fminf(smin, pk);
+		}
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+	if (lane == 0) wmin[w] = smin;
+	__syncthreads();
+	if (tid == 0) {
+		float mn = wmin[0];
+		for (int ww = 1; ww < nw; ww++) mn = fminf(mn, wmin[ww]);
+		bmin = mn;
+	}
+	cluster.sync();
+	if (rank == 0) {
+		for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x)
+			if (k != GSR_ST_GRID_SCALE && k != GSR_ST_MIN_S) st[k] = cst[k];
+		if (tid == 0) {
+			float mn = fminf(bmin, cst[GSR_ST_MIN_S]);
+#pragma unroll
+			for (int q = 1; q < SC_CTAS; q++) mn = fminf(mn, *cluster.map_shared_rank(&bmin, q));
+			step_grid_scale(cfg, st, mn);
+		}
+	}
+	cluster.sync();	// no CTA may exit while another still reads its shared memory
+}
+
 __global__ void min_into_kernel(const float *__restrict__ a, size_t n, float *out)
 {
 	float m = __int_as_float(0x7f800000);
@@ -718,7 +962,12 @@ static int step_impl(const gsr_step_cfg *cfg, int64_t N, float *positions, float
 		for (int k = 0; k < 8; k++) ls.w[s][k] = (s < n_loss_src) ? loss_src[s].w[k] : 0.f;
 	}
 	const float *ex0 = extra_direct ? extra_direct[0] : nullptr, *ex1 = extra_direct ? extra_direct[1] : nullptr;
-	if (N <= g_step_small_n && N <= SC_MAX_N) {
+	if (N <= g_step_small_n && N <= SC4_MAX_N && g_step_lanes4) {
+		const int bt = ((((n + SC_CTAS - 1) / SC_CTAS) * SC4_G) + 31) & ~31;	// Gaussians per CTA x 4 lanes, whole warps
+		if (cfg->D == 3) step_cluster4_kernel<3><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state);
+		else step_cluster4_kernel<2><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state);
+		g_launches += 1;
+	} else if (N <= g_step_small_n && N <= SC_MAX_N) {
 		const int bt = (((n + SC_CTAS - 1) / SC_CTAS) + 31) & ~31;
 		if (cfg->D == 3) step_cluster_kernel<3><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state);
 		else step_cluster_kernel<2><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state);
