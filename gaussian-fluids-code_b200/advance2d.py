@@ -296,14 +296,17 @@ def project(gaussian_velocity, reference_field, data_generator, test_data_genera
 	use_b1 = boundary_lambda > 0. and boundary_generator_1
 	use_b2 = boundary_lambda > 0. and boundary_generator_2
 
-	def iteration():	# sync-free: draws come from torch's CUDA generator, every changing scalar lives in the stepper's state
+	def batches():	# sync-free: the draws come from torch's CUDA generator
 		data = data_generator(batch_size, gv)
 		b1 = boundary_generator_1(batch_size) if use_b1 else None
 		b2 = boundary_generator_2(batch_size) if use_b2 else None
-		fp.iterate(data, b1, b2)
+		return data, b1, b2
+
+	def iteration(inputs):	# sync-free: every scalar that changes between iterations lives in the stepper's device state
+		fp.iterate(*inputs)
 	if use_graph is None:
 		use_graph = all(getattr(g, 'graph_safe', False) for g in (data_generator, boundary_generator_1 if use_b1 else data_generator, boundary_generator_2 if use_b2 else data_generator))
-	loop = GraphedLoop(iteration, unit=next(u for u in (10, 5, 2, 1) if check_iter % u == 0), enabled=use_graph)
+	loop = GraphedLoop(iteration, unit=next(u for u in (10, 5, 2, 1) if check_iter % u == 0), enabled=use_graph, prepare=batches)
 	best, stale = [np.inf, np.inf], [0, 0]
 	epochs = max_epoch
 	st_time = time.time()
@@ -357,10 +360,13 @@ def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gra
 	e._packed_key = None
 	st_time = time.time()
 
-	def iteration():
+	def batches():	# the samples and the analytic targets at them: functions of the random stream only
 		data = data_generator(batch_size).detach()
+		return data, reference_field(data).contiguous(), reference_gradient(data).contiguous()
+
+	def iteration(inputs):
+		data, ref_val, ref_grad = inputs
 		Q = data.shape[0]
-		ref_val, ref_grad = reference_field(data).contiguous(), reference_gradient(data).contiguous()
 		bins = e.bin_samples(data, True)
 		val, grad = torch.empty((Q, 2), device=_dev()), torch.empty((Q, 2, 2), device=_dev())
 		e.forward(data, val, grad, accumulate=False, perm=bins)
@@ -370,7 +376,7 @@ def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gra
 		stepper.step([p.detach() for p in gv._params()], acc, mask, loss_srcs=[(lp, nblk, [0., 0., 0., 0., 1. / Q, 1. / Q, 0., 0.])], rebuild=True)
 	if use_graph is None:
 		use_graph = all(getattr(g, 'graph_safe', False) for g in (data_generator, reference_field, reference_gradient))
-	loop = GraphedLoop(iteration, unit=10, enabled=use_graph)
+	loop = GraphedLoop(iteration, unit=10, enabled=use_graph, prepare=batches)
 	done = 0
 	while done < max_epoch:
 		k = min(100, max_epoch - done)

@@ -17,13 +17,32 @@ from . import _lib
 TRACE = bool(os.environ.get('GSR_GRAPHLOOP_TRACE'))	# development: print where a loop's wall time goes (synchronises)
 
 GRAPH_LAUNCHES = 0	# kernels of this library launched from graph replays (the library's host-side launch counter does not see them)
-_FREE_POOLS = []	# memory pools of released loops: the next capture reuses one instead of growing a new pool with cudaMalloc
 _CAPTURE_STREAM = None
 
 
+_SIDE_STREAM = None
+
+
+def _side_stream():
+	global _SIDE_STREAM
+	if _SIDE_STREAM is None:
+		_SIDE_STREAM = torch.cuda.Stream()
+	return _SIDE_STREAM
+
+
 class GraphedLoop:
-	def __init__(self, body, unit=10, enabled=True):
-		self.body, self.unit, self.enabled = body, unit, enabled
+	"""
+	body()                      one iteration, or
+	body(prepare())             when the iteration's inputs (sample batches) depend on nothing but the random stream: inside a
+	                            captured unit the inputs of iteration j + 1 are then prepared on a second stream while iteration j
+	                            computes.  Program order — and with it the order of the random draws — is unchanged, so the results
+	                            are those of the plain loop.
+	"""
+
+	def __init__(self, body, unit=10, enabled=True, prepare=None):
+		self.unit, self.enabled, self.prepare = unit, enabled, prepare
+		self.body = body if prepare is None else (lambda: body(prepare()))
+		self._body_in = body
 		self.graph = None
 		self.per_unit = 0
 
@@ -65,19 +84,30 @@ class GraphedLoop:
 
 	def _capture(self):
 		"""torch.cuda.graph() without its synchronize + empty_cache prologue (an optimisation phase is captured once per frame: emptying
-		the allocator's cache every time turns the next allocations into cudaMalloc calls), into a pool recycled from released loops"""
+		the allocator's cache every time turns the next allocations into cudaMalloc calls)"""
 		global _CAPTURE_STREAM
 		if _CAPTURE_STREAM is None:
 			_CAPTURE_STREAM = torch.cuda.Stream()
-		self.pool = _FREE_POOLS.pop() if _FREE_POOLS else torch.cuda.graph_pool_handle()
 		self.graph = torch.cuda.CUDAGraph()
 		cur = torch.cuda.current_stream()
 		_CAPTURE_STREAM.wait_stream(cur)
 		with torch.cuda.stream(_CAPTURE_STREAM):
-			self.graph.capture_begin(pool=self.pool, capture_error_mode='thread_local')
+			self.graph.capture_begin(capture_error_mode='thread_local')
 			try:
-				for _ in range(self.unit):
-					self.body()
+				if self.prepare is None:
+					for _ in range(self.unit):
+						self.body()
+				else:
+					main, side = _CAPTURE_STREAM, _side_stream()
+					keep = [self.prepare()]	# every prepared batch stays referenced until the capture ends: a block freed on one stream
+					for j in range(self.unit):	# must not be handed out again while the other stream's kernels still read it
+						if j + 1 < self.unit:
+							side.wait_stream(main)	# (joins the capture; orders this prepare after the previous one's consumers were issued)
+							with torch.cuda.stream(side):
+								keep.append(self.prepare())
+						self._body_in(keep[j])
+						main.wait_stream(side)
+					del keep
 			finally:
 				self.graph.capture_end()
 		cur.wait_stream(_CAPTURE_STREAM)
@@ -86,4 +116,3 @@ class GraphedLoop:
 		if self.graph is not None:
 			torch.cuda.current_stream().synchronize()	# the last replay may still be running on the pool's memory
 			self.graph = None
-			_FREE_POOLS.append(self.pool)
