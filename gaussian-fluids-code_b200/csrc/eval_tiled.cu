@@ -284,6 +284,7 @@ static int64_t tile_slots(const Grid &g, int64_t Q)
 extern int g_force_radix;	// grid.cu
 extern int g_step_small_n;	// step.cu
 extern int g_step_lanes4;	// step.cu
+extern int g_step_fused_hash;	// step.cu
 extern int g_gather_cta_max_n;	// backward.cu
 
 // tunables (gsr_set_tuning)
@@ -337,6 +338,7 @@ extern "C" int gsr_set_tuning(int key, int value)
 	case GSR_TUNE_FORCE_RADIX: g_force_radix = value; return GSR_OK;
 	case GSR_TUNE_STEP_SMALL_N: g_step_small_n = value; return GSR_OK;
 	case GSR_TUNE_STEP_LANES4: g_step_lanes4 = value; return GSR_OK;
+	case GSR_TUNE_STEP_FUSED_HASH: g_step_fused_hash = value; return GSR_OK;
 	case GSR_TUNE_GATHER_CTA_MAX_N: g_gather_cta_max_n = value; return GSR_OK;
 	case GSR_TUNE_LANES8_MIN_N: g_lanes8_min_n = value; return GSR_OK;
 	case GSR_TUNE_FW_P4_MIN_SPC: g_fw_p4_min_spc = value; return GSR_OK;

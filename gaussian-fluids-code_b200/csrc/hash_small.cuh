@@ -9,14 +9,13 @@ namespace gsr {
 // Gaussian keys: row-major cell index, or ncell for Gaussians outside the extended domain
 // (the reference silently drops those from the hash: 3D/GSR.py:212).
 template <int D>
-__device__ __forceinline__ uint32_t gauss_key(const float *__restrict__ pos, int i, const Grid &g)
+__device__ __forceinline__ uint32_t gauss_key_vals(const float *pt, const Grid &g, float gs)
 {
 	bool in = true;
 	int c[3] = {0, 0, 0};
-	const float gs = grid_gs(g);
 #pragma unroll
 	for (int k = 0; k < D; k++) {
-		float p = pos[(size_t)D * i + k];
+		float p = pt[k];
 		in = in && (g.lo[k] <= p) && (p <= g.hi[k]);
 		c[k] = cell_coord(p, g.lo[k], gs);
 	}
@@ -27,6 +26,15 @@ __device__ __forceinline__ uint32_t gauss_key(const float *__restrict__ pos, int
 	uint32_t key = (uint32_t)g.ncell;
 	if (in) key = (uint32_t)((c[0] * g.dims[1] + c[1]) * g.dims[2] + c[2]);
 	return key;
+}
+
+template <int D>
+__device__ __forceinline__ uint32_t gauss_key(const float *__restrict__ pos, int i, const Grid &g)
+{
+	float pt[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+	for (int k = 0; k < D; k++) pt[k] = pos[(size_t)D * i + k];
+	return gauss_key_vals<D>(pt, g, grid_gs(g));
 }
 
 
@@ -81,10 +89,10 @@ __device__ __forceinline__ float cull_coef(float smin, float smax)
 	return expf(-2.f * smin) * (1.f + 1e-4f + 8e-6f * kappa);
 }
 
-__device__ __forceinline__ void pack3d_one(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot,
-					   const float *__restrict__ vals, int t, int i, float4 *__restrict__ packed, float *__restrict__ cull)
+// the record from values: p, s = the Gaussian's position and log inverse radii, S[k] = exp2s(s[k]), r = quaternion, v = weight
+__device__ __forceinline__ void pack3d_core(const float *p, const float *s, const float *S, float4 r, const float *v, int t, float4 *__restrict__ packed,
+					    float *__restrict__ cull)
 {
-	float4 r = reinterpret_cast<const float4 *>(rot)[i];
 	float len = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.x, r.x), __fmul_rn(r.y, r.y)), __fmul_rn(r.z, r.z)), __fmul_rn(r.w, r.w)));
 	float q0 = __fdiv_rn(r.x, len), q1 = __fdiv_rn(r.y, len), q2 = __fdiv_rn(r.z, len), q3 = __fdiv_rn(r.w, len);
 #define MUL __fmul_rn
@@ -100,7 +108,6 @@ __device__ __forceinline__ void pack3d_one(const float *__restrict__ pos, const 
 	R[2][0] = MUL(2.f, SUB(MUL(q1, q3), MUL(q0, q2)));
 	R[2][1] = MUL(2.f, ADD(MUL(q2, q3), MUL(q0, q1)));
 	R[2][2] = SUB(1.f, MUL(2.f, ADD(MUL(q1, q1), MUL(q2, q2))));
-	float S[3] = {exp2s(scal[3 * (size_t)i]), exp2s(scal[3 * (size_t)i + 1]), exp2s(scal[3 * (size_t)i + 2])};
 	float A[3][3];
 #pragma unroll
 	for (int a = 0; a < 3; a++)
@@ -110,34 +117,42 @@ __device__ __forceinline__ void pack3d_one(const float *__restrict__ pos, const 
 #undef MUL
 #undef ADD
 #undef SUB
-	const float *p = pos + 3 * (size_t)i, *v = vals + 3 * (size_t)i;
 	packed[3 * (size_t)t + 0] = make_float4(p[0], p[1], p[2], v[0]);
 	packed[3 * (size_t)t + 1] = make_float4(A[0][0], A[0][1], A[0][2], v[1]);
 	packed[3 * (size_t)t + 2] = make_float4(A[1][1], A[1][2], A[2][2], v[2]);
-	if (cull) {
-		const float s0 = scal[3 * (size_t)i], s1 = scal[3 * (size_t)i + 1], s2 = scal[3 * (size_t)i + 2];
-		cull[t] = cull_coef(fminf(s0, fminf(s1, s2)), fmaxf(s0, fmaxf(s1, s2)));
-	}
+	if (cull) cull[t] = cull_coef(fminf(s[0], fminf(s[1], s[2])), fmaxf(s[0], fmaxf(s[1], s[2])));
+}
+
+__device__ __forceinline__ void pack3d_one(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot,
+					   const float *__restrict__ vals, int t, int i, float4 *__restrict__ packed, float *__restrict__ cull)
+{
+	const float4 r = reinterpret_cast<const float4 *>(rot)[i];
+	const float s[3] = {scal[3 * (size_t)i], scal[3 * (size_t)i + 1], scal[3 * (size_t)i + 2]};
+	const float S[3] = {exp2s(s[0]), exp2s(s[1]), exp2s(s[2])};
+	pack3d_core(pos + 3 * (size_t)i, s, S, r, vals + 3 * (size_t)i, t, packed, cull);
 }
 
 
 // 2D record (2 x float4): {mu.x, mu.y, v.x, v.y} {A00, A01, A11, 0},  A = R(theta) diag(e^{2s}) R^T (2D/GSR.py:275-277)
-__device__ __forceinline__ void pack2d_one(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot,
-					   const float *__restrict__ vals, int t, int i, float4 *__restrict__ packed, float *__restrict__ cull)
+// c, s = (float)cos / sin of the angle in double, S0, S1 = exp2s of the two log inverse radii sc[0], sc[1]
+__device__ __forceinline__ void pack2d_core(const float *p, const float *sc, float S0, float S1, float c, float s, const float *v, int t,
+					    float4 *__restrict__ packed, float *__restrict__ cull)
 {
-	double th = (double)rot[i];
-	float c = (float)cos(th), s = (float)sin(th);
-	float S0 = exp2s(scal[2 * (size_t)i]), S1 = exp2s(scal[2 * (size_t)i + 1]);
 	float R[2][2] = {{c, -s}, {s, c}};
 	float A00 = __fadd_rn(__fmul_rn(__fmul_rn(R[0][0], S0), R[0][0]), __fmul_rn(__fmul_rn(R[0][1], S1), R[0][1]));
 	float A01 = __fadd_rn(__fmul_rn(__fmul_rn(R[0][0], S0), R[1][0]), __fmul_rn(__fmul_rn(R[0][1], S1), R[1][1]));
 	float A11 = __fadd_rn(__fmul_rn(__fmul_rn(R[1][0], S0), R[1][0]), __fmul_rn(__fmul_rn(R[1][1], S1), R[1][1]));
-	packed[2 * (size_t)t + 0] = make_float4(pos[2 * (size_t)i], pos[2 * (size_t)i + 1], vals[2 * (size_t)i], vals[2 * (size_t)i + 1]);
+	packed[2 * (size_t)t + 0] = make_float4(p[0], p[1], v[0], v[1]);
 	packed[2 * (size_t)t + 1] = make_float4(A00, A01, A11, 0.f);
-	if (cull) {
-		const float s0 = scal[2 * (size_t)i], s1 = scal[2 * (size_t)i + 1];
-		cull[t] = cull_coef(fminf(s0, s1), fmaxf(s0, s1));
-	}
+	if (cull) cull[t] = cull_coef(fminf(sc[0], sc[1]), fmaxf(sc[0], sc[1]));
+}
+
+__device__ __forceinline__ void pack2d_one(const float *__restrict__ pos, const float *__restrict__ scal, const float *__restrict__ rot,
+					   const float *__restrict__ vals, int t, int i, float4 *__restrict__ packed, float *__restrict__ cull)
+{
+	const double th = (double)rot[i];
+	const float sc[2] = {scal[2 * (size_t)i], scal[2 * (size_t)i + 1]};
+	pack2d_core(pos + 2 * (size_t)i, sc, exp2s(sc[0]), exp2s(sc[1]), (float)cos(th), (float)sin(th), vals + 2 * (size_t)i, t, packed, cull);
 }
 
 

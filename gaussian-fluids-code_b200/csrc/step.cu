@@ -7,6 +7,7 @@
 // Here: 4 launches, no sync.  HBM-bound: per Gaussian reads params 52 B + Adam m,v 104 B + accumulators
 // 48 B/set (twice: kernels A and B), writes params 52 B + m,v 104 B.
 #include "chain.cuh"
+#include "hash_small.cuh"
 #include <math.h>
 #include <cooperative_groups.h>
 
@@ -664,12 +665,27 @@ constexpr int SC4_G = 4;
 constexpr int SC4_MAX_THREADS = 512;
 constexpr int SC4_MAX_N = SC_CTAS * SC4_MAX_THREADS / SC4_G;
 int g_step_lanes4 = 1;	// GSR_TUNE_STEP_LANES4
+int g_step_fused_hash = 1;	// GSR_TUNE_STEP_FUSED_HASH
 
-template <int D>
+constexpr int SC4_MAX_CELLS = 1024;	// hash cells the fused rebuild keeps in shared memory (+ 1 tail bucket)
+
+struct HashOut {	// HASH: the rebuilt hash of gsr_build_grid, written by the step kernel itself
+	Grid g;
+	int32_t *cell_start, *sorted_id;
+	float4 *packed;
+	float *cull;
+};
+
+// HASH = true: the kernel goes on to rebuild the cell hash and the packed records from the parameters it has just updated (what
+// gsr_step_rebuild otherwise appends as a second launch): a stable counting sort over the cluster — per-CTA histograms in shared
+// memory, read by every CTA through distributed shared memory; a Gaussian's slot is cell_start[key] + the counts of the lower-ranked
+// CTAs in its cell + the number of lower ids with the same key in its own CTA (ids ascend with CTA rank and thread), which is the
+// canonical ascending-id order of every other hash path.
+template <int D, bool HASH>
 __global__ void __cluster_dims__(SC_CTAS, 1, 1) __launch_bounds__(SC4_MAX_THREADS, 1)
 step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__restrict__ scal, float *__restrict__ rot, float *__restrict__ vals,
 		     const float *__restrict__ acc, int sets_mask, const float *__restrict__ ex0, const float *__restrict__ ex1,
-		     const float *__restrict__ pos_org, LossSrcs ls, float *st)
+		     const float *__restrict__ pos_org, LossSrcs ls, float *st, HashOut H)
 {
 	namespace cg = cooperative_groups;
 	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR, P = Dim<D>::P, G = SC4_G, KPL = (P + G - 1) / G;
@@ -683,12 +699,21 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 	__shared__ float wmin[SC4_MAX_THREADS / 32];
 	__shared__ float bmin;
 	__shared__ float Tg[SC4_MAX_THREADS / G][G][P + 1];	// parameter-space gradients of the four roles of every Gaussian of this CTA
+	__shared__ uint32_t hist[HASH ? SC4_MAX_CELLS + 1 : 1];	// this CTA's Gaussians per cell (read by the other CTAs)
+	__shared__ uint32_t hstart[HASH ? SC4_MAX_CELLS + 1 : 1];	// cell totals over the cluster, then their exclusive prefix (= cell_start)
+	__shared__ uint32_t hbase[HASH ? SC4_MAX_CELLS + 1 : 1];	// Gaussians of lower-ranked CTAs per cell
+	__shared__ uint32_t hkey[HASH ? SC4_MAX_THREADS / G : 1];	// key of every Gaussian of this CTA
+	__shared__ uint32_t hwarp[32];
+	__shared__ float gs_sm;
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
 	const int rank = (int)cluster.block_rank();
 	const int gl = tid / G, sub = tid % G;
 	const int i = rank * (blockDim.x / G) + gl;
 	const bool on = i < N;
 	for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x) cst[k] = st[k];
+	if (HASH) {
+		for (int c = tid; c <= H.g.ncell; c += blockDim.x) hist[c] = 0;
+	}
 	// ---- every load of this lane, issued together ------------------------------------------------------------------------
 	float sc[D], r[NR], a[AF], a2nd[AF];
 	// role of this lane: 0 vorticity set, 1 divergence set, 2 direct set, 3 the extra direct sets (boundary passes)
@@ -872,6 +897,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 			m[k] = mk;
 			vv[k] = vk;
 			*pp[j] = pk;
+			if (HASH) Tg[gl][0][k] = pk;	// (the gradients were consumed above) the updated record, for the key and the packed record
 			if (grp == 1) smin = fminf(smin, pk);
 		}
 	}
@@ -888,11 +914,107 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 	if (rank == 0) {
 		for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x)
 			if (k != GSR_ST_GRID_SCALE && k != GSR_ST_MIN_S) st[k] = cst[k];
-		if (tid == 0) {
-			float mn = fminf(bmin, cst[GSR_ST_MIN_S]);
+	}
+	if (tid == 0 && (rank == 0 || HASH)) {	// the next grid_scale: every CTA needs it for the keys, CTA 0 publishes it
+		float mn = cst[GSR_ST_MIN_S];
 #pragma unroll
-			for (int q = 1; q < SC_CTAS; q++) mn = fminf(mn, *cluster.map_shared_rank(&bmin, q));
-			step_grid_scale(cfg, st, mn);
+		for (int q = 0; q < SC_CTAS; q++) mn = fminf(mn, *cluster.map_shared_rank(&bmin, q));
+		double gs = cfg.grid_scale_tau0;
+		if (cfg.grid_coef > 0.) gs = fmax(cfg.grid_coef * exp(-(double)mn), cfg.min_grid_scale);
+		gs_sm = (float)gs;
+		if (rank == 0) step_grid_scale(cfg, st, mn);
+	}
+	if (HASH) {
+		const Grid &g = H.g;
+		const int ncell = g.ncell;
+		__syncthreads();	// gs_sm (the Tg rows of the updated parameters were written by this warp's own lanes)
+		uint32_t key = 0;
+		if (sub == 0) {
+			if (on) {
+				float pt[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+				for (int k = 0; k < D; k++) pt[k] = Tg[gl][0][k];
+				key = gauss_key_vals<D>(pt, g, gs_sm);
+				atomicAdd(&hist[key], 1u);
+			}
+			hkey[gl] = on ? key : 0xffffffffu;	// (not a Gaussian: matches no key)
+		}
+		cluster.sync();	// every CTA's histogram is complete
+		for (int c = tid; c <= ncell; c += blockDim.x) {
+			uint32_t tot = 0, base = 0;
+#pragma unroll
+			for (int q = 0; q < SC_CTAS; q++) {
+				const uint32_t h = *cluster.map_shared_rank(&hist[c], q);
+				base += (q < rank) ? h : 0u;
+				tot += h;
+			}
+			hstart[c] = tot;
+			hbase[c] = base;
+		}
+		__syncthreads();
+		{	// exclusive prefix of hstart[0..ncell]: a chunk per thread, warp scan, scan of the warp sums
+			const int mm = ncell + 1, chunk = (mm + (int)blockDim.x - 1) / (int)blockDim.x;
+			const int b = min(tid * chunk, mm), e = min(b + chunk, mm);
+			uint32_t sum = 0;
+			for (int c = b; c < e; c++) sum += hstart[c];
+			uint32_t v = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+				if (lane >= o) v += t;
+			}
+			if (lane == 31) hwarp[w] = v;
+			__syncthreads();
+			if (w == 0) {
+				const uint32_t ws = lane < nw ? hwarp[lane] : 0u;
+				uint32_t t2 = ws;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t t = __shfl_up_sync(0xffffffffu, t2, o);
+					if (lane >= o) t2 += t;
+				}
+				hwarp[lane] = t2 - ws;
+			}
+			__syncthreads();
+			uint32_t run = hwarp[w] + (v - sum);
+			for (int c = b; c < e; c++) {
+				const uint32_t t = hstart[c];
+				hstart[c] = run;
+				if (rank == 0) H.cell_start[c] = (int32_t)run;
+				run += t;
+			}
+		}
+		__syncthreads();
+		// slot of this Gaussian: its four lanes count the lower ids of the CTA with the same key, a quarter of the range each
+		const int l0 = lane & ~(G - 1);
+		key = __shfl_sync(0xffffffffu, key, l0);
+		uint32_t lower = 0;
+		for (int q = sub; q < gl; q += G) lower += (hkey[q] == key) ? 1u : 0u;
+		lower += __shfl_xor_sync(0xffffffffu, lower, 1);
+		lower += __shfl_xor_sync(0xffffffffu, lower, 2);
+		// the double-precision exponentials (3D) / exponentials, cosine and sine (2D) of the record, one per lane
+		float piece = 0.f;
+		if (on) {
+			if (D == 3) {
+				if (sub < 3) piece = exp2s(Tg[gl][0][D + sub]);
+			} else {
+				const double th = (double)Tg[gl][0][2 * D];
+				piece = sub < 2 ? exp2s(Tg[gl][0][D + sub]) : (sub == 2 ? (float)cos(th) : (float)sin(th));
+			}
+		}
+		const float e0 = __shfl_sync(0xffffffffu, piece, l0), e1 = __shfl_sync(0xffffffffu, piece, l0 + 1), e2 = __shfl_sync(0xffffffffu, piece, l0 + 2),
+			    e3 = __shfl_sync(0xffffffffu, piece, l0 + 3);
+		if (on && sub == 0) {
+			const int slot = (int)(hstart[key] + hbase[key] + lower);
+			H.sorted_id[slot] = i;
+			const float *q = Tg[gl][0];
+			if (D == 3) {
+				const float S3[3] = {e0, e1, e2};
+				pack3d_core(q, q + D, S3, make_float4(q[2 * D], q[2 * D + 1], q[2 * D + 2], q[2 * D + 3]), q + 2 * D + NR, slot, H.packed, H.cull);
+			} else {
+				pack2d_core(q, q + D, e0, e1, e2, e3, q + 2 * D + NR, slot, H.packed, H.cull);
+				(void)e3;
+			}
 		}
 	}
 	cluster.sync();	// no CTA may exit while another still reads its shared memory
@@ -964,8 +1086,18 @@ static int step_impl(const gsr_step_cfg *cfg, int64_t N, float *positions, float
 	const float *ex0 = extra_direct ? extra_direct[0] : nullptr, *ex1 = extra_direct ? extra_direct[1] : nullptr;
 	if (N <= g_step_small_n && N <= SC4_MAX_N && g_step_lanes4) {
 		const int bt = ((((n + SC_CTAS - 1) / SC_CTAS) * SC4_G) + 31) & ~31;	// Gaussians per CTA x 4 lanes, whole warps
-		if (cfg->D == 3) step_cluster4_kernel<3><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state);
-		else step_cluster4_kernel<2><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state);
+		HashOut H;
+		H.cell_start = nullptr;
+		if (gd && packed && g_step_fused_hash && g.ncell <= SC4_MAX_CELLS) {	// step + hash rebuild + packed records: one launch
+			H.g = g; H.cell_start = cell_start; H.sorted_id = sorted_id; H.packed = (float4 *)packed; H.cull = cull;
+			if (cfg->D == 3) step_cluster4_kernel<3, true><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state, H);
+			else step_cluster4_kernel<2, true><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state, H);
+			g_launches += 1;
+			GSR_CHECK_LAUNCH();
+			return GSR_OK;
+		}
+		if (cfg->D == 3) step_cluster4_kernel<3, false><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state, H);
+		else step_cluster4_kernel<2, false><<<SC_CTAS, bt, 0, st>>>(*cfg, n, positions, scalings, rotations, values, acc, sets_mask, ex0, ex1, positions_org, ls, state, H);
 		g_launches += 1;
 	} else if (N <= g_step_small_n && N <= SC_MAX_N) {
 		const int bt = (((n + SC_CTAS - 1) / SC_CTAS) + 31) & ~31;

@@ -77,12 +77,20 @@ def test_sample_box_surface_matches_reference_semantics():
 		assert np.abs(u.mean(0) - .5).max() < 1e-2
 
 
-def test_step_rebuild_equals_step_then_build():
-	"""gsr_step_rebuild == gsr_step followed by gsr_build_grid + gsr_pack_gaussians on the updated parameters"""
+@pytest.mark.parametrize('n,outside', [(8, 0), (6, 0), (10, 0), (10, 7), (12, 0)])
+def test_step_rebuild_equals_step_then_build(n, outside):
+	"""gsr_step_rebuild == gsr_step followed by gsr_build_grid + gsr_pack_gaussians on the updated parameters.  Up to 1024 Gaussians
+	the rebuild happens inside the step's own cluster launch (step_cluster4_kernel<D, true>: counting sort over distributed shared
+	memory): cell table, ids and packed records must be those of the separate hash build bit for bit; `outside` Gaussians sit
+	beyond the extended domain (the tail bucket, whose internal order no kernel reads)"""
 	from gaussian_fluids_code_b200.engine import FusedStepper
 	res = []
 	for rebuild in (False, True):
-		o, gen = engine_field(8)
+		o, gen = engine_field(n)
+		if outside:
+			with torch.no_grad():
+				o.positions[torch.arange(outside) * 37 % o.N] += 5.
+			o.reinitialize_grid()
 		e = o._engine
 		x = torch.rand((o.N, 3), generator=torch.Generator().manual_seed(3)).cuda()
 		e.ensure_packed(o._params())
@@ -101,7 +109,14 @@ def test_step_rebuild_equals_step_then_build():
 		torch.cuda.synchronize()
 		res.append([p.cpu().numpy().copy() for p in params] + [e.cell_start.cpu().numpy().copy(), e.sorted_id.cpu().numpy().copy(), e.packed.cpu().numpy().copy(),
 																   e.cull.cpu().numpy().copy(), np.array(st.scalars()[:14])])
-	for a, b in zip(*res):
+	n_in = int(res[0][4][-1])	# cell_start[ncell]: Gaussians inside the hash
+	assert n_in == o.N - outside
+	for k, (a, b) in enumerate(zip(*res)):
+		if k in (5, 6, 7) and outside:	# sorted_id, packed, cull: the tail bucket holds the same Gaussians in any order
+			a, b = a.reshape(o.N, -1), b.reshape(o.N, -1)
+			np.testing.assert_array_equal(a[:n_in], b[:n_in])
+			np.testing.assert_array_equal(np.sort(a[n_in:], axis=0), np.sort(b[n_in:], axis=0))
+			continue
 		np.testing.assert_array_equal(a, b)
 
 
@@ -145,8 +160,8 @@ def test_step_cluster_launch_equals_four_launch(n):
 
 def test_xrank_sum_single_rank():
 	"""gsr_xrank_sum with world = 1 (a single GPU cannot host kernels that wait for one another): the handshake with itself, the
-	epoch arithmetic over two parities, and the copy-out.  The 2-rank behaviour is checked by tools/exchange_check.py under torchrun
-	(bit-identical replicas, equality with NCCL) and the summation identity by tests/test_multirank_cpu.py."""
+	epoch arithmetic over two parities, and the copy-out.  The 2-rank behaviour is checked by tests/test_gpu_multirank.py on a two-GPU box
+	(bit-identical replicas, equality with NCCL, lost peer) and the summation identity by tests/test_multirank_cpu.py."""
 	import ctypes as C
 	from gaussian_fluids_code_b200 import _lib
 	lib = _lib.lib()
