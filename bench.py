@@ -549,6 +549,8 @@ def run_ours(args):
 	value = C_job * args.steps / (ms * 1e-3)
 
 	# ---- end-to-end: host buffers in, host buffers out, copies inside the timed region -----------------------------
+	import argparse
+	timed_steps(ts, argparse.Namespace(steps=1), barrier, dev, world, dist, host_params, host_out, host_fields)	# untimed: first use of the pinned buffers and copy paths
 	ms_e2e = timed_steps(ts, args, barrier, dev, world, dist, host_params, host_out, host_fields)
 	h2d = sum(p.numel() * 4 for p in host_params)
 	d2h = sum(p.numel() * 4 for p in host_out) + sum(f.numel() * 4 for f in host_fields)

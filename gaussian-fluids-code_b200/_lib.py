@@ -26,7 +26,7 @@ class LossCfg(C.Structure):
 	_fields_ = [('w_val', C.c_float), ('w_boundary', C.c_float), ('w_grad', C.c_float), ('w_vor', C.c_float), ('w_hel', C.c_float), ('w_div', C.c_float),
 				('Q_norm', C.c_int64),
 				('ref_val', C.c_void_p), ('normals', C.c_void_p), ('normal_ref', C.c_void_p), ('ref_grad', C.c_void_p),
-				('ref_vor', C.c_void_p), ('ref_hel', C.c_void_p), ('stop_gradient', C.c_void_p), ('loss_partials', C.c_void_p)]
+				('ref_vor', C.c_void_p), ('ref_hel', C.c_void_p), ('stop_gradient', C.c_void_p), ('sample_grid_scale_dev', C.c_void_p), ('loss_partials', C.c_void_p)]
 
 
 class StepCfg(C.Structure):
@@ -36,7 +36,7 @@ class StepCfg(C.Structure):
 				('w_aniso', C.c_float), ('w_vol', C.c_float), ('w_valreg', C.c_float), ('w_dpos', C.c_float),
 				('aniso_ratio', C.c_float), ('pcgrad', C.c_int32),
 				('grid_coef', C.c_double), ('min_grid_scale', C.c_double), ('grid_scale_tau0', C.c_double),
-				('keep_clock', C.c_int32), ('grid_scale_out', C.c_void_p)]
+				('keep_clock', C.c_int32), ('sample_gs_slots', C.c_void_p), ('sample_gs_margin', C.c_float), ('grid_scale_out', C.c_void_p)]
 
 
 class LossSrc(C.Structure):
@@ -47,6 +47,7 @@ class LossSrc(C.Structure):
 STATE_SCALARS = 64
 ST_T, ST_BEST, ST_BAD, ST_LR, ST_GRID_SCALE, ST_MIN_S, ST_LOSS_TOT, ST_L_ANISO, ST_L_VOL, ST_L_VALREG, ST_L_DPOS = 0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 13
 ST_CLOCK = 22
+ST_SGS_ERR = 23
 
 
 class GsrError(RuntimeError):

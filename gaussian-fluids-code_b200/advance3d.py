@@ -28,6 +28,7 @@ import torch
 import torch.nn.functional as F
 
 from . import gsr3d
+from . import _lib
 from .engine import FusedStepper
 from .gsr3d import GaussianSplatting3DFast, get_grid_points  # noqa: F401  (re-exported like the reference's star import)
 
@@ -205,12 +206,21 @@ class FusedProjector:
 		e = gv._engine
 		self.stepper = FusedStepper(e, [self.lrs[k] for k in ('positions', 'scalings', 'rotations', 'values')], patience,
 									self.w['aniso'], self.w['vol'], w_valreg=self.w['val_reg'], pcgrad=True,
-									tau=gv.clamp_threshold, min_grid_scale=gv.min_grid_scale, ext_bounds=gv._ext())
+									tau=gv.clamp_threshold, min_grid_scale=gv.min_grid_scale, ext_bounds=gv._ext(), sample_grid_ahead=True)
 		self.stepper.init(gv.scalings)
+		self._it = 0	# iterations since the phase began (host count; inside replayed graphs only its parity is meaningful)
 		self._rebuild()
 		cur = reference_field.velocity_field
 		cur._engine.ensure_packed(cur._params())
 		self._buf = {}
+
+	def sample_grid(self, iteration=None):
+		"""The grid scale the sample batches of an iteration are binned with (a device scalar): not the hash's own but one the step
+		kernel left an iteration EARLIER (gsr_step_cfg.sample_gs_slots: slot [iteration & 1] = (1 + margin) x the previous grid_scale,
+		checked against the next one) — so a batch can be drawn and ordered before the step that rebuilds the hash has finished
+		(timestep3d.ShardedProjector does).  Every form of the iteration uses it, which keeps them bit-identical."""
+		it = self._it if iteration is None else iteration
+		return self.stepper.sample_gs[(it & 1):(it & 1) + 1]
 
 	def _rebuild(self):
 		gv = self.gv
@@ -231,14 +241,16 @@ class FusedProjector:
 		cur = self.ref.velocity_field
 		Q = data.shape[0]
 		data = data.detach()
-		bins = e.bin_samples(data, True)
+		sgs = self.sample_grid()
+		self._it += 1
+		bins = e.bin_samples(data, True, gs_dev=sgs)
 		perm, scs = bins
 		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
 		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
 		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
 		e.forward(data, val, grad, accumulate=False, perm=bins)
 		acc, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
-									  {'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, want_losses=True)
+									  {'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, want_losses=True, sample_gs=sgs)
 		lp, nblk = e.last_loss_partials
 		srcs = [(lp, nblk, [self.w['vor'] / Q, 0., self.w['div'] / Q, 0., 0., 0., 0., 0.])]
 		extra = []
@@ -246,12 +258,12 @@ class FusedProjector:
 			bdata, bnormal = boundary
 			bdata, bnormal = bdata.detach(), bnormal.detach()
 			Qb = bdata.shape[0]
-			bins_b = e.bin_samples(bdata, True, tag='b')
+			bins_b = e.bin_samples(bdata, True, tag='b', gs_dev=sgs)
 			perm_b, scs_b = bins_b
 			valb = self._tmp('valb', (Qb, 3))
 			e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
 			acc_b, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
-											  {'normals': bnormal}, None, tag='acc_b', want_losses=True)
+											  {'normals': bnormal}, None, tag='acc_b', want_losses=True, sample_gs=sgs)
 			lpb, nblkb = e.last_loss_partials
 			srcs.append((lpb, nblkb, [0., 0., 0., self.boundary_lambda / Qb, 0., 0., 0., 0.]))
 			extra.append(acc_b)
@@ -277,8 +289,15 @@ class FusedProjector:
 		e.forward(data, val, grad, accumulate=False, perm=bins)
 		return e.sample_losses(val, grad, {'ref_vor': ref_vor, 'ref_hel': ref_hel}, Q) / Q
 
+	def check_sample_grid(self):
+		"""raises if a step found the hash's grid_scale above the sample grid a batch had been ordered with (synchronises)"""
+		if float(self.stepper.state[_lib.ST_SGS_ERR].item()) != 0.:
+			raise _lib.GsrError('grid_scale grew by more than the sample grid margin within one optimiser step: the learning rate of the '
+								'scalings is too large for exp(4 lr) to bound it')
+
 	def finish(self):
 		"""return control to the generic API: host grid_scale, fresh hash, version-tracked packing"""
+		self.check_sample_grid()
 		gv = self.gv
 		gv.grid_scale = self.stepper.detach()
 		gv._engine._packed_key = None

@@ -705,6 +705,7 @@ extern "C" int gsr_backward_gather(const gsr_grid_desc *d, const int32_t *cell_s
 	const AdjIn lin = {x, val, grad, cfg->ref_val, cfg->normals, cfg->normal_ref, cfg->ref_grad, cfg->ref_vor, cfg->ref_hel};
 	if (cfg->loss_partials && Q == 0) cudaMemsetAsync(cfg->loss_partials, 0, 8 * sizeof(float), st);
 	EvalParams P = make_params(g);
+	if (cfg->sample_grid_scale_dev) P.g.gs_dev = cfg->sample_grid_scale_dev;	// the gather uses the grid scale only to find a Gaussian's sample cells
 	// lanes per Gaussian: by the amount of parallelism N offers, and more when there are many samples per Gaussian
 	int lpg = pick_lanes(N);
 	if (lpg == 1 && Q >= 8 * N) lpg = 8;

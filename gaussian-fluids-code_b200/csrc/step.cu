@@ -320,12 +320,22 @@ __global__ void __launch_bounds__(ST_THREADS) stepB_kernel(gsr_step_cfg cfg, int
 
 // next grid_scale (3D/GSR.py:248-251), formed in double like the reference's host code, then rounded to f32;
 // re-arms the min accumulator for the next iteration.
-__device__ __forceinline__ void step_grid_scale(const gsr_step_cfg &cfg, float *st, float min_s)
+__device__ __forceinline__ void step_grid_scale(const gsr_step_cfg &cfg, float *st, float min_s, int t_new = -1)
 {
 	double gs = cfg.grid_scale_tau0;
 	if (cfg.grid_coef > 0.) gs = fmax(cfg.grid_coef * exp(-(double)min_s), cfg.min_grid_scale);
 	st[GSR_ST_GRID_SCALE] = (float)gs;
 	if (cfg.grid_scale_out) *cfg.grid_scale_out = (float)gs;
+	if (cfg.sample_gs_slots) {	// the sample grid scales, one iteration ahead (include/gsr_b200.h)
+		const float ahead = (float)(gs * (double)cfg.sample_gs_margin);
+		if (t_new <= 0) {	// gsr_step_init
+			cfg.sample_gs_slots[0] = cfg.sample_gs_slots[1] = ahead;
+			st[GSR_ST_SGS_ERR] = 0.f;
+		} else {
+			if ((float)gs > cfg.sample_gs_slots[t_new & 1]) st[GSR_ST_SGS_ERR] = 1.f;
+			cfg.sample_gs_slots[(t_new + 1) & 1] = ahead;
+		}
+	}
 	st[GSR_ST_MIN_S] = __int_as_float(0x7f800000);
 }
 
@@ -333,7 +343,7 @@ __global__ void stepS_kernel(gsr_step_cfg cfg, float *st, float *min_out)
 {
 	const float min_s = st[GSR_ST_MIN_S];
 	if (min_out) *min_out = min_s;
-	step_grid_scale(cfg, st, min_s);
+	step_grid_scale(cfg, st, min_s, (int)st[GSR_ST_T]);	// T was advanced by kernel R (0 at gsr_step_init)
 }
 
 // ---- small N (the reference's own sizes): the whole step as ONE launch of ONE 8-CTA cluster ---------------------------------
@@ -631,12 +641,12 @@ step_cluster_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__r
 	cluster.sync();
 	if (rank == 0) {
 		for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x)
-			if (k != GSR_ST_GRID_SCALE && k != GSR_ST_MIN_S) st[k] = cst[k];
+			if (k != GSR_ST_GRID_SCALE && k != GSR_ST_MIN_S && k != GSR_ST_SGS_ERR) st[k] = cst[k];
 		if (tid == 0) {
 			float mn = fminf(bmin, cst[GSR_ST_MIN_S]);
 #pragma unroll
 			for (int q = 1; q < SC_CTAS; q++) mn = fminf(mn, *cluster.map_shared_rank(&bmin, q));
-			step_grid_scale(cfg, st, mn);
+			step_grid_scale(cfg, st, mn, (int)cst[GSR_ST_T]);
 		}
 	}
 	cluster.sync();	// no CTA leaves while CTA 0 may still read its shared memory
@@ -913,7 +923,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 	cluster.sync();
 	if (rank == 0) {
 		for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x)
-			if (k != GSR_ST_GRID_SCALE && k != GSR_ST_MIN_S) st[k] = cst[k];
+			if (k != GSR_ST_GRID_SCALE && k != GSR_ST_MIN_S && k != GSR_ST_SGS_ERR) st[k] = cst[k];
 	}
 	if (tid == 0 && (rank == 0 || HASH)) {	// the next grid_scale: every CTA needs it for the keys, CTA 0 publishes it
 		float mn = cst[GSR_ST_MIN_S];
@@ -922,7 +932,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 		double gs = cfg.grid_scale_tau0;
 		if (cfg.grid_coef > 0.) gs = fmax(cfg.grid_coef * exp(-(double)mn), cfg.min_grid_scale);
 		gs_sm = (float)gs;
-		if (rank == 0) step_grid_scale(cfg, st, mn);
+		if (rank == 0) step_grid_scale(cfg, st, mn, (int)cst[GSR_ST_T]);
 	}
 	if (HASH) {
 		const Grid &g = H.g;

@@ -92,6 +92,15 @@ class HashEngine:
 		self.desc.grid_scale_dev = self.gs_dev.data_ptr()
 		self.ncell = host.n_cells(self.D, dims)
 
+	def desc_at(self, gs_dev):
+		"""the hash descriptor with ANOTHER device-resident grid scale: sample batches may be binned on a grid one iteration ahead of
+		the hash's (gsr_step_cfg.sample_gs_slots), as long as the gather is told (backward_gather(sample_gs=...))"""
+		if gs_dev is None:
+			return self.desc
+		d = _lib.GridDesc.from_buffer_copy(self.desc)
+		d.grid_scale_dev = gs_dev.data_ptr()
+		return d
+
 	def build(self, positions, want_ref_format=False, params=None):
 		"""gsr_build_grid: radix sort of the Gaussian cell keys; with params = (positions, scalings, rotations, values) the packed
 		records are produced by the same call (one launch for small N)"""
@@ -156,7 +165,7 @@ class HashEngine:
 
 	BIN_CACHE_AGE = 16	# uses of a cached ordering before it is refreshed while grid_scale lives on the device
 
-	def bin_samples(self, x, need_cells, tag='x'):
+	def bin_samples(self, x, need_cells, tag='x', gs_dev=None):
 		"""
 		Order a batch of query points for the kernels.  Large forward-only batches (a static test / output lattice evaluated
 		again and again) keep their ordering: the tiled kernels only use it for locality — every point recomputes its own cell
@@ -185,7 +194,7 @@ class HashEngine:
 			scs = alloc('scs_', (pcell + 1,))
 		nbytes = self.lib.gsr_bin_samples_ws_bytes(C.byref(self.desc), C.c_int64(Q))
 		ws = self.scratch.get('sort_' + tag, nbytes)	# per tag: batches of different tags may be in flight on different streams
-		check(self.lib.gsr_bin_samples(C.byref(self.desc), ptr(x, name='x'), C.c_int64(Q), ptr(perm, torch.int32), ptr(scs, torch.int32, True), C.c_int(1 if need_tiles else 0),
+		check(self.lib.gsr_bin_samples(C.byref(self.desc_at(gs_dev)), ptr(x, name='x'), C.c_int64(Q), ptr(perm, torch.int32), ptr(scs, torch.int32, True), C.c_int(1 if need_tiles else 0),
 									   ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()), 'gsr_bin_samples')
 		tiles = None
 		if need_tiles:
@@ -240,8 +249,10 @@ class HashEngine:
 		check(self.lib.gsr_mark_neighbors(C.byref(self.desc), ptr(self.cell_start, torch.int32), ptr(self.sorted_id, torch.int32),
 										  ptr(self.packed, align16=True), ptr(x, name='x'), C.c_int64(x.shape[0]), ptr(mark, torch.int32), stream()), 'gsr_mark_neighbors')
 
-	def backward_gather(self, x, perm, scs, val, grad, weights, refs, stop_gradient, Q_norm=None, tag='acc', want_losses=False, acc=None, loss_partials=None):
-		"""returns (acc, sets_mask); acc is (3, N, 12|7) in original Gaussian order"""
+	def backward_gather(self, x, perm, scs, val, grad, weights, refs, stop_gradient, Q_norm=None, tag='acc', want_losses=False, acc=None, loss_partials=None,
+						sample_gs=None):
+		"""returns (acc, sets_mask); acc is (3, N, 12|7) in original Gaussian order; sample_gs: the device grid scale `scs` was binned
+		with when that is not the hash's (bin_samples(gs_dev=...))"""
 		x = self._x(x)
 		Q = x.shape[0]
 		cfg = LossCfg()
@@ -259,6 +270,8 @@ class HashEngine:
 				stop_gradient = stop_gradient.to(torch.int32)
 			keep.append(stop_gradient)
 			cfg.stop_gradient = ptr(stop_gradient, torch.int32, name='stop_gradient').value
+		if sample_gs is not None:
+			cfg.sample_grid_scale_dev = sample_gs.data_ptr()
 		self.last_loss_partials = None
 		if want_losses or loss_partials is not None:
 			nblk = self.lib.gsr_loss_blocks(C.c_int64(Q))
@@ -300,7 +313,7 @@ class HashEngine:
 		check(self.lib.gsr_sample_box(b, C.c_int64(out.shape[0]), C.c_uint64(seed), C.c_uint32(stream_id), ptr(iteration, allow_none=True), ptr(out), stream()), 'gsr_sample_box')
 		return out
 
-	def sample_box_surface_binned(self, box, data, normal, seed, stream_id, iteration=None, tag='pb'):
+	def sample_box_surface_binned(self, box, data, normal, seed, stream_id, iteration=None, tag='pb', gs_dev=None):
 		"""gsr_sample_box_surface_binned: draw the boundary samples AND order them for the kernels (one launch for the per-iteration
 		batch sizes); returns Bins — exactly what sample_box_surface + bin_samples(data, True, tag) give"""
 		b = (C.c_float * 6)(*[float(v) for v in box])
@@ -309,7 +322,7 @@ class HashEngine:
 		scs = self.scratch.typed('scs_' + tag, (self.lib.gsr_padded_cells(C.byref(self.desc)) + 1,), torch.int32)
 		ws = self.scratch.get('sort_' + tag, self.lib.gsr_bin_samples_ws_bytes(C.byref(self.desc), C.c_int64(Q)))
 		check(self.lib.gsr_sample_box_surface_binned(b, C.c_int64(Q), C.c_uint64(seed), C.c_uint32(stream_id), ptr(iteration, allow_none=True), ptr(data), ptr(normal),
-													 C.byref(self.desc), ptr(perm, torch.int32), ptr(scs, torch.int32), ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()),
+													 C.byref(self.desc_at(gs_dev)), ptr(perm, torch.int32), ptr(scs, torch.int32), ptr(ws, torch.uint8), C.c_size_t(ws.numel()), stream()),
 			  'gsr_sample_box_surface_binned')
 		return Bins(perm, scs, None)
 
@@ -362,7 +375,7 @@ class FusedStepper:
 	"""
 
 	def __init__(self, engine, lrs, patience, w_aniso, w_vol, w_valreg=0., w_dpos=0., pcgrad=True, factor=.9,
-				 tau=None, min_grid_scale=None, ext_bounds=None):
+				 tau=None, min_grid_scale=None, ext_bounds=None, sample_grid_ahead=False):
 		import numpy as np
 		self.e = engine
 		D = engine.D
@@ -380,6 +393,11 @@ class FusedStepper:
 		cfg.min_grid_scale = float(min_grid_scale)
 		cfg.grid_scale_tau0 = float(max(ext_bounds[2 * k + 1] - ext_bounds[2 * k] for k in range(D)))
 		cfg.grid_scale_out = engine.gs_dev.data_ptr()	# every step also leaves the next grid_scale in the field's persistent scalar
+		self.sample_gs = None
+		if sample_grid_ahead:	# sample grid scales one iteration ahead of the hash (gsr_step_cfg.sample_gs_slots): slot [iteration & 1]
+			self.sample_gs = torch.zeros(2, dtype=torch.float32, device=engine.device)
+			cfg.sample_gs_slots = self.sample_gs.data_ptr()
+			cfg.sample_gs_margin = float(np.exp(4. * float(lrs[1])) * (1. + 1e-6))	# Adam moves a log-radius by < 3.17 lr per step
 		self.cfg = cfg
 		self.N = None
 		self.state = None

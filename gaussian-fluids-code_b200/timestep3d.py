@@ -134,6 +134,8 @@ class ShardedProjector(advance3d.FusedProjector):
 	"""FusedProjector whose accumulators and loss partials live in one flat buffer that is all-reduced once per iteration"""
 
 	def __init__(self, gv, reference_field, boundary_lambda, Q, Qb, world=1, rank=0, patience=50, box=(0., 1.) * 3, boundary_box=None, seed=42):
+		# samples of iteration k + 1 drawn and binned while iteration k still runs (see iterate()); GSR_SAMPLES_AHEAD=0: after step k
+		self.ahead = os.environ.get('GSR_SAMPLES_AHEAD', '1') != '0'
 		super().__init__(gv, reference_field, boundary_lambda, patience=patience)
 		e = gv._engine
 		self.world, self.rank = world, rank
@@ -144,6 +146,7 @@ class ShardedProjector(advance3d.FusedProjector):
 		# persistent sample buffers: the device samplers write them, the captured graph reads them
 		self._x = torch.empty((Q, 3), dtype=torch.float32, device=dev)
 		self._xb, self._nb = torch.empty((Qb, 3), dtype=torch.float32, device=dev), torch.empty((Qb, 3), dtype=torch.float32, device=dev)
+		self._clock1 = torch.zeros(1, dtype=torch.float32, device=dev)	# sample clock + 1: the counter of a batch drawn one iteration early
 		self.graph, self.unit, self.per_iter, self.graph_launches = None, 0, 0, 0
 		N = gv.N
 		nblk, nblkb = e.lib.gsr_loss_blocks(Q), e.lib.gsr_loss_blocks(Qb)
@@ -172,17 +175,18 @@ class ShardedProjector(advance3d.FusedProjector):
 		self.set_samplers(self.draw_samples, self.draw_boundary_binned if self.boundary_lambda else None)
 
 	# ---- device samplers (one kernel each; the iteration number comes from the state's running sample clock) ----------------------
-	def draw_samples(self):
+	def draw_samples(self, clock=None):
 		"""this rank's training samples of the coming iteration: uniform in the box, Q = N (3D/advance.py:339-340)"""
-		return self.gv._engine.sample_box(self.box, self._x, self.seed, 2 * self.rank, self.stepper.clock)
+		return self.gv._engine.sample_box(self.box, self._x, self.seed, 2 * self.rank, clock if clock is not None else self.stepper.clock)
 
-	def draw_boundary(self):
-		"""sample_on_box(Qb) (3D/init_cond.py:227-249)"""
-		return self.gv._engine.sample_box_surface(self.boundary_box, self._xb, self._nb, self.seed, 2 * self.rank + 1, self.stepper.clock)
+	def draw_boundary(self, clock=None, gs_dev=None):
+		"""sample_on_box(Qb) (3D/init_cond.py:227-249) (unordered: gs_dev is for the samplers that also order the batch)"""
+		return self.gv._engine.sample_box_surface(self.boundary_box, self._xb, self._nb, self.seed, 2 * self.rank + 1, clock if clock is not None else self.stepper.clock)
 
-	def draw_boundary_binned(self):
+	def draw_boundary_binned(self, clock=None, gs_dev=None):
 		"""draw_boundary + the engine's ordering of the batch, one launch: ((points, normals), Bins)"""
-		bins = self.gv._engine.sample_box_surface_binned(self.boundary_box, self._xb, self._nb, self.seed, 2 * self.rank + 1, self.stepper.clock, tag='pb')
+		bins = self.gv._engine.sample_box_surface_binned(self.boundary_box, self._xb, self._nb, self.seed, 2 * self.rank + 1,
+														 clock if clock is not None else self.stepper.clock, tag='pb', gs_dev=gs_dev)
 		return (self._xb, self._nb), bins
 
 	def restart(self, keep_clock=True):
@@ -193,6 +197,7 @@ class ShardedProjector(advance3d.FusedProjector):
 		if getattr(self, '_drop_clock', False):	# LeapfrogTimestep.reset(): replay from the first sample
 			keep_clock, self._drop_clock = False, False
 		self.stepper.init(self.gv.scalings, keep_clock=keep_clock)
+		self._it = 0
 		self._rebuild()
 		cur = self.ref.velocity_field
 		cur._engine._packed_key = None
@@ -206,8 +211,9 @@ class ShardedProjector(advance3d.FusedProjector):
 	ORDERED_REF_MIN_Q = 8192	# from this batch size the pull-back reference walks its samples in cell order
 
 	def set_samplers(self, data_fn, boundary_fn=None):
-		"""data_fn() -> (Q,3) samples; boundary_fn() -> ((Qb,3) points, (Qb,3) normals), or (that pair, engine.Bins) when the sampler
-		already ordered the batch (sample_box_surface_binned); both must write persistent tensors"""
+		"""data_fn(clock=None) -> (Q,3) samples; boundary_fn(clock=None, gs_dev=None) -> ((Qb,3) points, (Qb,3) normals), or (that pair,
+		engine.Bins) when the sampler already ordered the batch (sample_box_surface_binned, on the sample grid gs_dev); clock: the device
+		counter to draw with (None: the optimiser state's running clock); both must write persistent tensors"""
 		self._samplers = (data_fn, boundary_fn)
 		self._prep = None
 
@@ -217,35 +223,31 @@ class ShardedProjector(advance3d.FusedProjector):
 		main = torch.cuda.current_stream()
 		return (main,) + (self._streams if census is None else (main, main, main))	# the census pass shares one counter: keep it serial
 
-	def _prepare(self, census=None):
-		"""fork: samples + sample hash of the next iteration on the two side streams (not joined: see _join_prepared)"""
+	def _prep_boundary(self, prep, clock=None, gs_dev=None):
+		"""the boundary batch of an iteration, drawn and ordered on the CURRENT stream; gs_dev: the sample grid scale to bin with"""
 		e = self.gv._engine
-		main, s_fwd, s_bnd, s_ref = self._side_streams(census)
-		data_fn, boundary_fn = self._samplers
-		fork = torch.cuda.Event()
-		fork.record(main)
-		prep = {'boundary': None, 'ev': []}
-		if boundary_fn is not None:
-			s_bnd.wait_event(fork)
-			with torch.cuda.stream(s_bnd):
-				res = boundary_fn()
-				if isinstance(res[1], engine.Bins):	# the sampler drew and ordered the batch in one launch
-					prep['boundary'], prep['bins_b'] = res
-				else:
-					prep['boundary'] = res
-					prep['bins_b'] = e.bin_samples(res[0], True, tag='pb')
-				ev = torch.cuda.Event()
-				ev.record(s_bnd)
-				prep['ev'].append(ev)
-		s_fwd.wait_event(fork)
-		with torch.cuda.stream(s_fwd):
-			data = prep['data'] = data_fn()
-			made = torch.cuda.Event()
-			made.record(s_fwd)
-			prep['bins'] = e.bin_samples(data, True, tag='pt')
-			ev = torch.cuda.Event()
-			ev.record(s_fwd)
-			prep['ev'].append(ev)
+		boundary_fn = self._samplers[1]
+		prep['gs_b'] = gs_dev
+		res = boundary_fn(clock=clock, gs_dev=gs_dev)
+		if isinstance(res[1], engine.Bins):	# the sampler drew and ordered the batch in one launch
+			prep['boundary'], prep['bins_b'] = res
+		else:
+			prep['boundary'] = res
+			prep['bins_b'] = e.bin_samples(res[0], True, tag='pb', gs_dev=gs_dev)
+
+	def _prep_training(self, prep, s_ref, clock=None, gs_dev=None):
+		"""the training batch on the CURRENT stream, and its RK4 pull-back reference on s_ref"""
+		e = self.gv._engine
+		data_fn = self._samplers[0]
+		prep['gs_t'] = gs_dev
+		data = prep['data'] = data_fn(clock) if clock is not None else data_fn()
+		cur_stream = torch.cuda.current_stream()
+		made = torch.cuda.Event()
+		made.record(cur_stream)
+		prep['bins'] = e.bin_samples(data, True, tag='pt', gs_dev=gs_dev)
+		ev = torch.cuda.Event()
+		ev.record(cur_stream)
+		prep['ev'].append(ev)
 		# the RK4 pull-back reference reads only the samples and the PREVIOUS field, which does not change during the phase: it
 		# starts as soon as the samples exist and has until the adjoint kernel of the next iteration to finish — beside the hash
 		# builds and the forward passes, off the critical path (it was 14 us of the longer of the two chains)
@@ -261,6 +263,23 @@ class ShardedProjector(advance3d.FusedProjector):
 			self.ref.velocity_field._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=prep['bins'] if ordered else self._ident)
 			prep['ev_ref'] = torch.cuda.Event()
 			prep['ev_ref'].record(s_ref)
+
+	def _prepare(self, census=None, gs_dev=None):
+		"""fork: samples + sample hash of the next iteration on the two side streams (not joined: see _join_prepared)"""
+		main, s_fwd, s_bnd, s_ref = self._side_streams(census)
+		fork = torch.cuda.Event()
+		fork.record(main)
+		prep = {'boundary': None, 'ev': [], 'gs_b': None, 'gs_t': None}
+		if self._samplers[1] is not None:
+			s_bnd.wait_event(fork)
+			with torch.cuda.stream(s_bnd):
+				self._prep_boundary(prep, gs_dev=gs_dev)
+				ev = torch.cuda.Event()
+				ev.record(s_bnd)
+				prep['ev'].append(ev)
+		s_fwd.wait_event(fork)
+		with torch.cuda.stream(s_fwd):
+			self._prep_training(prep, s_ref, gs_dev=gs_dev)
 		self._prep = prep
 
 	def _join_prepared(self, join_ref=True):
@@ -275,33 +294,53 @@ class ShardedProjector(advance3d.FusedProjector):
 			self._prep['ev_ref'] = None
 
 	def prime(self, census=None):
-		"""prologue of a pipelined phase: prepare the samples of its first iteration"""
-		self._prepare(census)
+		"""prologue of a pipelined phase: prepare the samples of its first iteration (binned on the sample grid of iteration 0 when
+		the sample grids run ahead of the hash)"""
+		self._prepare(census, gs_dev=self.sample_grid())
 		self._join_prepared()
 
-	def iterate(self, data=None, boundary=None, census=None, parity=0, join_all=True):
+	def iterate(self, data=None, boundary=None, census=None, join_all=True):
 		"""
 		One optimiser iteration.  Three independent chains run on three streams (fork / join by events, so a captured graph
 		keeps the concurrency): the RK4 pull-back reference (previous field), the forward pass of the current field, and the
 		whole boundary pass; they meet at the adjoint kernel and at the all-reduce.
 		data=None: pipelined — use the samples prepared by prime() / the previous iteration and prepare the next ones;
 		join_all=False leaves the next pull-back reference running into the next call (not for the last call of a captured graph).
+
+		Pipelined with self.ahead (the default): the batches of iteration k + 1 are drawn and ordered WHILE iteration k runs — the
+		boundary batch on its stream right behind the boundary gather, the training batch behind the training gather — instead of
+		behind step k.  They need nothing from step k: the sample counter is the running clock + 1, and the samples are ordered on the
+		sample grid of iteration k + 1 (sample_grid(): left by step k - 1, checked by step k against the hash it builds).  What
+		remains on the cycle is step (+ hash, same launch) -> boundary forward -> boundary adjoint + gather.
 		"""
 		gv, e = self.gv, self.gv._engine
 		cur = self.ref.velocity_field
 		pipelined = data is None
+		it = self._it
+		self._it += 1
+		parity = it & 1
+		sgs_now, sgs_next = self.sample_grid(it), self.sample_grid(it + 1)
 		prep = None
 		if pipelined:
 			prep = self._prep
 			if prep is None or prep['ev']:
 				raise _lib.GsrError('pipelined iterate() needs set_samplers() + prime() first')
 			data, boundary = prep['data'], prep['boundary']
+		ahead = pipelined and self.ahead
 		Q, Qg = data.shape[0], data.shape[0] * self.world
 		acc_w, lp_w, lpb_w = self.views[parity if self.peer else 0]
 		acc_r, lp_r, lpb_r = self.reduced
-		main, s_fwd, s_bnd, _ = self._side_streams(census)
+		main, s_fwd, s_bnd, s_ref = self._side_streams(census)
 		fork = torch.cuda.Event()
 		fork.record(main)
+		nxt = {'boundary': None, 'ev': [], 'gs_b': None, 'gs_t': None}
+		ev_clock = None
+		if ahead:	# the sample counter of the next batches, read before this iteration's step advances the clock
+			s_ref.wait_event(fork)
+			with torch.cuda.stream(s_ref):
+				torch.add(self.stepper.clock, 1., out=self._clock1)
+				ev_clock = torch.cuda.Event()
+				ev_clock.record(s_ref)
 		mask_b = 0
 		srcs_b = []
 		if boundary is not None:
@@ -309,18 +348,25 @@ class ShardedProjector(advance3d.FusedProjector):
 			with torch.cuda.stream(s_bnd):
 				bdata, bnormal = boundary
 				Qb, Qbg = bdata.shape[0], bdata.shape[0] * self.world
-				bins_b = prep['bins_b'] if pipelined else e.bin_samples(bdata, True, tag='b')
+				bins_b = prep['bins_b'] if pipelined else e.bin_samples(bdata, True, tag='b', gs_dev=sgs_now)
 				perm_b, scs_b = bins_b
 				valb = self._tmp('valb', (Qb, 3))
 				e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
 				_, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
-											  {'normals': bnormal}, None, Q_norm=Qbg, tag='acc_b', acc=acc_w, loss_partials=lpb_w)
+											  {'normals': bnormal}, None, Q_norm=Qbg, tag='acc_b', acc=acc_w, loss_partials=lpb_w,
+											  sample_gs=prep['gs_b'] if pipelined else sgs_now)
 				srcs_b = [(lpb_r, self.nblkb, [0., 0., 0., self.boundary_lambda / Qbg, 0., 0., 0., 0.])]
 				if census is not None:
 					e.count_pairs(bdata, census.c, 2, True)
 				done_b = torch.cuda.Event()
 				done_b.record(s_bnd)
-		bins = prep['bins'] if pipelined else e.bin_samples(data, True)
+				if ahead:	# same stream, behind the consumers of the buffers it overwrites
+					s_bnd.wait_event(ev_clock)
+					self._prep_boundary(nxt, clock=self._clock1, gs_dev=sgs_next)
+					ev = torch.cuda.Event()
+					ev.record(s_bnd)
+					nxt['ev'].append(ev)
+		bins = prep['bins'] if pipelined else e.bin_samples(data, True, gs_dev=sgs_now)
 		perm, scs = bins
 		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
 		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
@@ -338,11 +384,20 @@ class ShardedProjector(advance3d.FusedProjector):
 			prep['ev_ref'] = None
 		main.wait_event(done_f)
 		_, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
-									{'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, Q_norm=Qg, acc=acc_w, loss_partials=lp_w)
+									{'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, Q_norm=Qg, acc=acc_w, loss_partials=lp_w,
+									sample_gs=prep['gs_t'] if pipelined else sgs_now)
 		srcs = [(lp_r, self.nblk, [self.w['vor'] / Qg, 0., self.w['div'] / Qg, 0., 0., 0., 0., 0.])]
 		if census is not None:
 			cur._engine.count_pairs(data, census.c, 5, True)
 			e.count_pairs(data, census.c, 2, True)
+		if ahead:	# the training batch of the next iteration: its buffers are free once this gather has read them
+			gathered = torch.cuda.Event()
+			gathered.record(main)
+			s_fwd.wait_event(gathered)
+			s_fwd.wait_event(ev_clock)
+			with torch.cuda.stream(s_fwd):
+				self._prep_training(nxt, s_ref, clock=self._clock1, gs_dev=sgs_next)
+			main.wait_event(ev_clock)	# (long done) the step below advances the clock the counter was read from
 		if boundary is not None:
 			main.wait_event(done_b)
 			mask |= mask_b
@@ -352,21 +407,21 @@ class ShardedProjector(advance3d.FusedProjector):
 		elif self.world > 1:
 			torch.distributed.all_reduce(self.flat)
 		params = [p.detach() for p in gv._params()]
-		if not pipelined:
-			self.stepper.step(params, acc_r, mask, loss_srcs=srcs, rebuild=True)	# update + hash + packed records
+		if not pipelined or ahead:
+			self.stepper.step(params, acc_r, mask, loss_srcs=srcs, rebuild=True)	# update + hash + packed records (one launch for N <= 1024)
+			if ahead:
+				self._prep = nxt
+				self._join_prepared(join_ref=join_all)
 			return
 		self.stepper.step(params, acc_r, mask, loss_srcs=srcs)	# update; leaves iteration counter and grid_scale of the next iteration
-		self._prepare(census)	# side streams: next samples + their hash ...
+		self._prepare(census, gs_dev=sgs_next)	# side streams: next samples + their hash ...
 		self._rebuild()	# ... beside the Gaussian hash + packed records on this one
 		self._join_prepared(join_ref=join_all)
-
-
 
 	# ---- a phase: begin(), run_iterations() as often as needed, finish() -----------------------------------------------------------
 	def begin(self, census=None):
 		"""prepare the samples of the phase's first iteration"""
 		self.prime(census)
-		self._parity = 0
 
 	def run_iterations(self, n, census=None, use_graph=True):
 		"""
@@ -377,14 +432,17 @@ class ShardedProjector(advance3d.FusedProjector):
 		"""
 		unit = int(os.environ.get('GSR_GRAPH_UNIT', '0'))
 		if unit <= 0:
-			unit = self.unit or next(u for u in (10, 4, 2, 1) if n % u == 0 and not (self.peer and u % 2))
+			# whole pairs per captured unit: the exchange buffers and the sample grids alternate with the iteration's parity
+			unit = self.unit or next((u for u in (10, 4, 2) if n % u == 0), 1)
 		if self.peer and (unit % 2 or n % 2):
 			raise ValueError('with the peer-memory exchange iterations run in pairs')
+		if unit % 2:
+			use_graph = False	# an odd number of iterations: no static parity to capture, run them one by one
 		e = self.gv._engine
 
 		def body(k_iters, cen=None):
 			for k in range(k_iters):
-				self.iterate(None, None, cen, parity=(self._parity + k) & 1, join_all=(k == k_iters - 1))
+				self.iterate(None, None, cen, join_all=(k == k_iters - 1))
 
 		done = 0
 		graphed = use_graph and census is None
@@ -410,13 +468,13 @@ class ShardedProjector(advance3d.FusedProjector):
 				k = min(unit, n - done)
 				body(k, census)
 				done += k
-				self._parity = (self._parity + k) & 1
 
 	def evaluate_global(self, data, total=None, probe=None, census=None):
 		"""the test losses over the WHOLE lattice: `data` is this rank's share, `total` the number of points of all ranks"""
 		Q = data.shape[0]
 		if self.peer:
 			self.peer.check()	# (this call synchronises anyway) a lost peer is reported within check_iter iterations, not at the end of the phase
+		self.check_sample_grid()
 		sums = self.evaluate(data, probe=probe) * Q
 		if census is not None:
 			census.count(self.ref.velocity_field._engine, data, 5, lattice=True)

@@ -173,6 +173,9 @@ typedef struct {
 	const float *ref_vor;	/* 3D (Q,3); 2D (Q) */
 	const float *ref_hel;	/* 3D (Q) */
 	const int32_t *stop_gradient;	/* (N) int32 or NULL */
+	const float *sample_grid_scale_dev;	/* optional DEVICE scalar: the grid scale `sample_cell_start` was built with (gsr_bin_samples with a
+				 * descriptor pointing at it) when that is not the hash's own — it must be >= the hash's grid_scale: a Gaussian then
+				 * still finds every sample of its support in the 3^D sample cells around its own */
 	float *loss_partials;	/* optional out, device (gsr_loss_blocks(Q), 8): per-block partial sums of the sample losses,
 				 * reduced deterministically by gsr_step / gsr_sample_losses.  Slots (sums over the samples):
 				 * 0 mean_k|omega-omega_ref| (3D) or |omega-omega_ref| (2D)   1 |u.omega - hel_ref|   2 (div u)^2
@@ -225,6 +228,12 @@ typedef struct {
 	double min_grid_scale;
 	double grid_scale_tau0;	/* the constant grid_scale used when tau == 0 (3D/GSR.py:251) */
 	int32_t keep_clock;	/* gsr_step_init: leave GSR_ST_CLOCK as it is (the state has been initialised before) */
+	float *sample_gs_slots;	/* optional DEVICE float[2]: a SAMPLE grid scale per iteration parity, one iteration ahead of the hash.  Step k of a
+				 * phase (k = 0, 1, ...) writes slot k & 1 = sample_gs_margin x the grid_scale it leaves — the scale the caller bins
+				 * the samples of iteration k + 2 with while iteration k + 1 still runs (gsr_loss_cfg.sample_grid_scale_dev tells the
+				 * gather) — after checking that slot (k + 1) & 1, which the samples of iteration k + 1 were binned with, still covers
+				 * that grid_scale (else state[GSR_ST_SGS_ERR] = 1, sticky).  gsr_step_init sets both slots. */
+	float sample_gs_margin;	/* > 1: bound on the growth of grid_scale over one step (Adam moves a log-radius by < 3.2 lr) */
 	float *grid_scale_out;	/* optional DEVICE scalar that also receives the next grid_scale: the hash descriptor's grid_scale_dev
 				 * of the field being optimised, so that every kernel launched on that field — also from a CUDA
 				 * graph captured earlier — bins with the current value */
@@ -253,7 +262,8 @@ typedef struct {
 #define GSR_ST_L_VALREG 12
 #define GSR_ST_L_DPOS 13
 #define GSR_ST_LOSS_SRC 14	/* [14..21] sum over sources of the raw loss slots divided by nothing (plain sums) */
-#define GSR_ST_CLOCK 22		/* steps taken since the state was created: like GSR_ST_T, but gsr_step_init keeps it when
+#define GSR_ST_CLOCK 22
+#define GSR_ST_SGS_ERR 23	/* 1: grid_scale outgrew the sample grid scale of a pre-binned batch (sample_gs_slots) */		/* steps taken since the state was created: like GSR_ST_T, but gsr_step_init keeps it when
 				 * cfg->keep_clock != 0 — the iteration number for the sample generators, so that successive
 				 * optimisation phases (time steps) draw fresh samples (the reference draws from one running RNG) */
 size_t gsr_step_state_floats(int D, int64_t N);
