@@ -461,6 +461,7 @@ def timed_steps(ts, args, barrier, dev, world, dist, host_params=None, host_out=
 	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 	e0.record()
 	for _ in range(args.steps):
+		t_host = time.perf_counter()
 		if host_params is None:
 			ts.reset()
 			ts.step()
@@ -472,6 +473,8 @@ def timed_steps(ts, args, barrier, dev, world, dist, host_params=None, host_out=
 			host_fields[0].copy_(vor, non_blocking=True)
 			host_fields[1].copy_(div, non_blocking=True)
 			torch.cuda.synchronize()	# the caller owns the results only once they are on the host
+			if os.environ.get('GSR_BENCH_TRACE'):
+				print(f'[e2e step] {1e3 * (time.perf_counter() - t_host):.1f} ms host wall', file=sys.stderr, flush=True)
 	e1.record()
 	barrier()
 	t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
