@@ -157,7 +157,10 @@ __device__ __forceinline__ void step_reduce_tail(const gsr_step_cfg &cfg, int N,
 	const double t = (double)st[GSR_ST_T] + 1.;
 	st[GSR_ST_T] = (float)t;
 	st[GSR_ST_CLOCK] += 1.f;
-	const double bc1 = 1. - pow((double)cfg.beta1, t), bc2 = 1. - pow((double)cfg.beta2, t);
+	const double p1 = pow((double)cfg.beta1, t), p2 = pow((double)cfg.beta2, t);
+	const double bc1 = 1. - p1, bc2 = 1. - p2;
+	reinterpret_cast<double *>(st + GSR_ST_BPOW)[0] = p1;	// (the four-lane step advances these by multiplication instead of calling pow)
+	reinterpret_cast<double *>(st + GSR_ST_BPOW)[1] = p2;
 	for (int g = 0; g < 4; g++) {
 		st[C_LRUSED + g] = st[GSR_ST_LR + g];
 		st[C_STEP + g] = (float)((double)st[GSR_ST_LR + g] / bc1);
@@ -399,7 +402,9 @@ __device__ __forceinline__ void step_reduce_tail_split(const gsr_step_cfg &cfg, 
 		*decay_sm = decay;
 	} else if (w == 2 && lane < 2) {
 		const double t = (double)st[GSR_ST_T] + 1.;
-		bc_sm[lane] = 1. - pow((double)(lane ? cfg.beta2 : cfg.beta1), t);
+		const double pw = pow((double)(lane ? cfg.beta2 : cfg.beta1), t);
+		bc_sm[lane] = 1. - pw;
+		reinterpret_cast<double *>(st + GSR_ST_BPOW)[lane] = pw;
 	}
 	__syncthreads();
 	if (tid < 4) {
@@ -428,7 +433,7 @@ step_cluster_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__r
 	namespace cg = cooperative_groups;
 	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR, P = Dim<D>::P;
 	cg::cluster_group cluster = cg::this_cluster();
-	__shared__ float cst[GSR_STATE_SCALARS];	// the state scalars: read once, advanced by the tail, written back by CTA 0
+	__shared__ __align__(8) float cst[GSR_STATE_SCALARS];	// the state scalars: read once, advanced by the tail, written back by CTA 0
 	__shared__ float wpart[SC_MAX_THREADS / 32][S_COUNT];
 	__shared__ float part[S_COUNT];	// this CTA's partial sums (read by every CTA of the cluster)
 	__shared__ double Tsm[S_COUNT + 8];
@@ -661,6 +666,10 @@ __global__ void init_state_kernel(float *st, size_t n_moments, gsr_step_cfg cfg)
 		if (i == GSR_ST_BEST || i == GSR_ST_MIN_S) v = __int_as_float(0x7f800000);
 		if (i >= GSR_ST_LR && i < GSR_ST_LR + 4) v = cfg.lr[i - GSR_ST_LR];
 		if (i == GSR_ST_CLOCK && cfg.keep_clock) return;	// the sample clock runs on across optimisation phases
+		if (i >= GSR_ST_BPOW && i < GSR_ST_BPOW + 4) {	// beta1^0 = beta2^0 = 1 (doubles)
+			if (!(i & 1)) reinterpret_cast<double *>(st + i)[0] = 1.;
+			return;
+		}
 		st[i] = v;
 	}
 }
@@ -671,6 +680,90 @@ __global__ void init_state_kernel(float *st, size_t n_moments, gsr_step_cfg cfg)
 // Here a Gaussian is a group of four consecutive lanes: lane s of the group runs the chain rule of ONE set (vorticity, divergence,
 // direct, boundary) and leaves its 13 (7) parameter gradients in shared memory; then lane s owns parameters s, s + 4, s + 8 (, 12)
 // for the PCGrad dots, the regulariser gradients and Adam.  Same formulas; the float block sums are grouped differently.
+#ifdef GSR_STEP_TIMING
+__device__ unsigned long long g_step_stamps[16];
+__device__ __forceinline__ unsigned long long gtime()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+#define STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_step_stamps[k] = gtime(); } while (0)
+#else
+#define STAMP(k) do { } while (0)
+#endif
+
+// The reduction tail of the four-lane step in two pieces.  EARLY (needs only the step count and the learning rates, so it runs while
+// the loads of the step are in flight): Adam's bias corrections (two double pow) and the per-group step sizes lr / bc1, 1 / sqrt(bc2).
+// LATE (once the global sums T are known): PCGrad coefficients and the volume moments — all Adam waits for — beside the loss total,
+// the scheduler decision and the learning-rate update, which only the next step needs.  Same formulas as step_reduce_tail.
+// early_sm: [0..3] lr / bc1 per group, [4..7] the learning rates in use, [8] 1 / sqrt(bc2)
+__device__ __forceinline__ void step_tail_early(const gsr_step_cfg &cfg, const float *__restrict__ st_global, int lane, float *early_sm)
+{
+	double pw = 1.;	// beta^t by one multiplication per step (pow() in double is ~2 us of one thread's latency, which every warp would wait for)
+	if (lane < 2) pw = reinterpret_cast<const double *>(st_global + GSR_ST_BPOW)[lane] * (double)(lane ? cfg.beta2 : cfg.beta1);
+	const double p1 = __shfl_sync(0xffffffffu, pw, 0), p2 = __shfl_sync(0xffffffffu, pw, 1);
+	const double bc1 = 1. - p1, bc2 = 1. - p2;
+	if (lane == 0) { reinterpret_cast<double *>(early_sm + 12)[0] = p1; reinterpret_cast<double *>(early_sm + 12)[1] = p2; }
+	if (lane < 4) {
+		const float lr = st_global[GSR_ST_LR + lane];
+		early_sm[lane] = (float)((double)lr / bc1);
+		early_sm[4 + lane] = lr;
+	} else if (lane == 4) {
+		early_sm[8] = (float)(1. / sqrt(bc2));
+	}
+}
+
+template <int D>
+__device__ __forceinline__ void step_tail_late(const gsr_step_cfg &cfg, int N, const double *T, float *st, const float *early_sm)
+{
+	const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+	if (w == 0 && lane < 4) {
+		const int g = lane;
+		float a1 = 1.f, a2 = 1.f;
+		if (cfg.pcgrad && T[S_DOT + g] < 0.) {
+			a1 = (float)(1. - T[S_DOT + g] / T[S_N1 + g]);
+			a2 = (float)(1. - T[S_DOT + g] / T[S_N2 + g]);
+		}
+		st[C_A1 + g] = a1;
+		st[C_A2 + g] = a2;
+	} else if (w == 1 && lane == 0) {
+		const double n = (double)N;
+		const double meanV = T[S_V] / n, meanR2 = T[S_V2] / n / (meanV * meanV);
+		st[C_MEANV] = (float)meanV;
+		st[C_MEANR2] = (float)meanR2;
+		const double L_aniso = T[S_ANISO] / n, L_vol = meanR2 - 1., L_valreg = T[S_ABSV] / (n * D), L_dpos = T[S_DPOS] / (n * D);
+		double loss_src = 0.;
+		for (int k = 0; k < 8; k++) loss_src += T[S_COUNT + k];
+		const double loss_tot = loss_src + cfg.w_aniso * L_aniso + cfg.w_vol * L_vol + cfg.w_valreg * L_valreg + cfg.w_dpos * L_dpos;
+		st[GSR_ST_LOSS_TOT] = (float)loss_tot;
+		st[GSR_ST_L_ANISO] = (float)L_aniso;
+		st[GSR_ST_L_VOL] = (float)L_vol;
+		st[GSR_ST_L_VALREG] = (float)L_valreg;
+		st[GSR_ST_L_DPOS] = (float)L_dpos;
+		const float cur = (float)loss_tot;
+		float best = st[GSR_ST_BEST], bad = st[GSR_ST_BAD];
+		if (cur < best * (1.f - cfg.sched_threshold)) { best = cur; bad = 0.f; } else bad += 1.f;
+		const int decay = bad > (float)cfg.sched_patience;
+		if (decay) bad = 0.f;
+		st[GSR_ST_BEST] = best;
+		st[GSR_ST_BAD] = bad;
+		for (int g = 0; g < 4; g++) {	// the step sizes of THIS step were formed from the rates before this update (early_sm)
+			const float lr = early_sm[4 + g];
+			const float new_lr = fmaxf(lr * cfg.sched_factor, cfg.sched_min_lr);
+			if (decay && lr - new_lr > cfg.sched_eps) st[GSR_ST_LR + g] = new_lr;
+		}
+	} else if (w == 2) {
+		if (lane < 4) { st[C_STEP + lane] = early_sm[lane]; st[C_LRUSED + lane] = early_sm[4 + lane]; }
+		else if (lane == 4) st[C_BC2] = early_sm[8];
+		else if (lane == 5) { st[GSR_ST_T] = (float)((double)st[GSR_ST_T] + 1.); st[GSR_ST_CLOCK] += 1.f; }
+		else if (lane == 6) {
+			reinterpret_cast<double *>(st + GSR_ST_BPOW)[0] = reinterpret_cast<const double *>(early_sm + 12)[0];
+			reinterpret_cast<double *>(st + GSR_ST_BPOW)[1] = reinterpret_cast<const double *>(early_sm + 12)[1];
+		}
+	}
+}
+
 constexpr int SC4_G = 4;
 constexpr int SC4_MAX_THREADS = 512;
 constexpr int SC4_MAX_N = SC_CTAS * SC4_MAX_THREADS / SC4_G;
@@ -700,7 +793,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 	namespace cg = cooperative_groups;
 	constexpr int AF = Dim<D>::AF, NR = Dim<D>::NR, P = Dim<D>::P, G = SC4_G, KPL = (P + G - 1) / G;
 	cg::cluster_group cluster = cg::this_cluster();
-	__shared__ float cst[GSR_STATE_SCALARS];
+	__shared__ __align__(8) float cst[GSR_STATE_SCALARS];
 	__shared__ float wpart[SC4_MAX_THREADS / 32][S_COUNT];
 	__shared__ float part[S_COUNT];
 	__shared__ double Tsm[S_COUNT + 8];
@@ -715,11 +808,13 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 	__shared__ uint32_t hkey[HASH ? SC4_MAX_THREADS / G : 1];	// key of every Gaussian of this CTA
 	__shared__ uint32_t hwarp[32];
 	__shared__ float gs_sm;
+	__shared__ __align__(8) float early_sm[16];
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
 	const int rank = (int)cluster.block_rank();
 	const int gl = tid / G, sub = tid % G;
 	const int i = rank * (blockDim.x / G) + gl;
 	const bool on = i < N;
+	STAMP(0);
 	for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x) cst[k] = st[k];
 	if (HASH) {
 		for (int c = tid; c <= H.g.ncell; c += blockDim.x) hist[c] = 0;
@@ -760,23 +855,31 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 			if (k < D && pos_org) po[j] = pos_org[(size_t)D * i + k];
 		}
 	}
-	if (w == nw - 1 && lane < 8) {	// weighted sums of the sample-loss partials (blocks in order, double); loads four deep
-		const int k = lane;
-		double s = 0.;
-		for (int q = 0; q < ls.n; q++) {
-			double t = 0.;
+	if (w == nw - 1) {	// weighted sums of the sample-loss partials: lanes 8 q + k sum slot k of source q (blocks in order, double,
+		const int k = lane & 7, q = lane >> 3;	// loads eight deep); then the sources in order, as step_reduce_tail's callers do
+		double t = 0.;
+		if (q < ls.n) {
 			const float *pt = ls.partials[q] + k;
 			const int nb = ls.nblocks[q];
 			int b = 0;
-			for (; b + 4 <= nb; b += 4) {
-				const float v0 = pt[(size_t)b * 8], v1 = pt[(size_t)(b + 1) * 8], v2 = pt[(size_t)(b + 2) * 8], v3 = pt[(size_t)(b + 3) * 8];
-				t += (double)v0; t += (double)v1; t += (double)v2; t += (double)v3;
+			for (; b + 8 <= nb; b += 8) {
+				float v[8];
+#pragma unroll
+				for (int u = 0; u < 8; u++) v[u] = pt[(size_t)(b + u) * 8];
+#pragma unroll
+				for (int u = 0; u < 8; u++) t += (double)v[u];
 			}
 			for (; b < nb; b++) t += (double)pt[(size_t)b * 8];
-			s += (double)ls.w[q][k] * t;
 		}
-		Tsm[S_COUNT + k] = s;
+		double s = 0.;
+#pragma unroll
+		for (int qq = 0; qq < 3; qq++) {
+			const double tq = __shfl_sync(0xffffffffu, t, 8 * qq + k);
+			if (qq < ls.n) s += (double)ls.w[qq][k] * tq;
+		}
+		if (lane < 8) Tsm[S_COUNT + k] = s;
 	}
+	if (w == (nw >= 2 ? nw - 2 : 0)) step_tail_early(cfg, st, lane, early_sm);
 	// ---- chain rule of this lane's set ---------------------------------------------------------------------------------------
 	{
 		float g[P];
@@ -800,6 +903,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 #pragma unroll
 		for (int k = 0; k < P; k++) Tg[gl][sub][k] = g[k];
 	}
+	STAMP(1);
 	__syncwarp();
 	// ---- this lane's parameters: PCGrad dots, regulariser moments ----------------------------------------------------------------
 	float S[S_COUNT];
@@ -862,7 +966,9 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 		for (int ww = 0; ww < nw; ww++) t += wpart[ww][tid];
 		part[tid] = t;
 	}
+	STAMP(2);
 	cluster.sync();
+	STAMP(3);
 	if (tid < S_COUNT) {	// CTAs in order, double: the same T in every CTA
 		double t = 0.;
 #pragma unroll
@@ -871,7 +977,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 	}
 	__syncthreads();
 	if (nw >= 3) {
-		step_reduce_tail_split<D>(cfg, N, Tsm, cst, bc_sm, &decay_sm);
+		step_tail_late<D>(cfg, N, Tsm, cst, early_sm);
 	} else if (tid == 0) {
 		double T[S_COUNT + 8];
 #pragma unroll
@@ -879,9 +985,10 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 		step_reduce_tail<D>(cfg, N, T, cst);
 	}
 	__syncthreads();
+	STAMP(4);
 	// ---- projected gradient + regulariser gradients + Adam on this lane's parameters ----------------------------------------
 	float smin = __int_as_float(0x7f800000);
-	const float bc2 = cst[C_BC2];
+	const float bc2 = early_sm[8];
 	const float rV = V / cst[C_MEANV];
 	const float cv = -cfg.w_vol * 2.f / (float)N * rV * (rV - cst[C_MEANR2]);
 	const float ca = (rho >= cfg.aniso_ratio && kmin != kmax) ? cfg.w_aniso * rho / (float)N : 0.f;
@@ -903,7 +1010,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 			if (grp == 0 && pos_org && cfg.w_dpos != 0.f) g += cfg.w_dpos * 2.f / (float)(N * D) * (prm[j] - po[j]);
 			const float mk = mo[j] + (g - mo[j]) * (1.f - cfg.beta1);
 			const float vk = vo[j] * cfg.beta2 + (1.f - cfg.beta2) * g * g;
-			const float pk = prm[j] - cst[C_STEP + grp] * (mk / (sqrtf(vk) * bc2 + cfg.eps));
+			const float pk = prm[j] - early_sm[grp] * (mk / (sqrtf(vk) * bc2 + cfg.eps));
 			m[k] = mk;
 			vv[k] = vk;
 			*pp[j] = pk;
@@ -911,6 +1018,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 			if (grp == 1) smin = fminf(smin, pk);
 		}
 	}
+	STAMP(5);
 #pragma unroll
 	for (int o = 16; o; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
 	if (lane == 0) wmin[w] = smin;
@@ -921,6 +1029,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 		bmin = mn;
 	}
 	cluster.sync();
+	STAMP(6);
 	if (rank == 0) {
 		for (int k = tid; k < GSR_STATE_SCALARS; k += blockDim.x)
 			if (k != GSR_ST_GRID_SCALE && k != GSR_ST_MIN_S && k != GSR_ST_SGS_ERR) st[k] = cst[k];
@@ -949,7 +1058,9 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 			}
 			hkey[gl] = on ? key : 0xffffffffu;	// (not a Gaussian: matches no key)
 		}
+		STAMP(7);
 		cluster.sync();	// every CTA's histogram is complete
+		STAMP(8);
 		for (int c = tid; c <= ncell; c += blockDim.x) {
 			uint32_t tot = 0, base = 0;
 #pragma unroll
@@ -995,6 +1106,7 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 			}
 		}
 		__syncthreads();
+		STAMP(9);
 		// slot of this Gaussian: its four lanes count the lower ids of the CTA with the same key, a quarter of the range each
 		const int l0 = lane & ~(G - 1);
 		key = __shfl_sync(0xffffffffu, key, l0);
@@ -1027,7 +1139,9 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 			}
 		}
 	}
+	STAMP(10);
 	cluster.sync();	// no CTA may exit while another still reads its shared memory
+	STAMP(11);
 }
 
 __global__ void min_into_kernel(const float *__restrict__ a, size_t n, float *out)
@@ -1042,6 +1156,13 @@ __global__ void min_into_kernel(const float *__restrict__ a, size_t n, float *ou
 }  // namespace gsr
 
 using namespace gsr;
+
+#ifdef GSR_STEP_TIMING
+extern "C" int gsr_debug_step_stamps(unsigned long long *out)
+{
+	return (int)cudaMemcpyFromSymbol(out, g_step_stamps, sizeof(unsigned long long) * 16);
+}
+#endif
 
 extern "C" size_t gsr_step_state_floats(int D, int64_t N) { return GSR_STATE_SCALARS + 2 * (size_t)(D == 3 ? 13 : 7) * (size_t)N; }
 

@@ -262,6 +262,7 @@ typedef struct {
 #define GSR_ST_L_VALREG 12
 #define GSR_ST_L_DPOS 13
 #define GSR_ST_LOSS_SRC 14	/* [14..21] sum over sources of the raw loss slots divided by nothing (plain sums) */
+#define GSR_ST_BPOW 48		/* [48..51] two DOUBLES (8-byte aligned): beta1^t, beta2^t of Adam's bias corrections, advanced by one multiplication per step */
 #define GSR_ST_CLOCK 22
 #define GSR_ST_SGS_ERR 23	/* 1: grid_scale outgrew the sample grid scale of a pre-binned batch (sample_gs_slots) */		/* steps taken since the state was created: like GSR_ST_T, but gsr_step_init keeps it when
 				 * cfg->keep_clock != 0 — the iteration number for the sample generators, so that successive
