@@ -170,7 +170,7 @@ constexpr int RKS_P = 4;
 constexpr int RKS_STATE = 24;	// x0 3 | vs 3 | S 9 | A 9
 
 template <int MODE>
-__global__ void __launch_bounds__(TL_TILE / RKS_P, 3) rk4_tiled3s_kernel(TiledArgs a, float dt, float *__restrict__ goal_pos, float *__restrict__ deformation,
+__global__ void __launch_bounds__(TL_TILE / RKS_P, 4) rk4_tiled3s_kernel(TiledArgs a, float dt, float *__restrict__ goal_pos, float *__restrict__ deformation,
 									  float *__restrict__ goal_val, float *__restrict__ goal_grad, float *__restrict__ ref_vor,
 									  float *__restrict__ ref_hel)
 {
@@ -291,6 +291,7 @@ extern int g_gather_cta_max_n;	// backward.cu
 int g_tiled_min_q = 1 << 17;
 int g_tiled_cap = 512;
 int g_fw_p4_min_spc = 0;	// samples per cell above which the forward kernel takes 4 points per thread (else 2)
+int g_rk4s_cap = 128;	// staging capacity of rk4_tiled3s_kernel (GSR_TUNE_RK4S_CAP)
 int g_rk4_smem_state = 1;	// 1: RK4 with the deformation chain keeps its state in shared memory (4 points / thread)
 
 static size_t tiled_smem(int cap) { return (size_t)cap * 48; }
@@ -337,6 +338,7 @@ extern "C" int gsr_set_tuning(int key, int value)
 	case GSR_TUNE_RK4_SMEM_STATE: g_rk4_smem_state = value; return GSR_OK;
 	case GSR_TUNE_FORCE_RADIX: g_force_radix = value; return GSR_OK;
 	case GSR_TUNE_STEP_SMALL_N: g_step_small_n = value; return GSR_OK;
+	case GSR_TUNE_RK4S_CAP: g_rk4s_cap = value; return GSR_OK;
 	case GSR_TUNE_STEP_LANES4: g_step_lanes4 = value; return GSR_OK;
 	case GSR_TUNE_STEP_FUSED_HASH: g_step_fused_hash = value; return GSR_OK;
 	case GSR_TUNE_GATHER_CTA_MAX_N: g_gather_cta_max_n = value; return GSR_OK;
@@ -411,6 +413,10 @@ int launch_rk4_tiled3(int mode, const EvalParams &P, const int32_t *cell_start, 
 	// many samples per cell: warps of 128 points are still compact, and 4 points per thread halve the per-candidate overhead;
 	// fewer: 64-point warps cull better
 	if (mode != 0 && g_rk4_smem_state && (double)Q >= 1024. * (double)P.g.ncell) {
+		// four CTAs per SM (launch bounds: 128 registers) instead of three: the integrator state takes 48 KB of shared memory per CTA,
+		// so the staging area shrinks to 128 records (what does not fit is read through L1) — measured on the 128^3 lattice at S1:
+		// 1.216 -> 1.124 ms; with 128 registers and the full staging area (three CTAs) 1.280 ms
+		a.cap = min(a.cap, g_rk4s_cap);
 		const size_t sm = tiled_smem(a.cap) + sizeof(float) * RKS_STATE * RKS_P * (TL_TILE / RKS_P);
 		cudaError_t e = (mode == 1) ? cudaFuncSetAttribute(rk4_tiled3s_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
 					    : cudaFuncSetAttribute(rk4_tiled3s_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
