@@ -38,8 +38,10 @@ constexpr int DN_P = 4;
 
 // CTA = 8 x 8 x 8 voxels, 4 warps; warp w owns the 4 x 4 x 8 block at (4 (w / 2), 4 (w % 2), 0); slot p of lane l is voxel
 // v = 32 p + l of that block, (v / 32, (v / 8) % 4, v % 8).  NF density fields are advected through the same back-trace.
-template <int NF, bool COUNT = false>
-__global__ void __launch_bounds__(128, 4) advect_density_kernel(TiledArgs a, LatticeArgs L, float dt, const float *__restrict__ f0, const float *__restrict__ f1,
+// 80 registers -> six CTAs (24 warps) per SM: the evaluator's dependent chains want warps to hide behind (measured at 512^3:
+// 53.1 ms with four CTAs / 128 registers, 49.6 with five, 46.2 with six, 45.7 with eight / 64 registers and spills)
+template <int NF, bool COUNT = false, int OCC = 6>
+__global__ void __launch_bounds__(128, OCC) advect_density_kernel(TiledArgs a, LatticeArgs L, float dt, const float *__restrict__ f0, const float *__restrict__ f1,
 								  float *__restrict__ o0, float *__restrict__ o1)
 {
 	__shared__ TileSh sh;
