@@ -292,6 +292,7 @@ extern int g_gather_cta_max_n;	// backward.cu
 int g_tiled_min_q = 1 << 17;
 int g_tiled_cap = 512;
 int g_fw_p4_min_spc = 0;	// samples per cell above which the forward kernel takes 4 points per thread (else 2)
+int g_rk4s_min_spc = 1024;	// samples per hash cell from which the shared-memory-state RK4 kernel is used (GSR_TUNE_RK4S_MIN_SPC)
 int g_rk4s_cap = 128;	// staging capacity of rk4_tiled3s_kernel (GSR_TUNE_RK4S_CAP)
 int g_rk4_smem_state = 1;	// 1: RK4 with the deformation chain keeps its state in shared memory (4 points / thread)
 
@@ -340,6 +341,7 @@ extern "C" int gsr_set_tuning(int key, int value)
 	case GSR_TUNE_FORCE_RADIX: g_force_radix = value; return GSR_OK;
 	case GSR_TUNE_STEP_SMALL_N: g_step_small_n = value; return GSR_OK;
 	case GSR_TUNE_RK4S_CAP: g_rk4s_cap = value; return GSR_OK;
+	case GSR_TUNE_RK4S_MIN_SPC: g_rk4s_min_spc = value; return GSR_OK;
 	case GSR_TUNE_STEP_LANES4: g_step_lanes4 = value; return GSR_OK;
 	case GSR_TUNE_STEP_FUSED_HASH: g_step_fused_hash = value; return GSR_OK;
 	case GSR_TUNE_GATHER_CTA_MAX_N: g_gather_cta_max_n = value; return GSR_OK;
@@ -413,7 +415,7 @@ int launch_rk4_tiled3(int mode, const EvalParams &P, const int32_t *cell_start, 
 	const int blocks = (int)tile_slots(P.g, Q);
 	// many samples per cell: warps of 128 points are still compact, and 4 points per thread halve the per-candidate overhead;
 	// fewer: 64-point warps cull better
-	if (mode != 0 && g_rk4_smem_state && (double)Q >= 1024. * (double)P.g.ncell) {
+	if (mode != 0 && g_rk4_smem_state && (double)Q >= (double)g_rk4s_min_spc * (double)P.g.ncell) {
 		// four CTAs per SM (launch bounds: 128 registers) instead of three: the integrator state takes 48 KB of shared memory per CTA,
 		// so the staging area shrinks to 128 records (what does not fit is read through L1) — measured on the 128^3 lattice at S1:
 		// 1.216 -> 1.124 ms; with 128 registers and the full staging area (three CTAs) 1.280 ms

@@ -100,6 +100,7 @@ int gsr_build_tiles(const gsr_grid_desc *g, const int32_t *sample_cell_start, in
 #define GSR_TUNE_STEP_LANES4 9	/* 1 (default): the cluster step gives four lanes to a Gaussian when N <= 1024; 0: one thread per Gaussian */
 #define GSR_TUNE_STEP_FUSED_HASH 10	/* 1 (default): gsr_step_rebuild's four-lane cluster step also rebuilds the hash and the packed records (<= 1024 cells); 0: second launch */
 #define GSR_TUNE_RK4S_CAP 11	/* staging capacity (Gaussians) of the RK4 pull-back kernel that keeps its integrator state in shared memory (default 128: four CTAs per SM) */
+#define GSR_TUNE_RK4S_MIN_SPC 12	/* samples per hash cell from which the RK4 pull-back uses the shared-memory-state kernel (4 points per thread), else 2 points per thread in registers */
 #define GSR_TUNE_GATHER_CTA_MAX_N 7	/* 3D backward gather: up to this many Gaussians, with >= 4 samples per Gaussian, one CTA per Gaussian (default 4096; 0: never) */
 #define GSR_TUNE_LANES8_MIN_N 8	/* items (points / Gaussians) from which the latency-shape kernels give 8 lanes to an item instead of a warp (default 16384) */
 #define GSR_TUNE_RK4_SMEM_STATE 3	/* 1 (default): tiled RK4 keeps the integrator state in shared memory, 4 points per thread; 0: registers, 2 per thread */
