@@ -69,11 +69,17 @@ __global__ void __launch_bounds__(XR_THREADS) xrank_sum_kernel(XrankArgs a, size
 			out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 			continue;
 		}
-		float4 s = ld_peer4(a.peer[0] + i);
-		for (int r = 1; r < a.world; r++) {
-			const float4 v = ld_peer4(a.peer[r] + i);
-			s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-		}
+		// every peer's value is requested before the first is used: a peer-memory load is a ~2 us round trip, and a loop of
+		// {load, add} would pay it once per rank (the adds wait for their operands in order) — measured as 13.7 us per iteration
+		// at 8 ranks
+		float4 v[XR_MAX_WORLD];
+#pragma unroll
+		for (int r = 0; r < XR_MAX_WORLD; r++)
+			if (r < a.world) v[r] = ld_peer4(a.peer[r] + i);
+		float4 s = v[0];
+#pragma unroll
+		for (int r = 1; r < XR_MAX_WORLD; r++)
+			if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
 		out[i] = s;
 	}
 }
