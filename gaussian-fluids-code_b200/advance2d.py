@@ -65,7 +65,11 @@ def clone_velocity_field(res, velocity_field, data_generator, test_data_generato
 	from . import reseed
 	with torch.no_grad():
 		for nm in ('positions', 'scalings', 'rotations', 'values'):
-			setattr(res, nm, getattr(velocity_field, nm).detach().clone())
+			src, dst = getattr(velocity_field, nm).detach(), getattr(res, nm)
+			if dst.shape == src.shape and dst.device == src.device:
+				dst.copy_(src)	# same storage: a project() graph captured on these tensors stays valid for the next frame
+			else:
+				setattr(res, nm, src.clone())
 		res.N = res.positions.shape[0]
 		stop_gradient, n_split = reseed.split_all(res, 2, normals=[normals] if normals is not None else None, seed=seed, rounds=1)
 	res.unfreeze()
@@ -110,11 +114,16 @@ def advect_covector_field(covector_field, velocity_field, dt, advection_scheme='
 			raise NotImplementedError
 		valid = ((covector_field.x_min <= new_positions[:, 0]) & (new_positions[:, 0] <= covector_field.x_max)
 				 & (covector_field.y_min <= new_positions[:, 1]) & (new_positions[:, 1] <= covector_field.y_max))
-		params = [new_positions[valid].clone(), covector_field.scalings.detach()[valid].clone(), covector_field.rotations.detach()[valid].clone(),
-				  covector_field.values.detach()[valid].clone()]
-	for p in params:
-		p.requires_grad_()
-	covector_field.positions, covector_field.scalings, covector_field.rotations, covector_field.values = params
+		if bool(valid.all()):	# nobody left the domain (the usual frame): move in place, the tensors — and graphs captured on them — stay
+			covector_field.positions.detach().copy_(new_positions)
+			params = None
+		else:
+			params = [new_positions[valid].clone(), covector_field.scalings.detach()[valid].clone(), covector_field.rotations.detach()[valid].clone(),
+					  covector_field.values.detach()[valid].clone()]
+	if params is not None:
+		for p in params:
+			p.requires_grad_()
+		covector_field.positions, covector_field.scalings, covector_field.rotations, covector_field.values = params
 	covector_field.N = covector_field.positions.shape[0]
 	covector_field.zero_grad()
 	if extra_advector:
@@ -148,6 +157,18 @@ class FusedProjector2D:
 		cur = reference_field.velocity_field
 		cur._engine.ensure_packed(cur._params())
 		self._buf = {}
+
+	def restart(self, reference_field):
+		"""a new phase on the same tensors (the next frame): fresh optimiser state and hash; every buffer — and a graph captured on
+		them — stays"""
+		gv, e = self.gv, self.gv._engine
+		self.ref = reference_field
+		self.stepper.init(gv.scalings)
+		e.build(gv.positions.detach(), params=[p.detach() for p in gv._params()])
+		e._packed_key = None
+		self.positions_org.copy_(gv.positions.detach())
+		cur = reference_field.velocity_field
+		cur._engine.ensure_packed(cur._params())
 
 	def _tmp(self, name, shape):
 		t = self._buf.get(name)
@@ -272,7 +293,8 @@ def _project_unfused(gv, reference_field, data_generator, test_data_generator, b
 
 
 def project(gaussian_velocity, reference_field, data_generator, test_data_generator, boundary_generator_1=None, boundary_generator_2=None,
-			boundary_lambda=0., batch_size=512, max_epoch=3000, patience=500, verbose=1, fused=True, check_iter=100, weights=None, lrs=None, use_graph=None):
+			boundary_lambda=0., batch_size=512, max_epoch=3000, patience=500, verbose=1, fused=True, check_iter=100, weights=None, lrs=None, use_graph=None,
+			cache=True):
 	"""
 	One time step's projection by first-order optimisation (2D/advance.py:187-302): match the advected vorticity, drive
 	the divergence to zero, keep the Gaussians well shaped and close to their advected positions.  Early stop: every 100
@@ -282,6 +304,9 @@ def project(gaussian_velocity, reference_field, data_generator, test_data_genera
 	use_graph: replay the iterations as a CUDA graph (graphloop.py).  That is only valid when the generators are pure device
 	functions of torch's CUDA random stream — a generator that walks a Python list would be replayed with its first batches — so
 	the default (None) turns it on only when every generator carries `graph_safe = True` (Scene2D's samplers do).
+	cache: keep the projector and its captured graph on the field object and reuse them in the next frame when NOTHING the graph
+	holds has changed — the same tensors (clone and advect update in place when no Gaussian was split or dropped), the same
+	reference field object, time step, domain, weights, rates and generator objects — instead of warming up and capturing again.
 	"""
 	gv = gaussian_velocity
 	lr = dict(PROJECT_LRS, **(lrs or {}))
@@ -292,9 +317,28 @@ def project(gaussian_velocity, reference_field, data_generator, test_data_genera
 	if not fused:
 		return _project_unfused(gv, reference_field, data_generator, test_data_generator, boundary_generator_1, boundary_generator_2, boundary_lambda,
 								batch_size, max_epoch, patience, verbose, check_iter, weights)
-	fp = FusedProjector2D(gv, reference_field, boundary_lambda, patience=50, weights=weights, lrs=lrs)
 	use_b1 = boundary_lambda > 0. and boundary_generator_1
 	use_b2 = boundary_lambda > 0. and boundary_generator_2
+	if use_graph is None:
+		use_graph = all(getattr(g, 'graph_safe', False) for g in (data_generator, boundary_generator_1 if use_b1 else data_generator, boundary_generator_2 if use_b2 else data_generator))
+	cur = reference_field.velocity_field
+	key = None
+	if cache and use_graph:
+		key = (id(cur), gv.N, cur.N, float(reference_field.time_step), tuple(float(v) for v in (reference_field.domain or ())), reference_field.advection_scheme,
+			   float(boundary_lambda), batch_size, check_iter, tuple(sorted((weights or {}).items())), tuple(sorted(lr.items())),
+			   id(data_generator), id(boundary_generator_1) if use_b1 else 0, id(boundary_generator_2) if use_b2 else 0,
+			   tuple(p.data_ptr() for p in gv._params()), tuple(p.data_ptr() for p in cur._params()))
+		store = gv.__dict__.setdefault('_pipelines2d', {})
+		hit = store.get(key)
+		if hit is not None:
+			fp, loop = hit
+			fp.restart(reference_field)
+		else:
+			for old_fp, old_loop in store.values():	# tensors or settings changed: the old graphs can never be replayed again
+				old_loop.release()
+			store.clear()
+	if key is None or hit is None:
+		fp = FusedProjector2D(gv, reference_field, boundary_lambda, patience=50, weights=weights, lrs=lrs)
 
 	def batches():	# sync-free: the draws come from torch's CUDA generator
 		data = data_generator(batch_size, gv)
@@ -304,9 +348,10 @@ def project(gaussian_velocity, reference_field, data_generator, test_data_genera
 
 	def iteration(inputs):	# sync-free: every scalar that changes between iterations lives in the stepper's device state
 		fp.iterate(*inputs)
-	if use_graph is None:
-		use_graph = all(getattr(g, 'graph_safe', False) for g in (data_generator, boundary_generator_1 if use_b1 else data_generator, boundary_generator_2 if use_b2 else data_generator))
-	loop = GraphedLoop(iteration, unit=next(u for u in (10, 5, 2, 1) if check_iter % u == 0), enabled=use_graph, prepare=batches)
+	if key is None or hit is None:
+		loop = GraphedLoop(iteration, unit=next(u for u in (10, 5, 2, 1) if check_iter % u == 0), enabled=use_graph, prepare=batches)
+		if key is not None:
+			store[key] = (fp, loop)
 	best, stale = [np.inf, np.inf], [0, 0]
 	epochs = max_epoch
 	st_time = time.time()
@@ -329,7 +374,8 @@ def project(gaussian_velocity, reference_field, data_generator, test_data_genera
 		if stale[0] >= patience and stale[1] >= patience:
 			epochs = done
 			break
-	loop.release()
+	if key is None:
+		loop.release()
 	fp.finish()
 	return epochs
 
@@ -443,9 +489,12 @@ def simulation_initialize(scene, max_epoch=10000, verbose=1, fused=True, project
 
 def advance(scene, gaussian_velocity, new_gaussian_velocity, dt, max_epoch=20000, boundary_lambda=1., verbose=1, fused=True):
 	"""one frame of the `while t < last_time` loop of 2D/advance.py:354-365; returns (current, spare) after the swap"""
-	gen = lambda n, gs, restrict=None: scene.data_generator(gs)
-	gen.graph_safe = True
-	test = lambda gs: scene.test_generator()
+	gens = scene.__dict__.get('_advance_generators')	# the same generator OBJECTS every frame: project() keeps its captured graph across frames
+	if gens is None:
+		gen = lambda n, gs, restrict=None: scene.data_generator(gs)
+		gen.graph_safe = True
+		gens = scene._advance_generators = (gen, lambda gs: scene.test_generator())
+	gen, test = gens
 	clone_velocity_field(new_gaussian_velocity, gaussian_velocity, gen, test, max_epoch=max_epoch, verbose=verbose)
 	advect_covector_field(new_gaussian_velocity, gaussian_velocity, dt, extra_advector=scene.extra_advector)	# karman: the inlet moves with the flow
 	ref = AdvectedCovectorField(gaussian_velocity, gaussian_velocity, dt, domain=scene.scaled(scene.advance_domain))
