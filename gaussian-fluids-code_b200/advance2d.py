@@ -493,12 +493,11 @@ def advance(scene, gaussian_velocity, new_gaussian_velocity, dt, max_epoch=20000
 	if gens is None:
 		gen = lambda n, gs, restrict=None: scene.data_generator(gs)
 		gen.graph_safe = True
-		gens = scene._advance_generators = (gen, lambda gs: scene.test_generator())
-	gen, test = gens
+		gens = scene._advance_generators = (gen, lambda gs: scene.test_generator()) + tuple(scene.boundary_samplers)
+	gen, test, b1, b2 = gens
 	clone_velocity_field(new_gaussian_velocity, gaussian_velocity, gen, test, max_epoch=max_epoch, verbose=verbose)
 	advect_covector_field(new_gaussian_velocity, gaussian_velocity, dt, extra_advector=scene.extra_advector)	# karman: the inlet moves with the flow
 	ref = AdvectedCovectorField(gaussian_velocity, gaussian_velocity, dt, domain=scene.scaled(scene.advance_domain))
-	b1, b2 = scene.boundary_samplers
 	project(new_gaussian_velocity, ref, gen, test, boundary_generator_1=b1, boundary_generator_2=b2, boundary_lambda=boundary_lambda, max_epoch=max_epoch,
 			verbose=verbose, fused=fused)
 	return new_gaussian_velocity, gaussian_velocity
