@@ -41,6 +41,7 @@ struct XrankArgs {
 	unsigned spin_limit;
 };
 
+template <bool CONC>
 __global__ void __launch_bounds__(XR_THREADS) xrank_sum_kernel(XrankArgs a, size_t n4, const float *__restrict__ iter_dev, const int32_t *__restrict__ base_dev,
 							      float4 *__restrict__ out, int32_t *__restrict__ err)
 {
@@ -69,17 +70,24 @@ __global__ void __launch_bounds__(XR_THREADS) xrank_sum_kernel(XrankArgs a, size
 			out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 			continue;
 		}
-		// every peer's value is requested before the first is used: a peer-memory load is a ~2 us round trip, and a loop of
-		// {load, add} would pay it once per rank (the adds wait for their operands in order) — measured as 13.7 us per iteration
-		// at 8 ranks
-		float4 v[XR_MAX_WORLD];
+		float4 s;
+		if (CONC) {
+			// every peer's value is requested before the first is used (pays at 8 ranks, costs at 2: see the launch code)
+			float4 v[XR_MAX_WORLD];
 #pragma unroll
-		for (int r = 0; r < XR_MAX_WORLD; r++)
-			if (r < a.world) v[r] = ld_peer4(a.peer[r] + i);
-		float4 s = v[0];
+			for (int r = 0; r < XR_MAX_WORLD; r++)
+				if (r < a.world) v[r] = ld_peer4(a.peer[r] + i);
+			s = v[0];
 #pragma unroll
-		for (int r = 1; r < XR_MAX_WORLD; r++)
-			if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+			for (int r = 1; r < XR_MAX_WORLD; r++)
+				if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+		} else {
+			s = ld_peer4(a.peer[0] + i);
+			for (int r = 1; r < a.world; r++) {
+				const float4 v = ld_peer4(a.peer[r] + i);
+				s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+			}
+		}
 		out[i] = s;
 	}
 }
@@ -112,7 +120,11 @@ extern "C" int gsr_xrank_sum(const void *const *peer_bufs, void *const *peer_sig
 	int blocks = (int)((n4 + XR_THREADS - 1) / XR_THREADS);
 	if (blocks > kSMs) blocks = kSMs;	// all CTAs resident: every one of them polls the signal pad
 	g_launches += 1;
-	xrank_sum_kernel<<<blocks, XR_THREADS, 0, (cudaStream_t)stream>>>(a, n4, iteration_dev, epoch_base_dev, (float4 *)out, err_flag);
+	// measured (S1, ms per step): 2 ranks 40.8 with the {load, add} loop / 43.1 with all loads first; 8 ranks 44.3 / 43.7
+	static const int conc_env = getenv("GSR_XRANK_CONC") ? atoi(getenv("GSR_XRANK_CONC")) : -1;
+	const bool conc = conc_env >= 0 ? conc_env != 0 : world >= 8;
+	if (conc) xrank_sum_kernel<true><<<blocks, XR_THREADS, 0, (cudaStream_t)stream>>>(a, n4, iteration_dev, epoch_base_dev, (float4 *)out, err_flag);
+	else xrank_sum_kernel<false><<<blocks, XR_THREADS, 0, (cudaStream_t)stream>>>(a, n4, iteration_dev, epoch_base_dev, (float4 *)out, err_flag);
 	GSR_CHECK_LAUNCH();
 	return GSR_OK;
 }
