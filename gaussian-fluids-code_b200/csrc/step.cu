@@ -797,8 +797,6 @@ step_cluster4_kernel(gsr_step_cfg cfg, int N, float *__restrict__ pos, float *__
 	__shared__ float wpart[SC4_MAX_THREADS / 32][S_COUNT];
 	__shared__ float part[S_COUNT];
 	__shared__ double Tsm[S_COUNT + 8];
-	__shared__ double bc_sm[2];
-	__shared__ int decay_sm;
 	__shared__ float wmin[SC4_MAX_THREADS / 32];
 	__shared__ float bmin;
 	__shared__ float Tg[SC4_MAX_THREADS / G][G][P + 1];	// parameter-space gradients of the four roles of every Gaussian of this CTA
