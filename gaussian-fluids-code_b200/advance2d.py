@@ -157,6 +157,7 @@ class FusedProjector2D:
 		cur = reference_field.velocity_field
 		cur._engine.ensure_packed(cur._params())
 		self._buf = {}
+		self._streams = None
 
 	def restart(self, reference_field):
 		"""a new phase on the same tensors (the next frame): fresh optimiser state and hash; every buffer — and a graph captured on
@@ -177,38 +178,80 @@ class FusedProjector2D:
 			self._buf[name] = t
 		return t
 
+	def _ref_vorticity(self, data):
+		"""self.ref.vorticity(data) into a persistent buffer (the result crosses streams: no allocator involvement)"""
+		ref = self.ref
+		if ref.advection_scheme != 'rk4':
+			return ref.vorticity(data)
+		cur = ref.velocity_field
+		cur._engine.ensure_packed(cur._params())
+		out = self._tmp('ref_vor', (data.shape[0],))
+		cur._engine.advected_vorticity(data, -ref.time_step, out, None, domain=ref.domain)
+		return out
+
 	def iterate(self, data, boundary_1=None, boundary_2=None):
+		"""
+		One optimiser iteration; no host synchronisation.  Until the step the iteration is four independent chains — the RK4 pull-back
+		reference (previous field), the forward pass of the training batch, and one {order, forward, adjoint + gather} chain per boundary
+		batch — so they run on four streams (fork / join by events: a captured graph keeps the concurrency) and meet at the training
+		gather and at the step.  Same kernels on the same inputs as the sequential order: same bits.
+		"""
 		gv, e = self.gv, self.gv._engine
 		data = data.detach()
 		Q = data.shape[0]
-		ref_vor = self.ref.vorticity(data)
-		bins = e.bin_samples(data, True)
-		grad = self._tmp('grad', (Q, 2, 2))
-		e.forward(data, None, grad, accumulate=False, perm=bins)
-		acc, mask = e.backward_gather(data, bins.perm, bins.scs, None, grad, (0., 0., 0., self.w['vor'], 0., self.w['div']), {'ref_vor': ref_vor}, None, want_losses=True)
-		lp, nblk = e.last_loss_partials
-		srcs = [(lp, nblk, [self.w['vor'] / Q, 0., self.w['div'] / Q, 0., 0., 0., 0., 0.])]
-		extra = []
 		lam = self.boundary_lambda
+		main = torch.cuda.current_stream()
+		if self._streams is None:
+			self._streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
+		s_fwd, s_b1, s_b2 = self._streams
+		fork = torch.cuda.Event()
+		fork.record(main)
+		srcs_b, extra, joins = [], [], []
 		if lam > 0. and boundary_1 is not None:	# prescribed velocity on an obstacle (2D/advance.py:217-220)
 			bdata, bvalue = [t.detach() for t in boundary_1]
-			bins1 = e.bin_samples(bdata, True, tag='b1')
-			val1 = self._tmp('val1', (bdata.shape[0], 2))
-			e.forward(bdata, val1, None, accumulate=False, perm=bins1)
-			acc1, _ = e.backward_gather(bdata, bins1.perm, bins1.scs, val1, None, (lam, 0., 0., 0., 0., 0.), {'ref_val': bvalue}, None, tag='acc_b1', want_losses=True)
-			lp1, nb1 = e.last_loss_partials
-			srcs.append((lp1, nb1, [0., 0., 0., 0., lam / bdata.shape[0], 0., 0., 0.]))
+			s_b1.wait_event(fork)
+			with torch.cuda.stream(s_b1):
+				bins1 = e.bin_samples(bdata, True, tag='b1')
+				val1 = self._tmp('val1', (bdata.shape[0], 2))
+				e.forward(bdata, val1, None, accumulate=False, perm=bins1)
+				acc1, _ = e.backward_gather(bdata, bins1.perm, bins1.scs, val1, None, (lam, 0., 0., 0., 0., 0.), {'ref_val': bvalue}, None, tag='acc_b1', want_losses=True)
+				lp1, nb1 = e.last_loss_partials
+				ev = torch.cuda.Event()
+				ev.record(s_b1)
+				joins.append(ev)
+			srcs_b.append((lp1, nb1, [0., 0., 0., 0., lam / bdata.shape[0], 0., 0., 0.]))
 			extra.append(acc1)
 		if lam > 0. and boundary_2 is not None:	# prescribed normal velocity (2D/advance.py:231-235)
-			bdata, bnormal, bref = [t.detach() for t in boundary_2]
-			bins2 = e.bin_samples(bdata, True, tag='b2')
-			val2 = self._tmp('val2', (bdata.shape[0], 2))
-			e.forward(bdata, val2, None, accumulate=False, perm=bins2)
-			acc2, _ = e.backward_gather(bdata, bins2.perm, bins2.scs, val2, None, (0., lam, 0., 0., 0., 0.), {'normals': bnormal, 'normal_ref': bref}, None,
-										tag='acc_b2', want_losses=True)
-			lp2, nb2 = e.last_loss_partials
-			srcs.append((lp2, nb2, [0., 0., 0., lam / bdata.shape[0], 0., 0., 0., 0.]))
+			bdata2, bnormal, bref = [t.detach() for t in boundary_2]
+			s_b2.wait_event(fork)
+			with torch.cuda.stream(s_b2):
+				bins2 = e.bin_samples(bdata2, True, tag='b2')
+				val2 = self._tmp('val2', (bdata2.shape[0], 2))
+				e.forward(bdata2, val2, None, accumulate=False, perm=bins2)
+				acc2, _ = e.backward_gather(bdata2, bins2.perm, bins2.scs, val2, None, (0., lam, 0., 0., 0., 0.), {'normals': bnormal, 'normal_ref': bref}, None,
+											tag='acc_b2', want_losses=True)
+				lp2, nb2 = e.last_loss_partials
+				ev = torch.cuda.Event()
+				ev.record(s_b2)
+				joins.append(ev)
+			srcs_b.append((lp2, nb2, [0., 0., 0., lam / bdata2.shape[0], 0., 0., 0., 0.]))
 			extra.append(acc2)
+		bins = e.bin_samples(data, True)
+		grad = self._tmp('grad', (Q, 2, 2))
+		binned = torch.cuda.Event()
+		binned.record(main)
+		s_fwd.wait_event(binned)
+		with torch.cuda.stream(s_fwd):
+			e.forward(data, None, grad, accumulate=False, perm=bins)
+			done_f = torch.cuda.Event()
+			done_f.record(s_fwd)
+		ref_vor = self._ref_vorticity(data)	# beside the forward pass
+		main.wait_event(done_f)
+		acc, mask = e.backward_gather(data, bins.perm, bins.scs, None, grad, (0., 0., 0., self.w['vor'], 0., self.w['div']), {'ref_vor': ref_vor}, None, want_losses=True)
+		lp, nblk = e.last_loss_partials
+		srcs = [(lp, nblk, [self.w['vor'] / Q, 0., self.w['div'] / Q, 0., 0., 0., 0., 0.])] + srcs_b
+		for ev in joins:
+			main.wait_event(ev)
 		self.stepper.step([p.detach() for p in gv._params()], acc, mask, extra=extra, loss_srcs=srcs, positions_org=self.positions_org, rebuild=True)
 
 	def evaluate(self, data):

@@ -212,8 +212,9 @@ class Scene2D:
 		2D/initialize.py:216-217, draws them on the initialize domain: pass it as `domain`)"""
 		x_min, x_max, y_min, y_max = domain if domain is not None else self.advance_domain
 		dev = _dev()
-		return (torch.rand_like(gaussian_splatting.positions.detach(), device=dev) * _const([x_max - x_min, y_max - y_min], dev)
-				+ _const([x_min, y_min], dev)) * self.scaling_factor
+		sf = self.scaling_factor	# (rand * extent + lo) * sf, with the constants folded: two kernels
+		return torch.addcmul(_const([x_min * sf, y_min * sf], dev), torch.rand_like(gaussian_splatting.positions.detach(), device=dev),
+							 _const([(x_max - x_min) * sf, (y_max - y_min) * sf], dev))
 
 	def test_generator(self):
 		x_min, x_max, y_min, y_max = self.advance_domain
@@ -221,17 +222,19 @@ class Scene2D:
 
 	def _on_domain_boundary_2(self, n):
 		"""sample_on_domain_boundary_2 (2D/init_cond.py:306-325): points on the four edges (perimeter-weighted), OUTWARD normals,
-		target normal velocity 0.  Written without boolean-mask indexing (no host sync)."""
+		target normal velocity 0.  One torch.rand like the reference; the edge of a draw is a table lookup (corner + direction x
+		arc length) instead of the reference's four masked assignments: a dozen small kernels, no boolean-mask indexing (no host sync)."""
 		x_min, x_max, y_min, y_max = self.advance_domain
 		xs, ys = x_max - x_min, y_max - y_min
 		dev = _dev()
-		t = torch.rand(n, device=dev) * (xs + ys) * 2.
-		edge = (t >= xs).long() + (t >= xs + ys).long() + (t >= 2. * xs + ys).long()
-		px = torch.stack([x_min + t, torch.full_like(t, x_max), x_max - t + xs + ys, torch.full_like(t, x_min)], dim=1)
-		py = torch.stack([torch.full_like(t, y_min), y_min + t - xs, torch.full_like(t, y_max), y_max - t + 2. * xs + ys], dim=1)
-		data = torch.stack([px.gather(1, edge[:, None])[:, 0], py.gather(1, edge[:, None])[:, 0]], dim=1)
+		t = torch.rand(n, device=dev) * ((xs + ys) * 2.)
+		edge = torch.bucketize(t, _const([xs, xs + ys, 2. * xs + ys], dev), right=True)	# t >= bound -> next edge
+		s_ = t - _const([0., xs, xs + ys, 2. * xs + ys], dev)[edge]
+		corner = _const([[x_min, y_min], [x_max, y_min], [x_max, y_max], [x_min, y_max]], dev)[edge]
+		along = _const([[1., 0.], [0., 1.], [-1., 0.], [0., -1.]], dev)[edge]
+		data = torch.addcmul(corner, along, s_[:, None])
 		normals = _const([[0., -1.], [1., 0.], [0., 1.], [-1., 0.]], dev)[edge]
-		return data.contiguous(), normals.contiguous(), torch.zeros(n, device=dev)
+		return data, normals, torch.zeros(n, device=dev)
 
 	@staticmethod
 	def _on_circle(n, x, y, r):
