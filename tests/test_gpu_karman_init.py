@@ -34,6 +34,9 @@ def test_karman_initial_state_constants_and_paths_agree():
 		assert np.isfinite(x).all()
 		# Adam's first steps move every entry by ~ lr * sign(g): an entry whose gradient is rounding noise may flip (a few lr), the rest agrees
 		d = np.abs(x - y) / np.abs(y).max()
+		if nm == 'rotations':	# the lattice starts isotropic: a rotation gradient is -g/2 (e^{2 s0} - e^{2 s1}) (...) ~ rounding noise, and the
+			assert (d > 1e-5).mean() < .05, (nm, (d > 1e-5).mean())	# angles themselves are a few lr: flipped entries are a few percent, each O(1) relative
+			continue
 		assert (d > 1e-5).mean() < .01 and d.max() < 2e-2, (nm, (d > 1e-5).mean(), d.max())
 	assert a.grid_scale == pytest.approx(b.grid_scale, rel=1e-5)
 
