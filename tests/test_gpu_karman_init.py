@@ -33,11 +33,14 @@ def test_karman_initial_state_constants_and_paths_agree():
 		x, y = getattr(a, nm).detach().cpu().numpy(), getattr(b, nm).detach().cpu().numpy()
 		assert np.isfinite(x).all()
 		# Adam's first steps move every entry by ~ lr * sign(g): an entry whose gradient is rounding noise may flip (a few lr), the rest agrees
+		# The inflow is uniform: every gradient whose exact value is zero (second velocity component, rotation angles of the isotropic
+		# start, ...) is rounding noise, and Adam turns noise into +-lr steps — so a few percent of the entries legitimately differ
+		# by a few lr between two correct implementations.  The bulk must agree to rounding; the fields are compared below.
 		d = np.abs(x - y) / np.abs(y).max()
-		if nm == 'rotations':	# the lattice starts isotropic: a rotation gradient is -g/2 (e^{2 s0} - e^{2 s1}) (...) ~ rounding noise, and the
-			assert (d > 1e-5).mean() < .05, (nm, (d > 1e-5).mean())	# angles themselves are a few lr: flipped entries are a few percent, each O(1) relative
-			continue
-		assert (d > 1e-5).mean() < .01 and d.max() < 2e-2, (nm, (d > 1e-5).mean(), d.max())
+		assert (d > 1e-5).mean() < .05, (nm, (d > 1e-5).mean(), d.max())
+	pts = scene.test_generator()
+	ua, ub = a(pts), b(pts)
+	assert float((ua - ub).abs().max() / ub.abs().max()) < 5e-3
 	assert a.grid_scale == pytest.approx(b.grid_scale, rel=1e-5)
 
 
