@@ -36,9 +36,23 @@ def rings_of(init_cond):
 	return [info]
 
 
+_RING_CACHE = {}
+
+
 def _ring_particles(ring):
-	"""n vortex particles on the ring and their (strength-scaled) tangents (3D/init_cond.py:147-156)"""
+	"""n vortex particles on the ring and their (strength-scaled) tangents (3D/init_cond.py:147-156); built once per ring and device
+	(the construction uploads constants and reads a norm back: neither belongs into every evaluation, nor into a captured graph)"""
 	device = gsr3d.device
+	key = (id(ring), str(device))
+	hit = _RING_CACHE.get(key)
+	if hit is not None and hit[0] is ring:
+		return hit[1]
+	out = _ring_particles_build(ring, device)
+	_RING_CACHE[key] = (ring, out)
+	return out
+
+
+def _ring_particles_build(ring, device):
 	normal = torch.tensor(ring['normal'], device=device)
 	center = torch.tensor(ring['center'], device=device)
 	axis_x = torch.tensor([1., 0., 0.], device=device)
@@ -50,7 +64,7 @@ def _ring_particles(ring):
 	theta = torch.linspace(0., 2. * torch.pi, ring['n'] + 1, device=device)[:-1]
 	x0 = (axis_x[None] * torch.cos(theta)[:, None] + axis_y[None] * torch.sin(theta)[:, None]) * ring['radius'] + center
 	w = (axis_x[None] * -torch.sin(theta)[:, None] + axis_y[None] * torch.cos(theta)[:, None]) * ring['strength']
-	return x0, w, ring['radius'] / (2 * ring['n']), ring['thickness']
+	return x0.contiguous(), w.contiguous(), ring['radius'] / (2 * ring['n']), ring['thickness']
 
 
 def _biot_savart(x, ring, val, grad):
@@ -96,6 +110,7 @@ def make_field(init_cond):
 		return run(x, True, False)[0]
 	field.gradient = lambda x: run(x, False, True)[1]
 	field.both = lambda x: run(x, True, True)
+	field.graph_safe = True	# a pure device function of its argument: the fit may replay it from a CUDA graph (graphloop.py)
 	return field
 
 

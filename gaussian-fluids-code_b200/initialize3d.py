@@ -14,9 +14,14 @@ import torch.nn.functional as F
 
 from . import gsr3d, init_cond3d
 from .engine import FusedStepper
+from .graphloop import GraphedLoop
 
 
-def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gradient, data_generator, batch_size=8192, max_epoch=3000, verbose=1, fused=True):
+def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gradient, data_generator, batch_size=8192, max_epoch=3000, verbose=1, fused=True,
+							   use_graph=None):
+	"""the initial fit (3D/initialize.py:9-46).  fused=True: one device-resident iteration (forward, gather, gsr_step_rebuild) without host
+	synchronisation; use_graph (None: when the generator and the target field carry `graph_safe = True`): ten iterations per captured CUDA
+	graph, the next batch and its analytic targets prepared on a second stream (graphloop.py) — same results bit for bit"""
 	gv = gaussian_velocity
 	gv.initialize_optimizers()
 	dev = gsr3d.device
@@ -39,23 +44,39 @@ def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gra
 	e.build(gv.positions.detach(), params=[p.detach() for p in gv._params()])
 	e._packed_key = None
 	st_time = time.time()
-	for epoch in range(max_epoch):
+	def batches():	# the samples and the analytic targets at them: functions of the random stream only
 		data = data_generator(batch_size).detach()
-		Q = data.shape[0]
 		if hasattr(reference_field, 'both'):	# the analytic ring fields give velocity and Jacobian from one pass over the particles
 			ref_val, ref_grad = reference_field.both(data)
 		else:
 			ref_val, ref_grad = reference_field(data).contiguous(), reference_gradient(data).contiguous()
+		return data, ref_val, ref_grad
+
+	def iteration(inputs):
+		data, ref_val, ref_grad = inputs
+		Q = data.shape[0]
 		bins = e.bin_samples(data, True)
-		val, grad = torch.empty((Q, 3), device=dev), torch.empty((Q, 3, 3), device=dev)
+		if 'val' not in bufs:
+			bufs['val'], bufs['grad'] = torch.empty((Q, 3), device=dev), torch.empty((Q, 3, 3), device=dev)
+		val, grad = bufs['val'], bufs['grad']
 		e.forward(data, val, grad, accumulate=False, perm=bins)
 		acc, mask = e.backward_gather(data, bins.perm, bins.scs, val, grad, (1., 0., 1., 0., 0., 0.), {'ref_val': ref_val, 'ref_grad': ref_grad}, None, want_losses=True)
 		lp, nblk = e.last_loss_partials
 		stepper.step([p.detach() for p in gv._params()], acc, mask, loss_srcs=[(lp, nblk, [0., 0., 0., 0., 1. / Q, 1. / Q, 0., 0.])], rebuild=True)
-		if verbose and epoch % 100 == 0:
+	bufs = {}
+	if use_graph is None:
+		use_graph = getattr(data_generator, 'graph_safe', False) and getattr(reference_field, 'graph_safe', False)
+	loop = GraphedLoop(iteration, unit=10, enabled=bool(use_graph), prepare=batches)
+	done = 0
+	while done < max_epoch:
+		k = min(100, max_epoch - done)
+		loop.run(k)
+		done += k
+		if verbose:
 			sc = stepper.scalars()
 			print(f'loss_tot: {sc[9]}, loss_aniso: {sc[10]}, loss_vol: {sc[11]}, time: {time.time() - st_time}')
 			st_time = time.time()
+	loop.release()
 	gv.grid_scale = stepper.detach()
 	e._packed_key = None
 	for p in gv._params():
@@ -63,7 +84,7 @@ def fit_velocity_with_gradient(gaussian_velocity, reference_field, reference_gra
 	gv.zero_grad()
 
 
-def simulation_initialize(init_cond, max_epoch=500, verbose=1, fused=True, particle_count=None):
+def simulation_initialize(init_cond, max_epoch=500, verbose=1, fused=True, particle_count=None, use_graph=None):
 	"""lattice of Gaussians over the scene's domain -> fit to the analytic vortex-ring field -> the frame-0 field (3D/initialize.py:49-86)"""
 	x_min, x_max, y_min, y_max, z_min, z_max = init_cond3d.domain[init_cond]
 	nx, ny, nz = particle_count or init_cond3d.initial_particle_count[init_cond]
@@ -74,5 +95,6 @@ def simulation_initialize(init_cond, max_epoch=500, verbose=1, fused=True, parti
 	ext = torch.tensor([x_max - x_min, y_max - y_min, z_max - z_min], device=dev)
 	lo = torch.tensor([x_min, y_min, z_min], device=dev)
 	gen = lambda n: torch.rand_like(gv.positions.detach(), device=dev) * ext + lo	# Q = N: batch_size is ignored, as in the reference (:73-74)
-	fit_velocity_with_gradient(gv, field, field.gradient, gen, max_epoch=max_epoch, verbose=verbose, fused=fused)
+	gen.graph_safe = True
+	fit_velocity_with_gradient(gv, field, field.gradient, gen, max_epoch=max_epoch, verbose=verbose, fused=fused, use_graph=use_graph)
 	return gv

@@ -63,3 +63,21 @@ def test_accumulates_and_rejects_cpu_tensors():
 	np.testing.assert_allclose(twice.cpu().numpy(), 2. * once.cpu().numpy(), rtol=1e-6)
 	with pytest.raises(_lib.GsrError):
 		init_cond3d.vortex_ring(x.cpu(), ring)
+
+
+def test_initial_fit_from_cuda_graphs_equals_the_eager_fit():
+	"""initialize3d.simulation_initialize (the fit of 3D/initialize.py:49-86 to the analytic ring field) replayed from CUDA graphs, ten
+	iterations per graph with the next batch and its Biot-Savart targets prepared on a second stream, against the same loop run eagerly:
+	same kernels, same random stream — the same bits"""
+	import torch
+	from gaussian_fluids_code_b200 import graphloop, gsr3d, initialize3d
+	gsr3d.device = torch.device('cuda', 0)
+	out = {}
+	for use_graph in (False, True):
+		torch.manual_seed(9)
+		g0 = graphloop.GRAPH_LAUNCHES
+		gv = initialize3d.simulation_initialize('leapfrog', max_epoch=45, verbose=0, use_graph=use_graph)
+		assert (graphloop.GRAPH_LAUNCHES > g0) == use_graph
+		out[use_graph] = [p.detach().clone() for p in gv._params()] + [torch.tensor(gv.grid_scale)]
+	for a, b in zip(out[False], out[True]):
+		assert torch.isfinite(a).all() and torch.equal(a.cpu(), b.cpu())
