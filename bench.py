@@ -276,7 +276,8 @@ def timeit_graph(fn, reps=20, warm=2):
 	torch.cuda.current_stream().wait_stream(s)
 	torch.cuda.synchronize()
 	g = torch.cuda.CUDAGraph()
-	with torch.cuda.graph(g):
+	from gaussian_fluids_code_b200.graphloop import capture_guard
+	with capture_guard(), torch.cuda.graph(g):
 		for _ in range(reps):
 			fn()
 	g.replay()

@@ -20,6 +20,27 @@ GRAPH_LAUNCHES = 0	# kernels of this library launched from graph replays (the li
 _CAPTURE_STREAM = None
 
 
+import contextlib
+import gc
+
+
+@contextlib.contextmanager
+def capture_guard():
+	"""Around every stream capture: Python's cyclic collector must not run inside one.  A CUDAGraph (or any object owning CUDA
+	resources) that sits in a reference cycle — a dead projector and the closures of its loop — is destroyed whenever the collector
+	happens to run; if that is in the middle of ANOTHER capture, its clean-up is an operation the capturing stream does not permit
+	and the capture is invalidated (seen in the full test suite: "operation not permitted when stream is capturing (function
+	reset)").  So: collect first, then keep the collector off until the capture has ended."""
+	gc.collect()
+	was = gc.isenabled()
+	gc.disable()
+	try:
+		yield
+	finally:
+		if was:
+			gc.enable()
+
+
 _SIDE_STREAM = None
 
 
@@ -91,7 +112,7 @@ class GraphedLoop:
 		self.graph = torch.cuda.CUDAGraph()
 		cur = torch.cuda.current_stream()
 		_CAPTURE_STREAM.wait_stream(cur)
-		with torch.cuda.stream(_CAPTURE_STREAM):
+		with capture_guard(), torch.cuda.stream(_CAPTURE_STREAM):
 			self.graph.capture_begin(capture_error_mode='thread_local')
 			try:
 				if self.prepare is None:
@@ -113,6 +134,9 @@ class GraphedLoop:
 		cur.wait_stream(_CAPTURE_STREAM)
 
 	def release(self):
+		"""drop the graph (and the closures: they and the objects they hold form a reference cycle with this loop)"""
 		if self.graph is not None:
 			torch.cuda.current_stream().synchronize()	# the last replay may still be running on the pool's memory
 			self.graph = None
+		self.enabled = False
+		self.body = self._body_in = self.prepare = None

@@ -456,7 +456,8 @@ class ShardedProjector(advance3d.FusedProjector):
 				done += unit
 			torch.cuda.current_stream().wait_stream(side)
 			self.graph, self.unit = torch.cuda.CUDAGraph(), unit
-			with torch.cuda.graph(self.graph):
+			from .graphloop import capture_guard
+			with capture_guard(), torch.cuda.graph(self.graph):
 				body(unit)
 			self.graph_launches -= self.per_iter	# the capture pass bumped the host counter without running anything
 		while done < n:
