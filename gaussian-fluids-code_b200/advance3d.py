@@ -213,6 +213,7 @@ class FusedProjector:
 		cur = reference_field.velocity_field
 		cur._engine.ensure_packed(cur._params())
 		self._buf = {}
+		self._streams = None
 
 	def sample_grid(self, iteration=None):
 		"""The grid scale the sample batches of an iteration are binned with (a device scalar): not the hash's own but one the step
@@ -236,37 +237,58 @@ class FusedProjector:
 		return t
 
 	def iterate(self, data, boundary=None):
-		"""one optimiser iteration; no host synchronisation"""
+		"""one optimiser iteration; no host synchronisation.  The boundary pass, the forward pass of the training batch and the RK4
+		pull-back reference are independent until the training gather / the step: three streams, joined by events (a captured graph keeps
+		the concurrency; same kernels on the same inputs as the sequential order, same bits)"""
 		gv, e = self.gv, self.gv._engine
 		cur = self.ref.velocity_field
 		Q = data.shape[0]
 		data = data.detach()
 		sgs = self.sample_grid()
 		self._it += 1
-		bins = e.bin_samples(data, True, gs_dev=sgs)
-		perm, scs = bins
-		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
-		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)
-		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
-		e.forward(data, val, grad, accumulate=False, perm=bins)
-		acc, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
-									  {'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, want_losses=True, sample_gs=sgs)
-		lp, nblk = e.last_loss_partials
-		srcs = [(lp, nblk, [self.w['vor'] / Q, 0., self.w['div'] / Q, 0., 0., 0., 0., 0.])]
-		extra = []
+		main = torch.cuda.current_stream()
+		if self._streams is None:
+			self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+		s_fwd, s_bnd = self._streams
+		fork = torch.cuda.Event()
+		fork.record(main)
+		extra, srcs_b, done_b = [], [], None
 		if boundary is not None and self.boundary_lambda:
 			bdata, bnormal = boundary
 			bdata, bnormal = bdata.detach(), bnormal.detach()
 			Qb = bdata.shape[0]
-			bins_b = e.bin_samples(bdata, True, tag='b', gs_dev=sgs)
-			perm_b, scs_b = bins_b
-			valb = self._tmp('valb', (Qb, 3))
-			e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
-			acc_b, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
-											  {'normals': bnormal}, None, tag='acc_b', want_losses=True, sample_gs=sgs)
-			lpb, nblkb = e.last_loss_partials
-			srcs.append((lpb, nblkb, [0., 0., 0., self.boundary_lambda / Qb, 0., 0., 0., 0.]))
+			s_bnd.wait_event(fork)
+			with torch.cuda.stream(s_bnd):
+				bins_b = e.bin_samples(bdata, True, tag='b', gs_dev=sgs)
+				perm_b, scs_b = bins_b
+				valb = self._tmp('valb', (Qb, 3))
+				e.forward(bdata, valb, None, accumulate=False, perm=bins_b)
+				acc_b, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
+												  {'normals': bnormal}, None, tag='acc_b', want_losses=True, sample_gs=sgs)
+				lpb, nblkb = e.last_loss_partials
+				done_b = torch.cuda.Event()
+				done_b.record(s_bnd)
+			srcs_b.append((lpb, nblkb, [0., 0., 0., self.boundary_lambda / Qb, 0., 0., 0., 0.]))
 			extra.append(acc_b)
+		bins = e.bin_samples(data, True, gs_dev=sgs)
+		perm, scs = bins
+		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
+		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
+		binned = torch.cuda.Event()
+		binned.record(main)
+		s_fwd.wait_event(binned)
+		with torch.cuda.stream(s_fwd):
+			e.forward(data, val, grad, accumulate=False, perm=bins)
+			done_f = torch.cuda.Event()
+			done_f.record(s_fwd)
+		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)	# beside the forward pass
+		main.wait_event(done_f)
+		acc, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
+									  {'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, want_losses=True, sample_gs=sgs)
+		lp, nblk = e.last_loss_partials
+		srcs = [(lp, nblk, [self.w['vor'] / Q, 0., self.w['div'] / Q, 0., 0., 0., 0., 0.])] + srcs_b
+		if done_b is not None:
+			main.wait_event(done_b)
 		self.stepper.step([p.detach() for p in gv._params()], acc, mask, extra=extra, loss_srcs=srcs, rebuild=True)	# update + hash + packed records
 
 	def evaluate(self, data, probe=None):
@@ -352,32 +374,48 @@ def project(gaussian_velocity, reference_field, x_min, x_max, y_min, y_max, z_mi
 	stale = {k: 0 for k in names}
 	st_time = time.time()
 	epochs = max_epoch
-	for epoch in range(max_epoch):
-		data = data_generator(batch_size, gv)
-		boundary = boundary_generator(batch_size) if (boundary_lambda and boundary_generator) else None
-		fp.iterate(data, boundary)
-		if epoch % check_iter == check_iter - 1:
-			t = fp.evaluate(test_data_generator(gv)).tolist()	# the only host sync of the loop
-			cur = dict(zip(names, t[:3]))
-			if history is not None:
-				history.setdefault('test', []).append(cur)
-				history.setdefault('state', []).append(fp.stepper.scalars()[:16])
+	use_b = bool(boundary_lambda and boundary_generator)
+
+	def batches():
+		return data_generator(batch_size, gv), (boundary_generator(batch_size) if use_b else None)
+
+	def iteration(inputs):
+		fp.iterate(*inputs)
+	# generators that are pure device functions of the CUDA random stream (`graph_safe = True`: init_cond3d.make_boundary_sampler's are)
+	# let the loop replay from CUDA graphs, ten iterations each (whole pairs: the sample grids alternate with the iteration's parity)
+	from .graphloop import GraphedLoop
+	safe = getattr(data_generator, 'graph_safe', False) and (not use_b or getattr(boundary_generator, 'graph_safe', False))
+	unit = next((u for u in (10, 4, 2) if check_iter % u == 0), 0)
+	loop = GraphedLoop(iteration, unit=unit or 1, enabled=bool(use_graph and safe and unit), prepare=batches)
+	done = 0
+	while done < max_epoch:
+		k = min(check_iter, max_epoch - done)
+		loop.run(k)
+		done += k
+		if k < check_iter:
+			break
+		t = fp.evaluate(test_data_generator(gv)).tolist()	# the only host sync of the loop
+		cur = dict(zip(names, t[:3]))
+		if history is not None:
+			history.setdefault('test', []).append(cur)
+			history.setdefault('state', []).append(fp.stepper.scalars()[:16])
+		if verbose:
+			print(f'[projection] loss_vor: {t[0]}, loss_hel: {t[1]}, loss_div: {t[2]}, time: {time.time() - st_time}')
+			st_time = time.time()
+		for kk in names:
+			if cur[kk] < best[kk] * (1. - 1e-3):
+				best[kk], stale[kk] = cur[kk], 0
+			else:
+				stale[kk] += check_iter
+		if all(stale[kk] >= patience for kk in names):
+			epochs = done
 			if verbose:
-				print(f'[projection] loss_vor: {t[0]}, loss_hel: {t[1]}, loss_div: {t[2]}, time: {time.time() - st_time}')
-				st_time = time.time()
-			for k in names:
-				if cur[k] < best[k] * (1. - 1e-3):
-					best[k], stale[k] = cur[k], 0
-				else:
-					stale[k] += check_iter
-			if all(stale[k] >= patience for k in names):
-				epochs = epoch + 1
-				if verbose:
-					print('[projection] Total epoch:', epochs)
-				break
+				print('[projection] Total epoch:', epochs)
+			break
 	else:
 		if verbose:
 			print('[projection] Total epoch:', max_epoch, '(Reached maximum iteration number)')
+	loop.release()
 	fp.finish()
 	return epochs
 

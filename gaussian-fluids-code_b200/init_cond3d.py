@@ -119,16 +119,17 @@ def sample_on_box(n, x_min, x_max, y_min, y_max, z_min, z_max):
 	n points on the faces of the box, area-weighted, with inward normals (3D/init_cond.py:227-249).
 	Written without boolean-mask indexing so that it never synchronises the host (the reference's version does).
 	"""
+	from .init_cond2d import _const	# constants uploaded once: no host->device copy per call, capturable into a CUDA graph
 	device = gsr3d.device
 	sx, sy, sz = x_max - x_min, y_max - y_min, z_max - z_min
-	areas = torch.tensor([sy * sz, sy * sz, sz * sx, sz * sx, sx * sy, sx * sy], device=device)
+	areas = _const([sy * sz, sy * sz, sz * sx, sz * sx, sx * sy, sx * sy], device)
 	t = torch.rand(n, device=device) * areas.sum()
 	face = torch.bucketize(t, torch.cumsum(areas, 0)[:-1], right=True)	# 0..5: x_min, x_max, y_min, y_max, z_min, z_max
-	uvw = torch.rand((n, 3), device=device) * torch.tensor([sx, sy, sz], device=device) + torch.tensor([x_min, y_min, z_min], device=device)
+	uvw = torch.rand((n, 3), device=device) * _const([sx, sy, sz], device) + _const([x_min, y_min, z_min], device)
 	axis = face // 2
 	upper = (face % 2).to(torch.float32)
-	lo = torch.tensor([x_min, y_min, z_min], device=device)[axis]
-	hi = torch.tensor([x_max, y_max, z_max], device=device)[axis]
+	lo = _const([x_min, y_min, z_min], device)[axis]
+	hi = _const([x_max, y_max, z_max], device)[axis]
 	onehot = torch.nn.functional.one_hot(axis, 3).to(torch.float32)
 	data = uvw * (1. - onehot) + onehot * (lo + upper * (hi - lo))[:, None]
 	normal = onehot * (1. - 2. * upper)[:, None]
@@ -141,6 +142,7 @@ def make_boundary_sampler(init_cond, obj_file=None):
 	assets/bunny.obj is not shipped with it)."""
 	x_min, x_max, y_min, y_max, z_min, z_max = domain[init_cond]
 	box = lambda n: sample_on_box(n, x_min, x_max, y_min, y_max, z_min, z_max)
+	box.graph_safe = True	# pure device functions of torch's CUDA random stream / a device-resident draw counter (graphloop.py)
 	info = other_info[init_cond]
 	if 'obj_file' not in info:
 		return box
@@ -152,4 +154,5 @@ def make_boundary_sampler(init_cond, obj_file=None):
 		d2, n2 = mesh.sample(n)
 		return torch.cat([d1, d2], dim=0), torch.cat([n1, n2], dim=0)
 	both.mesh = mesh
+	both.graph_safe = True
 	return both

@@ -147,3 +147,33 @@ def test_advance_loop_writes_the_reference_files(tmp_path):
 	d = torch.load(os.path.join(str(tmp_path), 'gaussian_velocity_2.pt'))
 	assert set(d) >= {'positions', 'scalings', 'rotations', 'values', 'clamp_threshold', 'min_grid_scale', 'domain_range'}
 	np.testing.assert_array_equal(d['positions'].detach().cpu().numpy(), a.positions.detach().cpu().numpy())
+
+
+def test_project_with_graph_safe_callables_replays_from_graphs_and_equals_eager():
+	"""advance3d.project with generators that are NOT the stock sampler objects — the scene's own boundary sampler
+	(init_cond3d.make_boundary_sampler: box, or box + obstacle mesh) and a plain callable — but carry `graph_safe = True`: the eager
+	fused iteration is replayed from CUDA graphs (graphloop.py), bit for bit what the same call computes eagerly"""
+	from gaussian_fluids_code_b200 import advance3d, graphloop, gsr3d, init_cond3d
+	from gaussian_fluids_code_b200.synth import make_fast3d, synthetic_field
+	gsr3d.device = torch.device('cuda', 0)
+	P, S, R, V, mgs, _ = synthetic_field(8)
+	box = (0., 1.) * 3
+	test_gen = advance3d.LatticeGenerator(*box, 16, 16, 16)
+	bgen = init_cond3d.make_boundary_sampler('leapfrog')
+	assert bgen.graph_safe
+	res = []
+	for use_graph in (False, True):
+		torch.manual_seed(21)
+		cur, new = make_fast3d(P, S, R, V, 5e-3, mgs), make_fast3d(P, S, R, V, 5e-3, mgs)
+		advance3d.advect_covector_field(new, cur, .02, new.x_min, new.x_max, new.y_min, new.y_max, new.z_min, new.z_max)
+		ref = advance3d.AdvectedCovectorField(cur, cur, .02, *box)
+		dgen = lambda n, gv: torch.rand_like(gv.positions.detach())
+		dgen.graph_safe = True
+		g0 = graphloop.GRAPH_LAUNCHES
+		ep = advance3d.project(new, ref, *box, dgen, test_gen, boundary_generator=bgen, boundary_lambda=10., batch_size=2048, max_epoch=60, patience=10 ** 9,
+							   verbose=0, check_iter=20, use_graph=use_graph)
+		assert ep == 60 and (graphloop.GRAPH_LAUNCHES > g0) == use_graph
+		assert not hasattr(new, '_pipelines') or not new._pipelines	# not the stock-sampler pipeline
+		res.append([p.detach().cpu().numpy().copy() for p in new._params()] + [np.float64(new.grid_scale)])
+	for a, b in zip(*res):
+		np.testing.assert_array_equal(a, b)
