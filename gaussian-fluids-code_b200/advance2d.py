@@ -203,27 +203,34 @@ class FusedProjector2D:
 		main = torch.cuda.current_stream()
 		if self._streams is None:
 			self._streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
-		s_fwd, s_b1, s_b2 = self._streams
-		fork = torch.cuda.Event()
-		fork.record(main)
+		# (forked only while being captured: eagerly the host is the bottleneck and the event calls would only slow it down)
+		multi = torch.cuda.is_current_stream_capturing()
+		s_fwd, s_b1, s_b2 = self._streams if multi else (main, main, main)
+		fork = done_f = None
+		if multi:
+			fork = torch.cuda.Event()
+			fork.record(main)
 		srcs_b, extra, joins = [], [], []
 		if lam > 0. and boundary_1 is not None:	# prescribed velocity on an obstacle (2D/advance.py:217-220)
 			bdata, bvalue = [t.detach() for t in boundary_1]
-			s_b1.wait_event(fork)
+			if multi:
+				s_b1.wait_event(fork)
 			with torch.cuda.stream(s_b1):
 				bins1 = e.bin_samples(bdata, True, tag='b1')
 				val1 = self._tmp('val1', (bdata.shape[0], 2))
 				e.forward(bdata, val1, None, accumulate=False, perm=bins1)
 				acc1, _ = e.backward_gather(bdata, bins1.perm, bins1.scs, val1, None, (lam, 0., 0., 0., 0., 0.), {'ref_val': bvalue}, None, tag='acc_b1', want_losses=True)
 				lp1, nb1 = e.last_loss_partials
-				ev = torch.cuda.Event()
-				ev.record(s_b1)
-				joins.append(ev)
+				if multi:
+					ev = torch.cuda.Event()
+					ev.record(s_b1)
+					joins.append(ev)
 			srcs_b.append((lp1, nb1, [0., 0., 0., 0., lam / bdata.shape[0], 0., 0., 0.]))
 			extra.append(acc1)
 		if lam > 0. and boundary_2 is not None:	# prescribed normal velocity (2D/advance.py:231-235)
 			bdata2, bnormal, bref = [t.detach() for t in boundary_2]
-			s_b2.wait_event(fork)
+			if multi:
+				s_b2.wait_event(fork)
 			with torch.cuda.stream(s_b2):
 				bins2 = e.bin_samples(bdata2, True, tag='b2')
 				val2 = self._tmp('val2', (bdata2.shape[0], 2))
@@ -231,22 +238,26 @@ class FusedProjector2D:
 				acc2, _ = e.backward_gather(bdata2, bins2.perm, bins2.scs, val2, None, (0., lam, 0., 0., 0., 0.), {'normals': bnormal, 'normal_ref': bref}, None,
 											tag='acc_b2', want_losses=True)
 				lp2, nb2 = e.last_loss_partials
-				ev = torch.cuda.Event()
-				ev.record(s_b2)
-				joins.append(ev)
+				if multi:
+					ev = torch.cuda.Event()
+					ev.record(s_b2)
+					joins.append(ev)
 			srcs_b.append((lp2, nb2, [0., 0., 0., lam / bdata2.shape[0], 0., 0., 0., 0.]))
 			extra.append(acc2)
 		bins = e.bin_samples(data, True)
 		grad = self._tmp('grad', (Q, 2, 2))
-		binned = torch.cuda.Event()
-		binned.record(main)
-		s_fwd.wait_event(binned)
+		if multi:
+			binned = torch.cuda.Event()
+			binned.record(main)
+			s_fwd.wait_event(binned)
 		with torch.cuda.stream(s_fwd):
 			e.forward(data, None, grad, accumulate=False, perm=bins)
-			done_f = torch.cuda.Event()
-			done_f.record(s_fwd)
+			if multi:
+				done_f = torch.cuda.Event()
+				done_f.record(s_fwd)
 		ref_vor = self._ref_vorticity(data)	# beside the forward pass
-		main.wait_event(done_f)
+		if multi:
+			main.wait_event(done_f)
 		acc, mask = e.backward_gather(data, bins.perm, bins.scs, None, grad, (0., 0., 0., self.w['vor'], 0., self.w['div']), {'ref_vor': ref_vor}, None, want_losses=True)
 		lp, nblk = e.last_loss_partials
 		srcs = [(lp, nblk, [self.w['vor'] / Q, 0., self.w['div'] / Q, 0., 0., 0., 0., 0.])] + srcs_b

@@ -249,15 +249,21 @@ class FusedProjector:
 		main = torch.cuda.current_stream()
 		if self._streams is None:
 			self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
-		s_fwd, s_bnd = self._streams
-		fork = torch.cuda.Event()
-		fork.record(main)
+		# (eagerly the host is the bottleneck: forking streams only adds event calls — 375 instead of 200 ms per S1 frame — so the
+		# chains are forked only while the iteration is being captured, where the graph then runs them side by side)
+		multi = torch.cuda.is_current_stream_capturing()
+		s_fwd, s_bnd = self._streams if multi else (main, main)
+		fork = binned = done_f = None
+		if multi:
+			fork = torch.cuda.Event()
+			fork.record(main)
 		extra, srcs_b, done_b = [], [], None
 		if boundary is not None and self.boundary_lambda:
 			bdata, bnormal = boundary
 			bdata, bnormal = bdata.detach(), bnormal.detach()
 			Qb = bdata.shape[0]
-			s_bnd.wait_event(fork)
+			if multi:
+				s_bnd.wait_event(fork)
 			with torch.cuda.stream(s_bnd):
 				bins_b = e.bin_samples(bdata, True, tag='b', gs_dev=sgs)
 				perm_b, scs_b = bins_b
@@ -266,23 +272,27 @@ class FusedProjector:
 				acc_b, mask_b = e.backward_gather(bdata, perm_b, scs_b, valb, None, (0., self.boundary_lambda, 0., 0., 0., 0.),
 												  {'normals': bnormal}, None, tag='acc_b', want_losses=True, sample_gs=sgs)
 				lpb, nblkb = e.last_loss_partials
-				done_b = torch.cuda.Event()
-				done_b.record(s_bnd)
+				if multi:
+					done_b = torch.cuda.Event()
+					done_b.record(s_bnd)
 			srcs_b.append((lpb, nblkb, [0., 0., 0., self.boundary_lambda / Qb, 0., 0., 0., 0.]))
 			extra.append(acc_b)
 		bins = e.bin_samples(data, True, gs_dev=sgs)
 		perm, scs = bins
 		ref_vor, ref_hel = self._tmp('ref_vor', (Q, 3)), self._tmp('ref_hel', (Q,))
 		val, grad = self._tmp('val', (Q, 3)), self._tmp('grad', (Q, 3, 3))
-		binned = torch.cuda.Event()
-		binned.record(main)
-		s_fwd.wait_event(binned)
+		if multi:
+			binned = torch.cuda.Event()
+			binned.record(main)
+			s_fwd.wait_event(binned)
 		with torch.cuda.stream(s_fwd):
 			e.forward(data, val, grad, accumulate=False, perm=bins)
-			done_f = torch.cuda.Event()
-			done_f.record(s_fwd)
+			if multi:
+				done_f = torch.cuda.Event()
+				done_f.record(s_fwd)
 		cur._engine.advected_vorticity(data, -self.ref.time_step, ref_vor, ref_hel, perm=bins)	# beside the forward pass
-		main.wait_event(done_f)
+		if multi:
+			main.wait_event(done_f)
 		acc, mask = e.backward_gather(data, perm, scs, val, grad, (0., 0., 0., self.w['vor'], self.w['hel'], self.w['div']),
 									  {'ref_vor': ref_vor, 'ref_hel': ref_hel}, None, want_losses=True, sample_gs=sgs)
 		lp, nblk = e.last_loss_partials
