@@ -48,6 +48,7 @@ def parse():
 	ap.add_argument('--workload', type=str, default='timestep', choices=('timestep', 'density'))
 	ap.add_argument('--density-res', type=int, default=512)
 	ap.add_argument('--no-cpu-baseline', action='store_true')
+	ap.add_argument('--no-unhoisted', action='store_true', help='skip the comparison run with the test reference recomputed at every test pass')
 	ap.add_argument('--no-kernel-table', action='store_true')
 	ap.add_argument('--no-graph', action='store_true', help='run the project iterations eagerly instead of replaying a CUDA graph')
 	return ap.parse_args()
@@ -337,7 +338,7 @@ def kernel_table(ts, args, peaks, step_ms):
 	Ql = lat.shape[0]
 	rv, rh = torch.empty((Ql, 3), device=dev), torch.empty((Ql,), device=dev)
 	bins_l = ce.bin_samples(lat, False)
-	row('RK4 pull-back on the test lattice (gsr_advected_vorticity, 5 evaluations)', iters // 100, timeit_graph(lambda: ce.advected_vorticity(lat, -ts.dt, rv, rh, perm=bins_l)),
+	row('RK4 pull-back on the test lattice (gsr_advected_vorticity, 5 evaluations)', 1 if advance3d.HOIST_TEST_REFERENCE else iters // 100, timeit_graph(lambda: ce.advected_vorticity(lat, -ts.dt, rv, rh, perm=bins_l)),
 		flop=5 * (24 * Cl + 28 * Pl))
 	val_l, grad_l = torch.empty((Ql, 3), device=dev), torch.empty((Ql, 3, 3), device=dev)
 	row('forward u + grad u on the test lattice (gsr_forward)', iters // 100 + 2, timeit_graph(lambda: ce.forward(lat, val_l, grad_l, False, perm=bins_l)), flop=24 * Cl + 28 * Pl)
@@ -494,7 +495,7 @@ def run_ours(args):
 	torch.cuda.set_device(local)
 	if world > 1:
 		dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-	from gaussian_fluids_code_b200 import _lib, gsr3d, timestep3d
+	from gaussian_fluids_code_b200 import _lib, advance3d, gsr3d, timestep3d
 	gsr3d.device = torch.device('cuda', local)
 	lib = _lib.lib()
 	n = SIZES[args.size]
@@ -517,6 +518,8 @@ def run_ours(args):
 	host_out = [torch.empty_like(p).pin_memory() for p in host_params]
 	host_fields = [torch.empty(ts.lattice.shape[0], dtype=torch.float32).pin_memory() for _ in range(2)]
 
+	skipped_job = [0]
+
 	def census_of(t):
 		"""job totals (C, P): weak — every rank's visits; strong — one copy of the replicated training visits + all lattice shares"""
 		cen = timestep3d.Census(dev)
@@ -524,10 +527,13 @@ def run_ours(args):
 		t.step(cen)
 		C_all, P_all = cen.value()
 		C_lat, P_lat = cen.lattice_value()
+		C_skip, _ = cen.skipped_value()	# lattice visits of the reference's algorithm this engine does not make (never part of C_all)
 		if world == 1:
+			skipped_job[0] = C_skip
 			return C_all, P_all
-		tot = torch.tensor([C_all, P_all, C_lat, P_lat], dtype=torch.int64, device=dev)
+		tot = torch.tensor([C_all, P_all, C_lat, P_lat, C_skip], dtype=torch.int64, device=dev)
 		dist.all_reduce(tot)
+		skipped_job[0] = int(tot[4])
 		if t.scaling == 'weak':
 			return int(tot[0]), int(tot[1])
 		return C_all - C_lat + int(tot[2]), P_all - P_lat + int(tot[3])
@@ -538,6 +544,7 @@ def run_ours(args):
 		ts.reset()
 		ts.step()
 	C_job, P_job = census_of(ts)
+	C_skipped = skipped_job[0]
 
 	# ---- timed region: device-resident inputs -------------------------------------------------------------------
 	sampler = ClockSampler(local)
@@ -560,6 +567,23 @@ def run_ours(args):
 	ms_e2e = timed_steps(ts, args, barrier, dev, world, dist, host_params, host_out, host_fields)
 	h2d = sum(p.numel() * 4 for p in host_params)
 	d2h = sum(p.numel() * 4 for p in host_out) + sum(f.numel() * 4 for f in host_fields)
+
+	# ---- the same steps with the test lattice's pull-back reference recomputed at every test pass, as the reference does (and as
+	# this engine did until the hoist): same results, the round-1 work mix — kept beside the headline for comparison -------------
+	unhoisted = None
+	if advance3d.HOIST_TEST_REFERENCE and not args.no_unhoisted:
+		advance3d.HOIST_TEST_REFERENCE = False
+		try:
+			ts.reset()
+			ts.step()
+			C_u, P_u = census_of(ts)
+			ms_u = timed_steps(ts, args, barrier, dev, world, dist)
+		finally:
+			advance3d.HOIST_TEST_REFERENCE = True
+		unhoisted = {'what': 'GSR_HOIST_TEST_REFERENCE=0: the RK4 pull-back reference on the fixed test lattice evaluated at each of the test passes of a frame '
+							 '(3D/advance.py:290-291 recomputes it) instead of once per frame; bitwise the same losses and fields',
+					 'ms_per_step': ms_u / args.steps, 'timesteps_per_s': args.steps / (ms_u * 1e-3), 'value': C_u * args.steps / (ms_u * 1e-3), 'unit': UNIT,
+					 'pair_evals_per_step': C_u, 'accepted_pairs_per_step': P_u}
 
 	# ---- the other scaling mode (N > 1): the fixed frame with its lattice shared between the ranks --------------------
 	other = None
@@ -631,7 +655,9 @@ def run_ours(args):
 	except Exception:
 		pass
 	step_flop = 24 * C_job + 28 * P_job
-	roofline = {'bound': 'fp32', 'kernel': 'rk4 pull-back of the previous field on the test lattice (gsr_advected_vorticity: rk4_tiled3s_kernel<2> at S1, 5 field evaluations per point)',
+	roofline = {'bound': 'fp32', 'kernel': ('rk4 pull-back of the previous field on the test lattice (gsr_advected_vorticity: rk4_tiled3s_kernel<2> at S1, 5 field evaluations per point): '
+											'the largest single launch and the FP32-bound kernel of the step; share_of_step says how much of the step it is (one launch per frame since the '
+											'test reference is hoisted) — most of the step is the latency-bound iteration cycle, see kernels[] and step_frac'),
 				'achieved': achieved, 'peak': fma.value, 'unit': 'TFLOP/s', 'frac': (achieved / fma.value) if achieved else None,
 				'traffic': traffic, 'traffic_source': 'profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of a committed ncu --set full capture of this kernel on this workload); null when this workload was not captured',
 				'peak_source': 'FP32 FFMA peak measured live by gsr_peak_fma on this GPU (MEASURED_PEAKS.json holds only HBM and bf16 peaks); nominal 74.4 at 1965 MHz',
@@ -657,9 +683,13 @@ def run_ours(args):
 																			 if os.environ.get('GSR_EXCHANGE', 'p2p') == 'p2p' else 'NCCL all-reduce'))
 								if main_mode == 'weak' else f'strong: the fixed frame, its {args.test_res}^3 lattice split over {world} ranks, training replicated') if world > 1 else 'single GPU',
 				   'l2_policy': 'every step sweeps > 126 MB (test lattice passes write 2.1M x 12 floats; the iterations rewrite all buffers), inputs regenerated each iteration',
-				   'work_census': 'candidate visits counted on the last warm-up step (gsr_count_pairs), RK4 counted as 4 or 5 evaluations of its start points'},
+				   'work_census': 'candidate visits EXECUTED, counted on the last warm-up step (gsr_count_pairs), RK4 counted as 4 or 5 evaluations of its start points',
+				   'test_reference': ('the pull-back reference on the fixed test lattice is evaluated by the first test pass of every frame and reused by the other '
+									  'passes of that frame (nothing is carried from one frame to the next); the visits this saves are NOT counted in value '
+									  '(pair_evals_not_executed_per_step); "unhoisted" holds the same steps with the recomputation')
+									 if advance3d.HOIST_TEST_REFERENCE else 'recomputed at every test pass (GSR_HOIST_TEST_REFERENCE=0)'},
 		'timesteps_per_s': args.steps / (ms * 1e-3), 'project_iters_per_s': args.steps * args.iters / (ms * 1e-3),
-		'pair_evals_per_step': C_job, 'accepted_pairs_per_step': P_job,
+		'pair_evals_per_step': C_job, 'accepted_pairs_per_step': P_job, 'pair_evals_not_executed_per_step': C_skipped,
 		'e2e': {'value': C_job * args.steps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
 				'ms_per_step': ms_e2e / args.steps, 'timesteps_per_s': args.steps / (ms_e2e * 1e-3)},
 		'gpu_launches': int(n_launches),
@@ -669,6 +699,9 @@ def run_ours(args):
 	}
 	if other is not None:
 		out['strong_scaling'] = other
+	if unhoisted is not None:
+		unhoisted['step_frac'] = (24 * unhoisted['pair_evals_per_step'] + 28 * unhoisted['accepted_pairs_per_step']) / (unhoisted['ms_per_step'] * 1e-3) / (fma.value * 1e12) / world
+		out['unhoisted'] = unhoisted
 	if world == 1 and not args.no_cpu_baseline:
 		out['cpu_baseline'] = cpu_baseline(args, n, N)
 	print(json.dumps(out))

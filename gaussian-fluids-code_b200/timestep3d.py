@@ -66,12 +66,22 @@ class Census:
 	def __init__(self, device):
 		self.c = torch.zeros(2, dtype=torch.int64, device=device)	# [candidate visits C, accepted pairs P], everything
 		self.lat = torch.zeros(2, dtype=torch.int64, device=device)	# the lattice passes' share of it
+		self.skipped = torch.zeros(2, dtype=torch.int64, device=device)	# NOT executed (and not in c): the reference's repeated pull-backs of the fixed lattice
 
-	def count(self, engine, x, evals, lattice=False):
+	def count(self, engine, x, evals, lattice=False, executed=True):
+		"""executed=False: visits the reference's algorithm makes at this point and this engine does not (the reused pull-back reference
+		of the test lattice): kept apart in `skipped`, never part of the executed totals"""
+		if not executed:
+			engine.count_pairs(x, self.skipped, evals, True)
+			return
 		before = self.c.clone() if lattice else None
 		engine.count_pairs(x, self.c, evals, True)
 		if lattice:
 			self.lat += self.c - before
+
+	def skipped_value(self):
+		c = self.skipped.tolist()
+		return int(c[0]), int(c[1])
 
 	def value(self):
 		c = self.c.tolist()
@@ -198,6 +208,7 @@ class ShardedProjector(advance3d.FusedProjector):
 			keep_clock, self._drop_clock = False, False
 		self.stepper.init(self.gv.scalings, keep_clock=keep_clock)
 		self._it = 0
+		self._test_ref_key = None	# the previous field has changed: the first test pass of the phase evaluates its pull-back reference anew
 		self._rebuild()
 		cur = self.ref.velocity_field
 		cur._engine._packed_key = None
@@ -470,15 +481,16 @@ class ShardedProjector(advance3d.FusedProjector):
 				body(k, census)
 				done += k
 
-	def evaluate_global(self, data, total=None, probe=None, census=None):
-		"""the test losses over the WHOLE lattice: `data` is this rank's share, `total` the number of points of all ranks"""
+	def evaluate_global(self, data, total=None, probe=None, census=None, fixed=False):
+		"""the test losses over the WHOLE lattice: `data` is this rank's share, `total` the number of points of all ranks; fixed: see
+		FusedProjector.evaluate (the pull-back reference of a fixed lattice is evaluated by the first test pass of the phase only)"""
 		Q = data.shape[0]
 		if self.peer:
 			self.peer.check()	# (this call synchronises anyway) a lost peer is reported within check_iter iterations, not at the end of the phase
 		self.check_sample_grid()
-		sums = self.evaluate(data, probe=probe) * Q
+		sums = self.evaluate(data, probe=probe, fixed=fixed) * Q
 		if census is not None:
-			census.count(self.ref.velocity_field._engine, data, 5, lattice=True)
+			census.count(self.ref.velocity_field._engine, data, 5, lattice=True, executed=not self.reference_reused)
 			census.count(self.gv._engine, data, 1, lattice=True)
 		if self.lattice_world > 1:
 			torch.distributed.all_reduce(sums)

@@ -37,6 +37,25 @@ def test_graph_replay_equals_eager_execution(steps):
 	assert np.isfinite(a[-1][0]).all() and np.abs(a[-1][0] - a[0][0]).max() > 0	# the field moved between the steps
 
 
+def test_hoisted_test_reference_equals_the_recomputed_one(monkeypatch):
+	"""the pull-back reference on the fixed test lattice is evaluated by the first test pass of a frame and reused by the later passes
+	of that frame (the reference, 3D/advance.py:290-291, recomputes it): bitwise the same test losses, parameters and output fields
+	over several frames — which also shows that a new frame (new previous field, same objects and pointers) evaluates it anew"""
+	from gaussian_fluids_code_b200 import advance3d
+	monkeypatch.setattr(advance3d, 'HOIST_TEST_REFERENCE', True)
+	ts, a = run(True, steps=4)
+	fp = next(iter(ts.cur.__dict__.get('_pipelines', {}).values()), None) or next(iter(ts.new._pipelines.values()))
+	assert fp.reference_reused	# the last test pass of the last frame did not launch the pull-back
+	monkeypatch.setattr(advance3d, 'HOIST_TEST_REFERENCE', False)
+	ts, b = run(True, steps=4)
+	fp = next(iter(ts.cur.__dict__.get('_pipelines', {}).values()), None) or next(iter(ts.new._pipelines.values()))
+	assert not fp.reference_reused
+	for sa, sb in zip(a, b):
+		for x, y in zip(sa, sb):
+			np.testing.assert_array_equal(x, y)
+	assert np.abs(a[-1][-1] - a[0][-1]).max() > 0	# the test losses differ between the frames
+
+
 def test_step_is_reproducible_after_reset():
 	ts, first = run(True, steps=1)
 	ts.reset()
