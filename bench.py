@@ -6,7 +6,7 @@ bench.py — measures the Gaussian-Fluids hot path on B200 (contract: the task s
                   [--dim 3|2 --scene taylor_green|leapfrog|karman] [--workload timestep|density] [--impl ours|reference]
 
 A "step" is one fixed-work 3D leapfrog time step run through the public API, advance3d.advance_frame: clone + advect +
-`iters` project iterations (+ boundary passes) + a test pass every 100 iterations + the two output-field passes.
+`iters` project iterations (+ boundary passes) + a test pass every 100 iterations + the output-field pass (|vorticity| and divergence from one gradient).
 `value` = Gaussian-sample pair evaluations per second, whole job (all ranks); `timesteps_per_s` rides along.
 `e2e` is the same call with the Gaussian parameters coming from pinned HOST buffers each step and the updated parameters plus the
 two output fields copied back to the host inside the timed region.
@@ -341,7 +341,7 @@ def kernel_table(ts, args, peaks, step_ms):
 	row('RK4 pull-back on the test lattice (gsr_advected_vorticity, 5 evaluations)', 1 if advance3d.HOIST_TEST_REFERENCE else iters // 100, timeit_graph(lambda: ce.advected_vorticity(lat, -ts.dt, rv, rh, perm=bins_l)),
 		flop=5 * (24 * Cl + 28 * Pl))
 	val_l, grad_l = torch.empty((Ql, 3), device=dev), torch.empty((Ql, 3, 3), device=dev)
-	row('forward u + grad u on the test lattice (gsr_forward)', iters // 100 + 2, timeit_graph(lambda: ce.forward(lat, val_l, grad_l, False, perm=bins_l)), flop=24 * Cl + 28 * Pl)
+	row('forward u + grad u on the test lattice (gsr_forward)', iters // 100 + 1, timeit_graph(lambda: ce.forward(lat, val_l, grad_l, False, perm=bins_l)), flop=24 * Cl + 28 * Pl)
 	del rv, rh, val_l, grad_l
 	# training batch Q = N
 	Cx, Px = census(e, x)

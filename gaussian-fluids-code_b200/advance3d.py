@@ -520,11 +520,13 @@ def advance_frame(gaussian_velocity, new_gaussian_velocity, x_min, x_max, y_min,
 	out = None
 	if fields:
 		lattice = test_data_generator(gv)
-		vor = curl(gv.gradient(lattice)).norm(dim=-1)	# the reference evaluates the gradient once per written field (:374-377, :389-390)
-		div = gv.gradient(lattice).diagonal(dim1=-2, dim2=-1).sum(dim=-1)
+		grad = gv.gradient(lattice)	# ONE pass for both fields (the reference evaluates it once per written field, :374-377, :389-390: same values)
+		vor = curl(grad).norm(dim=-1)
+		div = grad.diagonal(dim1=-2, dim2=-1).sum(dim=-1)
+		del grad
 		census = project_kw.get('census')
 		if census is not None:
-			census.count(gv._engine, lattice, 2, lattice=True)
+			census.count(gv._engine, lattice, 1, lattice=True)
 		out = (vor, div)
 	return gv, new, epochs, out
 

@@ -21,6 +21,12 @@ advance3d.FusedProjector.evaluate = timed('evaluate(lattice)', advance3d.FusedPr
 gsr3d.GaussianSplatting3DFast.gradient = timed('gradient(lattice)', gsr3d.GaussianSplatting3DFast.gradient)
 advance3d.advect_covector_field = timed('advect', advance3d.advect_covector_field)
 engine.HashEngine.bin_samples = timed('bin_samples', engine.HashEngine.bin_samples)
+advance3d.clone_velocity_field = timed('clone', advance3d.clone_velocity_field)
+advance3d._project_pipelined = timed('project (all of it)', advance3d._project_pipelined)
+for name in ('run_iterations', 'restart', 'begin', 'evaluate_global'):
+	setattr(timestep3d.ShardedProjector, name, timed(name, getattr(timestep3d.ShardedProjector, name)))
+advance3d.FusedProjector.finish = timed('finish', advance3d.FusedProjector.finish)
+advance3d.curl = timed('curl', advance3d.curl)
 for rep in range(3):
 	acc.clear()
 	ts.reset()
