@@ -9,4 +9,4 @@ evaluating the Gaussian Spatial Representation and running its per-timestep opti
 
 Import as `gaussian_fluids_code_b200` (see the shim module of that name at the repo root).
 """
-__version__ = '0.1.0'
+__version__ = '0.2.0'

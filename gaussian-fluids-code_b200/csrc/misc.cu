@@ -208,4 +208,4 @@ extern "C" int gsr_pipe_probe(int which, int iters, double *ops_per_s, void *str
 
 extern "C" uint64_t gsr_launch_count(void) { return g_launches.load(); }
 
-extern "C" const char *gsr_version(void) { return "gsr_b200 0.1.0 (sm_100a)"; }
+extern "C" const char *gsr_version(void) { return "gsr_b200 0.2.0 (sm_100a)"; }
