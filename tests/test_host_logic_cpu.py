@@ -61,3 +61,52 @@ def test_domain_boundary_sampler_tables_cover_the_four_edges():
 	frac = np.array([((n[:, 0] == a) & (n[:, 1] == b)).mean() for a, b in ((0., -1.), (1., 0.), (0., 1.), (-1., 0.))])
 	want = np.array([x_max - x_min, y_max - y_min, x_max - x_min, y_max - y_min]) / per
 	assert np.abs(frac - want).max() < 1.5e-2
+
+
+def test_test_pass_reference_is_reused_only_for_fixed_points_within_a_phase(monkeypatch):
+	"""FusedProjector.evaluate (host logic, engines stubbed): the pull-back reference of the test points is evaluated again unless the
+	caller vouches that the points are fixed, the phase is the same (restart() drops the key), the previous field and time step
+	are the same objects / values, and GSR_HOIST_TEST_REFERENCE is on"""
+	import types
+	import torch
+	from gaussian_fluids_code_b200 import advance3d
+
+	calls = []
+
+	class Engine:
+		def bin_samples(self, data, need_cells):
+			return types.SimpleNamespace(perm=None)
+
+		def advected_vorticity(self, data, dt, ref_vor, ref_hel, perm=None):
+			calls.append(float(dt))
+
+		def forward(self, data, val, grad, accumulate=False, perm=None):
+			pass
+
+		def sample_losses(self, val, grad, refs, Q):
+			return torch.ones(3) * Q
+
+	bufs = {}
+	fp = types.SimpleNamespace(gv=types.SimpleNamespace(_engine=Engine()), ref=types.SimpleNamespace(velocity_field=types.SimpleNamespace(_engine=Engine()), time_step=.02),
+							   _tmp=lambda name, shape: bufs.setdefault((name, shape), torch.zeros(shape)))
+	ev = lambda data, **kw: advance3d.FusedProjector.evaluate(fp, data, **kw)
+	lattice, other = torch.zeros((8, 3)), torch.zeros((8, 3))
+	monkeypatch.setattr(advance3d, 'HOIST_TEST_REFERENCE', True)
+	ev(lattice, fixed=True); ev(lattice, fixed=True); ev(lattice, fixed=True)
+	assert len(calls) == 1 and fp.reference_reused
+	ev(lattice)	# a plain callable's points: never reused, and the next fixed call may not trust the buffer either
+	assert len(calls) == 2 and not fp.reference_reused
+	ev(lattice, fixed=True); ev(lattice, fixed=True)
+	assert len(calls) == 3
+	ev(other, fixed=True)	# other points
+	assert len(calls) == 4
+	fp._test_ref_key = None	# what ShardedProjector.restart() does at the start of a phase
+	ev(other, fixed=True)
+	assert len(calls) == 5
+	fp.ref.time_step = .01	# another time step
+	ev(other, fixed=True)
+	assert len(calls) == 6 and calls[-1] == -.01
+	monkeypatch.setattr(advance3d, 'HOIST_TEST_REFERENCE', False)
+	ev(other, fixed=True); ev(other, fixed=True)
+	assert len(calls) == 8 and not fp.reference_reused
+	assert advance3d.LatticeGenerator.fixed_points is True
